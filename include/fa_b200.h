@@ -1,0 +1,182 @@
+/*
+ * fa_b200.h — C ABI of the B200-native flash-attention engine (libfa_b200.so).
+ *
+ * This is the drop-in boundary for nothingstopsme/tf_flash_attention: every entry
+ * point replaces one member of the reference's C++ launcher template
+ *   cuda_launch::FlashAttentionLauncher<T, RefShape, OrderMap, Policy>
+ *   (reference: flash_attention/kernel/flash_attention.h:220-260)
+ * plus the host helpers the reference's TF OpKernels run before calling it
+ *   (flash_attention/kernel/flash_attention_forward.cc:97-140,280-386 and
+ *    flash_attention/kernel/flash_attention_backward.cc:181-344).
+ * Plain pointers and sizes only; no TensorFlow, PyTorch or CuTe types.
+ *
+ * Tensors are dense, channel-first, row-major, exactly as TensorFlow hands them
+ * to the reference op:   Q [batch, d, q...]  K [batch, d, k...]  V [batch, v_d, k...]
+ *                        O [batch, v_d, q...]  l, m [batch, q...]
+ * with every leading batch axis (heads included) flattened into `batch` and the
+ * 1 or 2 sequence axes flattened row-major (q = prod(q_shape), k = prod(k_shape)).
+ *
+ * All functions are re-entrant and asynchronous with respect to the host: work is
+ * enqueued on `stream` and no host synchronisation happens (like the reference,
+ * flash_attention_forward.cc:371-385). The caller owns every buffer, workspace
+ * included; the library never allocates device memory.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* dtype of Q/K/V/O/m and the gradients. `l` is float for FA_F16 and T otherwise
+ * (reference: flash_attention.h:181-185, flash_attention_forward.cc:151-153,187-189). */
+enum { FA_F16 = 0, FA_F32 = 1, FA_F64 = 2 };
+/* masking rule (reference policies, flash_attention.h:45-149) */
+enum { FA_RULE_FULL = 0, FA_RULE_CAUSAL = 1, FA_RULE_LOCAL = 2 };
+/* sync mode (reference: sync_methods.cc:113-117) */
+enum { FA_SYNC_NONE_FRONT = 0, FA_SYNC_SCALE_FRONT = 1, FA_SYNC_SCALE_END = 2 };
+
+/* status codes; 0 = ok. Each FA_EINVAL_* mirrors one reference check. */
+enum {
+  FA_OK = 0,
+  FA_EINVAL_NULL = -1,         /* null problem / pointer                                   */
+  FA_EINVAL_DTYPE = -2,        /* dtype not in {f16,f32,f64}     (op "T" attr constraint)   */
+  FA_EINVAL_SEQ_DIMS = -3,     /* seq_dims not 1 or 2            (ops exist for 1d/2d only) */
+  FA_EINVAL_RULE = -4,         /* rule not in {full,causal,local}                           */
+  FA_EINVAL_SYNC_MODE = -5,    /* "Unsupported sync_mode: ..."   forward.cc:275-276         */
+  FA_EINVAL_WINDOW = -6,       /* window_size < 1                forward.cc:173 (int >= 1)  */
+  FA_EINVAL_STRIDE = -7,       /* log2_stride_size < 0, >= 31 or window<<stride overflows   */
+                               /*                                flash_attention.h:90       */
+  FA_EINVAL_SHAPE = -8,        /* a dimension < 1, or q/k/orders do not fit int32           */
+  FA_EINVAL_WORKSPACE = -9,    /* workspace smaller than fa_workspace_bytes()               */
+  FA_EINVAL_RANK = -10,        /* fa_check_*_shapes: rank mismatch / rank < seq_dims+2      */
+  FA_EINVAL_CHANNEL = -11,     /* fa_check_*_shapes: channel mismatch                       */
+  FA_EINVAL_BATCH = -12,       /* fa_check_*_shapes: batch shapes differ                    */
+  FA_EINVAL_SEQ_SHAPE = -13,   /* fa_check_*_shapes: sequence shapes differ                 */
+  FA_ECUDA = -100,             /* a CUDA call failed; fa_last_cuda_error() has the code     */
+  FA_ENODEVICE = -101          /* no sm_100 device is current                               */
+};
+
+typedef struct fa_problem_t {
+  int32_t dtype;            /* FA_F16 | FA_F32 | FA_F64                                      */
+  int32_t seq_dims;         /* 1 or 2                                                        */
+  int32_t rule;             /* FA_RULE_*                                                     */
+  int32_t window_size;      /* local only, >= 1; attended span per dim = 2*window-1          */
+  int32_t log2_stride_size; /* local only, 0..30                                             */
+  int32_t is_causal;        /* local only                                                    */
+  int32_t sync_mode;        /* FA_SYNC_*                                                     */
+  int32_t d;                /* channels of Q and K                                           */
+  int32_t v_d;              /* channels of V and O                                           */
+  int32_t reserved0;
+  int64_t batch;            /* product of all batch axes (heads included)                    */
+  int32_t q_shape[2];       /* TF axis order (outer, inner); 1-D uses q_shape[0]             */
+  int32_t k_shape[2];
+  /* K/V-ring support (one long sequence sharded over GPUs): this call sees rows
+   * [q_coord_base, q_coord_base + q_shape) of a longer logical sequence whose full
+   * extent is q_full_shape (same for k). All zeros = not sharded (the reference
+   * has no such notion; the rule is evaluated on global coordinates). 1-D only. */
+  int32_t q_index_base;
+  int32_t k_index_base;
+  int32_t q_full_len;       /* 0 = q_shape[0]                                                */
+  int32_t k_full_len;       /* 0 = k_shape[0]                                                */
+  /* 1 = `o`,`l`,`m` already hold a partial result of the same rows (from earlier
+   * K/V shards) and this call merges into them online; 0 = overwrite.              */
+  int32_t accumulate;
+  int32_t reserved1;
+} fa_problem_t;
+
+/* ---- the hot path ------------------------------------------------------------- */
+
+/* Replaces FlashAttentionLauncher::Forward (flash_attention.h:225-236) together with
+ * the four cudaMemsetAsync calls that precede it (flash_attention_forward.cc:352-369):
+ * every element of o, l, m is written by the kernels themselves.
+ *   o : T  [batch, v_d, q]     l : float (f16) or T  [batch, q]     m : T [batch, q]
+ * Rows with no attended key get o = 0, l = 0, m = bytes 0xFA.. (type_util.h:43-45).
+ * `stream` is a cudaStream_t passed as void*. */
+int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* v,
+               void* o, void* l, void* m, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces FlashAttentionLauncher::Backward (flash_attention.h:238-249) plus its four
+ * memsets (flash_attention_backward.cc:309-323). Inputs o, l, m are the forward outputs.
+ *   d_q : T [batch, d, q]    d_k : T [batch, d, k]    d_v : T [batch, v_d, k]       */
+int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void* v,
+                const void* o, const void* l, const void* m, const void* d_o,
+                void* d_q, void* d_k, void* d_v, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* Device scratch the caller must provide (replaces the reference's allocate_temp of
+ * Br_occupancy, flash_attention_forward.cc:330 / flash_attention_backward.cc:283).
+ * May be 0. */
+size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward);
+
+/* Replaces FlashAttentionLauncher::EstimateForwardFlops (flash_attention.h:254-260,
+ * flash_attention.cu:2069-2144): the reference's per-(Bc,Br)-block-pair estimate for a
+ * device with `shared_mem_bytes` of opt-in shared memory per block (pass 0 to use
+ * B200's 232448). Host only; writes *flops. */
+int fa_estimate_forward_flops(const fa_problem_t* p, int32_t shared_mem_bytes, float* flops);
+
+/* ---- host-side helpers shared with the kernels (same code, fa_rules.h) ---------- */
+
+/* Number of attended (q,k) pairs per batch element under the bit-exact rule; the unit
+ * of the unmasked-FLOP metric: fwd = 2*nnz*(d+v_d)*batch, bwd = 2*nnz*(3d+2v_d)*batch. */
+int fa_count_attended(const fa_problem_t* p, int64_t* nnz);
+
+/* Writes the dense attended-index pattern, mask[q*k] (1 = attended), evaluated by the
+ * very same inline functions the kernels use. For tests / debugging. */
+int fa_pattern_mask(const fa_problem_t* p, uint8_t* mask);
+
+/* Orders of the Q and K entries in the shared power-of-two reference grid
+ * (sync_methods.h:56-85); q_order[q], k_order[k], ref_shape[seq_dims] innermost first. */
+int fa_orders(const fa_problem_t* p, int32_t* q_order, int32_t* k_order, int32_t* ref_shape);
+
+/* Tile schedule the kernels derive for (q tile of `tile_q` rows) x (k tile of `tile_k`):
+ * cls[nq_tiles*nk_tiles] = 0 skip (never loaded), 1 partial (element mask), 2 full. */
+int fa_classify_tiles(const fa_problem_t* p, int32_t tile_q, int32_t tile_k, uint8_t* cls);
+
+/* Shape validation exactly as the reference OpKernels do it, on un-flattened TF shapes.
+ * Fills batch, d, v_d, q_shape, k_shape of *p (other fields untouched).
+ *   forward : flash_attention_forward.cc:97-140      backward: flash_attention_backward.cc:197-258 */
+int fa_check_forward_shapes(int32_t seq_dims, int32_t rank_q, const int64_t* q_dims,
+                            int32_t rank_k, const int64_t* k_dims,
+                            int32_t rank_v, const int64_t* v_dims, fa_problem_t* p);
+int fa_check_backward_shapes(int32_t seq_dims, int32_t rank_q, const int64_t* q_dims,
+                             int32_t rank_k, const int64_t* k_dims,
+                             int32_t rank_v, const int64_t* v_dims,
+                             int32_t rank_o, const int64_t* o_dims,
+                             int32_t rank_l, const int64_t* l_dims,
+                             int32_t rank_m, const int64_t* m_dims,
+                             int32_t rank_do, const int64_t* do_dims, fa_problem_t* p);
+
+/* ---- the reference-facing plugin call with HOST buffers -------------------------- */
+
+/* Same contract as fa_forward / fa_backward but every tensor pointer is HOST memory
+ * (pinned or pageable). The library stages through the caller-provided device arena
+ * `dev_arena` (>= fa_host_arena_bytes), copies in, runs, copies the results back and
+ * returns after the stream has drained. Used for the end-to-end number in bench.py. */
+size_t fa_host_arena_bytes(const fa_problem_t* p, int is_backward);
+int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const void* v,
+                    void* o, void* l, void* m, void* dev_arena, size_t dev_arena_bytes, void* stream);
+int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v,
+                     const void* o, const void* l, const void* m, const void* d_o,
+                     void* d_q, void* d_k, void* d_v, void* dev_arena, size_t dev_arena_bytes,
+                     void* stream);
+
+/* ---- diagnostics ---------------------------------------------------------------- */
+const char* fa_strerror(int status);
+int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on this thread */
+/* Which kernel family the last fa_forward/fa_backward on this thread dispatched to:
+ * 0 none, 1 generic SIMT, 2 tcgen05 f16, 3 3xTF32 tcgen05, 4 DMMA f64.               */
+int fa_last_path(void);
+/* Number of kernel launches issued by this library on this thread since the last reset. */
+int64_t fa_launch_count(int reset);
+/* Force a kernel family (testing): 0 auto, 1 generic only.                             */
+void fa_set_path_override(int path);
+const char* fa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */

@@ -1,0 +1,168 @@
+"""CPU-side checks of the C-ABI library (no compute calls without a GPU): it loads, exports every
+symbol include/fa_b200.h declares, evaluates the attended pattern bit-exactly (same inline code
+the kernels use), validates shapes like the reference OpKernels, and its tile schedule is
+conservative."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pattern
+from tests.helpers import case_id, load_pattern_golden
+from tf_flash_attention_b200 import _capi
+from tf_flash_attention_b200 import flash_attention as fa
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+CASES = load_pattern_golden()
+
+
+def _problem(c, dtype=0, batch=(2, 3), d=8, v_d=5):
+    qs, ks = tuple(c["q_shape"]), tuple(c["k_shape"])
+    return _capi.make_problem(dtype, c["dims"], c["rule"], c["sync_mode"], batch + (d,) + qs,
+                              batch + (d,) + ks, batch + (v_d,) + ks, c["window_size"],
+                              c["log2_stride_size"], c["is_causal"])
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fa_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = C.CDLL(_capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/fa_b200.h but not exported"
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in _capi.lib.fa_version()
+
+
+@pytest.mark.parametrize("c", CASES, ids=case_id)
+def test_pattern_bit_exact_vs_reference(c):
+    p = _problem(c)
+    assert np.array_equal(_capi.pattern_mask(p), c["mask"])
+    ref, qo, ko = _capi.orders(p)
+    assert ref == c["ref_shape"]
+    assert qo.tolist() == c["q_order"] and ko.tolist() == c["k_order"]
+    assert _capi.count_attended(p) == c["nnz"]
+
+
+@pytest.mark.parametrize("tile", [(4, 4), (8, 16), (3, 5), (64, 64), (128, 128)])
+def test_tile_schedule_is_conservative(tile):
+    tq, tk = tile
+    for c in CASES:
+        cls = _capi.classify_tiles(_problem(c), tq, tk)
+        m = c["mask"]
+        for a in range(cls.shape[0]):
+            for b in range(cls.shape[1]):
+                blk = m[a * tq:(a + 1) * tq, b * tk:(b + 1) * tk]
+                if cls[a, b] == 0:
+                    assert not blk.any(), (case_id(c), a, b)
+                elif cls[a, b] == 2:
+                    assert blk.all(), (case_id(c), a, b)
+                else:
+                    assert cls[a, b] == 1
+
+
+def test_tile_schedule_prunes_baseline_configs():
+    # C3: 150 of the 1024 128x128 tiles are live
+    p = _capi.make_problem(0, 2, "local", "none_front", (1, 64, 64, 64), (1, 64, 64, 64), (1, 64, 64, 64), 8, 0, True)
+    cls = _capi.classify_tiles(p, 128, 128)
+    m = pattern.tests_mask((64, 64), (64, 64), "none_front", "local", 8, 0, True)
+    live = sum(bool(m[a * 128:(a + 1) * 128, b * 128:(b + 1) * 128].any()) for a in range(32) for b in range(32))
+    assert live == 150
+    assert int((cls != 0).sum()) <= 160  # the conservative schedule keeps at most a few empty tiles
+    # C2: causal 8192 -> lower triangle of 64x64 tiles, diagonal partial, rest full
+    p = _capi.make_problem(0, 1, "causal", "none_front", (1, 128, 8192), (1, 128, 8192), (1, 128, 8192))
+    cls = _capi.classify_tiles(p, 128, 128)
+    assert np.array_equal(cls, np.tril(np.full((64, 64), 2), -1) + np.eye(64, dtype=int))
+    assert _capi.count_attended(p) == 8192 * 8193 // 2
+
+
+def test_count_attended_full_size():
+    # C1 README example
+    p = _capi.make_problem(1, 1, "local", "scale_front", (8, 32, 1024), (8, 32, 2048), (8, 16, 2048), 32, 0, False)
+    assert _capi.count_attended(p) == 64016
+    # C4 cross attention, scale_end
+    p = _capi.make_problem(0, 1, "full", "scale_end", (4, 64, 1024), (4, 64, 8192), (4, 64, 8192))
+    assert _capi.count_attended(p) == 1024 * 8192
+
+
+def test_shape_validation_mirrors_reference():
+    E = _capi.InvalidArgumentError
+    ok = _capi.make_problem(0, 1, "full", "none_front", (2, 3, 8, 10), (2, 3, 8, 12), (2, 3, 5, 12))
+    assert (ok.batch, ok.d, ok.v_d, ok.q_shape[0], ok.k_shape[0]) == (6, 8, 5, 10, 12)
+    with pytest.raises(E) as e:  # ranks differ (forward.cc:100-101)
+        _capi.make_problem(0, 1, "full", "none_front", (2, 8, 10), (2, 3, 8, 12), (2, 3, 5, 12))
+    assert e.value.status == _capi.FA_EINVAL_RANK
+    with pytest.raises(E) as e:  # rank < seq_dims + 2 (forward.cc:103-104)
+        _capi.make_problem(0, 2, "full", "none_front", (8, 4, 4), (8, 4, 4), (8, 4, 4))
+    assert e.value.status == _capi.FA_EINVAL_RANK
+    with pytest.raises(E) as e:  # Q/K channels (forward.cc:126-127)
+        _capi.make_problem(0, 1, "full", "none_front", (2, 8, 10), (2, 9, 12), (2, 5, 12))
+    assert e.value.status == _capi.FA_EINVAL_CHANNEL
+    with pytest.raises(E) as e:  # batch shapes (forward.cc:129-130)
+        _capi.make_problem(0, 1, "full", "none_front", (2, 8, 10), (3, 8, 12), (2, 5, 12))
+    assert e.value.status == _capi.FA_EINVAL_BATCH
+    with pytest.raises(E) as e:  # K/V sequence shapes (forward.cc:132-133)
+        _capi.make_problem(0, 1, "full", "none_front", (2, 8, 10), (2, 8, 12), (2, 5, 13))
+    assert e.value.status == _capi.FA_EINVAL_SEQ_SHAPE
+    with pytest.raises(E) as e:  # forward.cc:275-276
+        _capi.make_problem(0, 1, "full", "scale_middle", (2, 8, 10), (2, 8, 12), (2, 5, 12))
+    assert e.value.status == _capi.FA_EINVAL_SYNC_MODE and "Unsupported sync_mode: scale_middle" in str(e.value)
+    # rule attributes are validated when the rule is compiled
+    p = _capi.make_problem(0, 1, "local", "none_front", (2, 8, 10), (2, 8, 12), (2, 5, 12), 0, 0, False)
+    n = C.c_int64()
+    assert _capi.lib.fa_count_attended(C.byref(p), C.byref(n)) == _capi.FA_EINVAL_WINDOW
+    p = _capi.make_problem(0, 1, "local", "none_front", (2, 8, 10), (2, 8, 12), (2, 5, 12), 4, 31, False)
+    assert _capi.lib.fa_count_attended(C.byref(p), C.byref(n)) == _capi.FA_EINVAL_STRIDE
+    p = _capi.make_problem(0, 1, "local", "none_front", (2, 8, 10), (2, 8, 12), (2, 5, 12), 1 << 20, 12, False)
+    assert _capi.lib.fa_count_attended(C.byref(p), C.byref(n)) == _capi.FA_EINVAL_STRIDE
+
+
+def test_backward_shape_validation():
+    E = _capi.InvalidArgumentError
+    p = _capi.make_problem(0, 1, "full", "none_front", (2, 8, 10), (2, 8, 12), (2, 5, 12))
+    good = [(2, 8, 10), (2, 8, 12), (2, 5, 12), (2, 5, 10), (2, 10), (2, 10), (2, 5, 10)]
+    _capi.check_backward_shapes(p, good)
+    bad = list(good); bad[4] = (2, 1, 10)       # l rank (backward.cc:201-203)
+    with pytest.raises(E) as e:
+        _capi.check_backward_shapes(p, bad)
+    assert e.value.status == _capi.FA_EINVAL_RANK
+    bad = list(good); bad[3] = (2, 6, 10)       # V/O channels (backward.cc:245-246)
+    with pytest.raises(E) as e:
+        _capi.check_backward_shapes(p, bad)
+    assert e.value.status == _capi.FA_EINVAL_CHANNEL
+    bad = list(good); bad[6] = (2, 5, 11)       # sequence shape of dO (backward.cc:257-258)
+    with pytest.raises(E) as e:
+        _capi.check_backward_shapes(p, bad)
+    assert e.value.status == _capi.FA_EINVAL_SEQ_SHAPE
+    bad = list(good); bad[5] = (3, 10)          # batch of m (backward.cc:249-252)
+    with pytest.raises(E) as e:
+        _capi.check_backward_shapes(p, bad)
+    assert e.value.status == _capi.FA_EINVAL_BATCH
+
+
+def test_python_api_surface_matches_reference():
+    import inspect
+    sig = {n: list(inspect.signature(getattr(fa, n)).parameters) for n in
+           ("full_1d", "causal_1d", "local_1d", "full_2d", "causal_2d", "local_2d")}
+    assert sig["full_1d"] == sig["full_2d"] == ["Q", "K", "V", "sync_mode", "returning_l_m"]
+    assert sig["causal_1d"] == sig["causal_2d"] == ["Q", "K", "V", "sync_mode", "returning_l_m"]
+    assert sig["local_1d"] == sig["local_2d"] == ["Q", "K", "V", "window_size", "log2_stride_size", "is_causal",
+                                                  "sync_mode", "returning_l_m"]
+    assert inspect.signature(fa.full_1d).parameters["sync_mode"].default == "none_front"
+    assert inspect.signature(fa.causal_1d).parameters["sync_mode"].default is inspect.Parameter.empty
+
+
+def test_no_cpu_fallback():
+    """numpy (host) inputs must fail loudly when no CUDA device is present."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    x = np.zeros((1, 8, 16), dtype=np.float32)
+    with pytest.raises(_capi.FlashAttentionError):
+        fa.full_1d(x, x, x)

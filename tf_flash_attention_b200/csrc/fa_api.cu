@@ -1,0 +1,493 @@
+// fa_api.cu — the C ABI (include/fa_b200.h): validation, dispatch, host helpers.
+// No TensorFlow / PyTorch / CuTe types cross this boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/fa_b200.h"
+#include "fa_launch.h"
+
+namespace fa {
+static thread_local int64_t g_launches = 0;
+static thread_local int g_last_cuda = 0;
+static thread_local int g_last_path = 0;
+static int g_path_override = 0;
+void count_launch() { ++g_launches; }
+}  // namespace fa
+
+namespace {
+
+int make_rule(const fa_problem_t* p, FaRule* r) {
+  if (!p) return FA_EINVAL_NULL;
+  if (p->dtype < 0 || p->dtype > 2) return FA_EINVAL_DTYPE;
+  if (p->seq_dims != 1 && p->seq_dims != 2) return FA_EINVAL_SEQ_DIMS;
+  if (p->d < 1 || p->v_d < 1 || p->batch < 0) return FA_EINVAL_SHAPE;
+  return fa_make_rule(p->seq_dims, p->rule, p->window_size, p->log2_stride_size, p->is_causal,
+                      p->sync_mode, p->q_shape, p->k_shape, p->q_index_base, p->k_index_base,
+                      p->q_full_len, p->k_full_len, r);
+}
+
+size_t elt(int dtype) { return dtype == FA_F16 ? 2 : dtype == FA_F32 ? 4 : 8; }
+size_t l_elt(int dtype) { return dtype == FA_F64 ? 8 : 4; }
+
+int cuda_fail(cudaError_t e) {
+  fa::g_last_cuda = int(e);
+  return FA_ECUDA;
+}
+
+int fill_args(const fa_problem_t* p, fa::LaunchArgs* a) {
+  int rc = make_rule(p, &a->rule);
+  if (rc) return rc;
+  a->dtype = p->dtype;
+  a->d = p->d;
+  a->v_d = p->v_d;
+  a->batch = p->batch;
+  a->accumulate = p->accumulate;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fa_version(void) { return "tf_flash_attention_b200 0.1 (sm_100a)"; }
+
+const char* fa_strerror(int s) {
+  switch (s) {
+    case FA_OK: return "ok";
+    case FA_EINVAL_NULL: return "null argument";
+    case FA_EINVAL_DTYPE: return "unsupported dtype (expected float16, float32 or float64)";
+    case FA_EINVAL_SEQ_DIMS: return "sequence dims must be 1 or 2";
+    case FA_EINVAL_RULE: return "unknown masking rule";
+    case FA_EINVAL_SYNC_MODE: return "Unsupported sync_mode";
+    case FA_EINVAL_WINDOW: return "window_size must be >= 1";
+    case FA_EINVAL_STRIDE:
+      return "stride size is too big; please make sure the stride size/window size is within the range "
+             "representable by int32_t";
+    case FA_EINVAL_SHAPE: return "invalid or unsupported shape";
+    case FA_EINVAL_WORKSPACE: return "workspace too small";
+    case FA_EINVAL_RANK: return "The number of dimensions of the inputs is inconsistent or too small";
+    case FA_EINVAL_CHANNEL: return "The channel dimensions should be equal";
+    case FA_EINVAL_BATCH: return "The batch shape of all inputs should be equal";
+    case FA_EINVAL_SEQ_SHAPE: return "The sequence shapes are inconsistent";
+    case FA_ECUDA: return "CUDA error (see fa_last_cuda_error)";
+    case FA_ENODEVICE: return "no sm_100 CUDA device is current";
+    default: return "unknown status";
+  }
+}
+
+int fa_last_cuda_error(void) { return fa::g_last_cuda; }
+int fa_last_path(void) { return fa::g_last_path; }
+int64_t fa_launch_count(int reset) {
+  int64_t v = fa::g_launches;
+  if (reset) fa::g_launches = 0;
+  return v;
+}
+void fa_set_path_override(int path) { fa::g_path_override = path; }
+
+size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
+  fa::LaunchArgs a{};
+  if (fill_args(p, &a)) return 0;
+  size_t g = fa::generic_workspace_bytes(p->dtype, p->batch, a.rule.q.total, is_backward != 0);
+  size_t s = 0;
+  if (p->dtype == FA_F16) s = fa::sm100_f16_workspace_bytes(a, is_backward != 0);
+  return g > s ? g : s;
+}
+
+int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* v, void* o, void* l,
+               void* m, void* workspace, size_t workspace_bytes, void* stream) {
+  fa::LaunchArgs a{};
+  int rc = fill_args(p, &a);
+  if (rc) return rc;
+  if (p->batch == 0) return FA_OK;
+  if (!q || !k || !v || !o || !l || !m) return FA_EINVAL_NULL;
+  if (workspace_bytes < fa_workspace_bytes(p, 0)) return FA_EINVAL_WORKSPACE;
+  a.q = q; a.k = k; a.v = v; a.o = o; a.l = l; a.m = m;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_forward_supports(a)) {
+    fa::g_last_path = 2;
+    e = fa::sm100_f16_forward(a, st);
+  } else {
+    if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
+    fa::g_last_path = 1;
+    e = fa::generic_forward(a, st);
+  }
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
+int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  fa::LaunchArgs a{};
+  int rc = fill_args(p, &a);
+  if (rc) return rc;
+  if (p->batch == 0) return FA_OK;
+  if (!q || !k || !v || !o || !l || !m || !d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
+  if (workspace_bytes < fa_workspace_bytes(p, 1) || (!workspace && fa_workspace_bytes(p, 1)))
+    return FA_EINVAL_WORKSPACE;
+  a.q = q; a.k = k; a.v = v; a.o = (void*)o; a.l = (void*)l; a.m = (void*)m; a.d_o = d_o;
+  a.d_q = d_q; a.d_k = d_k; a.d_v = d_v;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_backward_supports(a)) {
+    fa::g_last_path = 2;
+    e = fa::sm100_f16_backward(a, st);
+  } else {
+    if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
+    fa::g_last_path = 1;
+    e = fa::generic_backward(a, st);
+  }
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
+// ---- host helpers on the shared rule code ---------------------------------------------------
+
+int fa_count_attended(const fa_problem_t* p, int64_t* nnz) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (!nnz) return FA_EINVAL_NULL;
+  int64_t total = 0;
+  if (r.rule == 0) {
+    total = int64_t(r.q.total) * r.k.total;
+  } else {
+    // per-row: walk only the K tiles the schedule keeps, count FULL tiles wholesale
+    const int TK = 128;
+    std::vector<FaPos> kpos(r.k.total);
+    for (int32_t j = 0; j < r.k.total; ++j) kpos[j] = fa_pos(r, r.k, j);
+    for (int32_t i = 0; i < r.q.total; ++i) {
+      FaPos qp = fa_pos(r, r.q, i);
+      int32_t f, l;
+      fa_k_tile_range(r, i, i, TK, &f, &l);
+      for (int32_t t = f; t <= l; ++t) {
+        int32_t k0 = t * TK, k1 = std::min(k0 + TK, r.k.total) - 1;
+        int cls = fa_classify(r, i, i, k0, k1);
+        if (cls == FA_TILE_SKIP) continue;
+        if (cls == FA_TILE_FULL) {
+          total += k1 - k0 + 1;
+          continue;
+        }
+        for (int32_t j = k0; j <= k1; ++j) total += fa_attend(r, qp, kpos[j]) ? 1 : 0;
+      }
+    }
+  }
+  *nnz = total;
+  return FA_OK;
+}
+
+int fa_pattern_mask(const fa_problem_t* p, uint8_t* mask) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (!mask) return FA_EINVAL_NULL;
+  std::vector<FaPos> kpos(r.k.total);
+  for (int32_t j = 0; j < r.k.total; ++j) kpos[j] = fa_pos(r, r.k, j);
+  for (int32_t i = 0; i < r.q.total; ++i) {
+    FaPos qp = fa_pos(r, r.q, i);
+    uint8_t* row = mask + int64_t(i) * r.k.total;
+    for (int32_t j = 0; j < r.k.total; ++j) row[j] = fa_attend(r, qp, kpos[j]) ? 1 : 0;
+  }
+  return FA_OK;
+}
+
+int fa_orders(const fa_problem_t* p, int32_t* q_order, int32_t* k_order, int32_t* ref_shape) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (q_order)
+    for (int32_t i = 0; i < r.q.total; ++i) q_order[i] = fa_pos(r, r.q, i).order;
+  if (k_order)
+    for (int32_t j = 0; j < r.k.total; ++j) k_order[j] = fa_pos(r, r.k, j).order;
+  if (ref_shape) {
+    ref_shape[0] = r.ref0;
+    if (r.dims == 2) ref_shape[1] = r.ref1;
+  }
+  return FA_OK;
+}
+
+int fa_classify_tiles(const fa_problem_t* p, int32_t tile_q, int32_t tile_k, uint8_t* cls) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (!cls || tile_q < 1 || tile_k < 1) return FA_EINVAL_NULL;
+  const int32_t nqt = (r.q.total + tile_q - 1) / tile_q, nkt = (r.k.total + tile_k - 1) / tile_k;
+  for (int32_t a = 0; a < nqt; ++a) {
+    int32_t q0 = a * tile_q, q1 = std::min(q0 + tile_q, r.q.total) - 1;
+    int32_t f, l;
+    fa_k_tile_range(r, q0, q1, tile_k, &f, &l);
+    for (int32_t b = 0; b < nkt; ++b) {
+      int32_t k0 = b * tile_k, k1 = std::min(k0 + tile_k, r.k.total) - 1;
+      int c = (b < f || b > l) ? FA_TILE_SKIP : fa_classify(r, q0, q1, k0, k1);
+      // the dK/dV kernels walk the transposed range; a tile either range drops is reported as
+      // SKIP so that the tests can verify both ranges only ever drop empty tiles
+      int32_t qf, ql;
+      fa_q_tile_range(r, k0, k1, tile_q, &qf, &ql);
+      if (a < qf || a > ql) c = FA_TILE_SKIP;
+      cls[int64_t(a) * nkt + b] = uint8_t(c);
+    }
+  }
+  return FA_OK;
+}
+
+// ---- the reference's FLOPs estimate ---------------------------------------------------------
+// Restates FlashAttentionLauncher::EstimateForwardFlops (flash_attention.cu:2069-2144) with the
+// reference's own tile configuration (flash_attention.cu:1977-2012, flash_attention.h:187-204) and
+// its own IsSkipped predicates (flash_attention.h:48-115), including their quirks, so that the
+// number TF's profiler shows stays comparable. Note the reference does not multiply by batch.
+namespace {
+struct RefCoords { int32_t c[2]; };
+inline int32_t ilog2(int32_t n) { int32_t l = 0; while ((int64_t(1) << (l + 1)) <= n) ++l; return l; }
+RefCoords ref_coords(const FaRule& r, int32_t order) {
+  RefCoords o;
+  o.c[0] = order & (r.ref0 - 1);
+  o.c[1] = r.dims == 2 ? (order >> r.ref_log2_0) & (r.ref1 - 1) : 0;
+  return o;
+}
+int32_t ref_order(const FaRule& r, const RefCoords& c) {
+  return c.c[0] + (r.dims == 2 ? (c.c[1] << r.ref_log2_0) : 0);
+}
+bool ref_is_skipped(const FaRule& r, int32_t minQ, int32_t maxQ, int32_t minK, int32_t maxK) {
+  if (r.rule == 0) return false;
+  if (r.rule == 1) return maxQ < minK;
+  const int32_t sw = r.window << r.log2_stride;
+  const int32_t look = r.causal ? 1 : sw;
+  RefCoords a = ref_coords(r, minQ), b = ref_coords(r, maxQ), lo, hi;
+  const int32_t lim[2] = {r.ref0, r.ref1};
+  for (int i = 0; i < 2; ++i) {
+    lo.c[i] = std::max(a.c[i] - sw + 1, 0);
+    hi.c[i] = std::min(b.c[i] + look, lim[i]) - 1;
+  }
+  return maxK < ref_order(r, lo) || minK > ref_order(r, hi);
+}
+}  // namespace
+
+int fa_estimate_forward_flops(const fa_problem_t* p, int32_t shared_mem_bytes, float* flops) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (!flops) return FA_EINVAL_NULL;
+  const int32_t smem = shared_mem_bytes > 0 ? shared_mem_bytes : 232448;
+  const int32_t sz = int32_t(elt(p->dtype));
+  const int32_t Br = std::max(32, 128 / sz);
+  const int32_t pad = sz == 2 ? 2 : 1;
+  const int32_t d = p->d, v_d = p->v_d, q = r.q.total, k = r.k.total;
+  const int32_t Bc = (smem - Br * (1 + 1 + d) * sz) / ((d + v_d + (Br + pad)) * sz);
+  if (Bc <= 0) return FA_EINVAL_SHAPE;
+  const int32_t nBr = (q + Br - 1) / Br, nBc = (k + Bc - 1) / Bc;
+  const int32_t per_pair = Br * Bc * (2 * d - 1) + (Br * (Bc - 1) * 2 + Br * Bc * 2) + Br * 7 +
+                           Br * (Bc + v_d) + Br * v_d * (2 * Bc - 1);
+  const int32_t max_order = r.ref0 * r.ref1 - 1;
+  float f = 0.0f;
+  for (int32_t bc = 0; bc < nBc; ++bc) {
+    const int32_t minK = fa_pos(r, r.k, bc * Bc).order;
+    const int32_t maxK = std::min(fa_pos(r, r.k, (bc + 1) * Bc - 1).order, max_order);
+    for (int32_t br = 0; br < nBr; ++br) {
+      const int32_t minQ = fa_pos(r, r.q, br * Br).order;
+      const int32_t maxQ = std::min(fa_pos(r, r.q, (br + 1) * Br - 1).order, max_order);
+      if (ref_is_skipped(r, minQ, maxQ, minK, maxK)) continue;
+      f += per_pair;
+    }
+  }
+  *flops = f;
+  return FA_OK;
+}
+
+// ---- shape validation as in the reference OpKernels -------------------------------------------
+namespace {
+struct Split { int64_t batch; int64_t ch; int32_t seq[2]; bool seq_ok; std::vector<int64_t> bdims; };
+bool split(int32_t seq_dims, int32_t rank, const int64_t* dims, bool has_channel, Split* s) {
+  const int lead = rank - seq_dims - (has_channel ? 1 : 0);
+  if (lead < 0) return false;
+  s->batch = 1;
+  s->bdims.assign(dims, dims + lead);
+  for (int i = 0; i < lead; ++i) s->batch *= dims[i];
+  s->ch = has_channel ? dims[lead] : 0;
+  s->seq_ok = true;
+  s->seq[0] = s->seq[1] = 1;
+  for (int i = 0; i < seq_dims; ++i) {
+    int64_t v = dims[lead + (has_channel ? 1 : 0) + i];
+    if (v < 1 || v > 0x7fffffffLL) s->seq_ok = false;
+    s->seq[i] = int32_t(v);
+  }
+  return true;
+}
+}  // namespace
+
+int fa_check_forward_shapes(int32_t seq_dims, int32_t rank_q, const int64_t* q_dims, int32_t rank_k,
+                            const int64_t* k_dims, int32_t rank_v, const int64_t* v_dims,
+                            fa_problem_t* p) {
+  if (!p || !q_dims || !k_dims || !v_dims) return FA_EINVAL_NULL;
+  if (seq_dims != 1 && seq_dims != 2) return FA_EINVAL_SEQ_DIMS;
+  // "The number of dimensions of Q, K, and V should be equal" / ">= SequenceDims+2" (forward.cc:100-104)
+  if (rank_q != rank_k || rank_k != rank_v) return FA_EINVAL_RANK;
+  if (rank_q < seq_dims + 2) return FA_EINVAL_RANK;
+  Split Q, K, V;
+  split(seq_dims, rank_q, q_dims, true, &Q);
+  split(seq_dims, rank_k, k_dims, true, &K);
+  split(seq_dims, rank_v, v_dims, true, &V);
+  if (Q.ch != K.ch) return FA_EINVAL_CHANNEL;                                    // forward.cc:126-127
+  if (Q.bdims != K.bdims || Q.bdims != V.bdims) return FA_EINVAL_BATCH;          // forward.cc:129-130
+  if (K.seq[0] != V.seq[0] || K.seq[1] != V.seq[1]) return FA_EINVAL_SEQ_SHAPE;  // forward.cc:132-133
+  if (!Q.seq_ok || !K.seq_ok || Q.ch < 1 || V.ch < 1 || Q.ch > 0x7fffffffLL || V.ch > 0x7fffffffLL)
+    return FA_EINVAL_SHAPE;
+  p->seq_dims = seq_dims;
+  p->batch = Q.batch;
+  p->d = int32_t(Q.ch);
+  p->v_d = int32_t(V.ch);
+  for (int i = 0; i < 2; ++i) {
+    p->q_shape[i] = i < seq_dims ? Q.seq[i] : 0;
+    p->k_shape[i] = i < seq_dims ? K.seq[i] : 0;
+  }
+  return FA_OK;
+}
+
+int fa_check_backward_shapes(int32_t seq_dims, int32_t rank_q, const int64_t* q_dims, int32_t rank_k,
+                             const int64_t* k_dims, int32_t rank_v, const int64_t* v_dims,
+                             int32_t rank_o, const int64_t* o_dims, int32_t rank_l,
+                             const int64_t* l_dims, int32_t rank_m, const int64_t* m_dims,
+                             int32_t rank_do, const int64_t* do_dims, fa_problem_t* p) {
+  if (!p || !q_dims || !k_dims || !v_dims || !o_dims || !l_dims || !m_dims || !do_dims)
+    return FA_EINVAL_NULL;
+  if (seq_dims != 1 && seq_dims != 2) return FA_EINVAL_SEQ_DIMS;
+  // backward.cc:197-208
+  if (!(rank_q == rank_k && rank_k == rank_v && rank_v == rank_o && rank_o == rank_do)) return FA_EINVAL_RANK;
+  if (!(rank_l == rank_m && rank_m == rank_q - 1)) return FA_EINVAL_RANK;
+  if (rank_q < seq_dims + 2) return FA_EINVAL_RANK;
+  Split Q, K, V, O, L, M, DO;
+  split(seq_dims, rank_q, q_dims, true, &Q);
+  split(seq_dims, rank_k, k_dims, true, &K);
+  split(seq_dims, rank_v, v_dims, true, &V);
+  split(seq_dims, rank_o, o_dims, true, &O);
+  split(seq_dims, rank_l, l_dims, false, &L);
+  split(seq_dims, rank_m, m_dims, false, &M);
+  split(seq_dims, rank_do, do_dims, true, &DO);
+  if (Q.ch != K.ch) return FA_EINVAL_CHANNEL;  // backward.cc:243-244
+  if (V.ch != O.ch) return FA_EINVAL_CHANNEL;  // backward.cc:245-246
+  if (!(Q.bdims == K.bdims && Q.bdims == V.bdims && V.bdims == O.bdims && O.bdims == L.bdims &&
+        L.bdims == M.bdims && M.bdims == DO.bdims))
+    return FA_EINVAL_BATCH;  // backward.cc:249-252
+  auto same = [](const Split& a, const Split& b) { return a.seq[0] == b.seq[0] && a.seq[1] == b.seq[1]; };
+  if (!same(K, V)) return FA_EINVAL_SEQ_SHAPE;  // backward.cc:254-255
+  if (!(same(Q, O) && same(O, L) && same(L, M) && same(M, DO))) return FA_EINVAL_SEQ_SHAPE;  // :257-258
+  // the reference never checks dO's channel count against V's; a mismatch would read out of
+  // bounds there, so it is rejected here.
+  if (DO.ch != V.ch) return FA_EINVAL_CHANNEL;
+  if (!Q.seq_ok || !K.seq_ok || Q.ch < 1 || V.ch < 1 || Q.ch > 0x7fffffffLL || V.ch > 0x7fffffffLL)
+    return FA_EINVAL_SHAPE;
+  p->seq_dims = seq_dims;
+  p->batch = Q.batch;
+  p->d = int32_t(Q.ch);
+  p->v_d = int32_t(V.ch);
+  for (int i = 0; i < 2; ++i) {
+    p->q_shape[i] = i < seq_dims ? Q.seq[i] : 0;
+    p->k_shape[i] = i < seq_dims ? K.seq[i] : 0;
+  }
+  return FA_OK;
+}
+
+// ---- host-buffer entry points (the e2e path) ----------------------------------------------------
+namespace {
+size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+struct Arena {
+  size_t q, k, v, o, l, m, d_o, d_q, d_k, d_v, ws, total;
+  size_t nq_b, nk_b, nv_b, no_b, nl_b, nm_b;
+};
+int arena_layout(const fa_problem_t* p, int bwd, Arena* a) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  const size_t e = elt(p->dtype), b = size_t(p->batch);
+  a->nq_b = e * b * p->d * r.q.total;
+  a->nk_b = e * b * p->d * r.k.total;
+  a->nv_b = e * b * p->v_d * r.k.total;
+  a->no_b = e * b * p->v_d * r.q.total;
+  a->nl_b = l_elt(p->dtype) * b * r.q.total;
+  a->nm_b = e * b * r.q.total;
+  size_t off = 0;
+  auto take = [&off](size_t n) { size_t o = off; off += align_up(n); return o; };
+  a->q = take(a->nq_b); a->k = take(a->nk_b); a->v = take(a->nv_b);
+  a->o = take(a->no_b); a->l = take(a->nl_b); a->m = take(a->nm_b);
+  if (bwd) {
+    a->d_o = take(a->no_b); a->d_q = take(a->nq_b); a->d_k = take(a->nk_b); a->d_v = take(a->nv_b);
+  }
+  a->ws = off;
+  off += align_up(fa_workspace_bytes(p, bwd));
+  a->total = off;
+  return 0;
+}
+}  // namespace
+
+size_t fa_host_arena_bytes(const fa_problem_t* p, int is_backward) {
+  Arena a;
+  if (arena_layout(p, is_backward, &a)) return 0;
+  return a.total;
+}
+
+#define FA_CU(x)                                   \
+  do {                                             \
+    cudaError_t e_ = (x);                          \
+    if (e_ != cudaSuccess) return cuda_fail(e_);   \
+  } while (0)
+
+int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, void* o, void* l,
+                    void* m, void* dev_arena, size_t dev_arena_bytes, void* stream) {
+  Arena a;
+  int rc = arena_layout(p, 0, &a);
+  if (rc) return rc;
+  if (!dev_arena || dev_arena_bytes < a.total) return FA_EINVAL_WORKSPACE;
+  if (!q || !k || !v || !o || !l || !m) return FA_EINVAL_NULL;
+  char* base = (char*)dev_arena;
+  cudaStream_t st = (cudaStream_t)stream;
+  FA_CU(cudaMemcpyAsync(base + a.q, q, a.nq_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.k, k, a.nk_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.v, v, a.nv_b, cudaMemcpyHostToDevice, st));
+  if (p->accumulate) {
+    FA_CU(cudaMemcpyAsync(base + a.o, o, a.no_b, cudaMemcpyHostToDevice, st));
+    FA_CU(cudaMemcpyAsync(base + a.l, l, a.nl_b, cudaMemcpyHostToDevice, st));
+    FA_CU(cudaMemcpyAsync(base + a.m, m, a.nm_b, cudaMemcpyHostToDevice, st));
+  }
+  rc = fa_forward(p, base + a.q, base + a.k, base + a.v, base + a.o, base + a.l, base + a.m,
+                  base + a.ws, a.total - a.ws, stream);
+  if (rc) return rc;
+  FA_CU(cudaMemcpyAsync(o, base + a.o, a.no_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaMemcpyAsync(l, base + a.l, a.nl_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaMemcpyAsync(m, base + a.m, a.nm_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaStreamSynchronize(st));
+  return FA_OK;
+}
+
+int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                     const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
+                     void* dev_arena, size_t dev_arena_bytes, void* stream) {
+  Arena a;
+  int rc = arena_layout(p, 1, &a);
+  if (rc) return rc;
+  if (!dev_arena || dev_arena_bytes < a.total) return FA_EINVAL_WORKSPACE;
+  if (!q || !k || !v || !o || !l || !m || !d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
+  char* base = (char*)dev_arena;
+  cudaStream_t st = (cudaStream_t)stream;
+  FA_CU(cudaMemcpyAsync(base + a.q, q, a.nq_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.k, k, a.nk_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.v, v, a.nv_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.o, o, a.no_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.l, l, a.nl_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.m, m, a.nm_b, cudaMemcpyHostToDevice, st));
+  FA_CU(cudaMemcpyAsync(base + a.d_o, d_o, a.no_b, cudaMemcpyHostToDevice, st));
+  rc = fa_backward(p, base + a.q, base + a.k, base + a.v, base + a.o, base + a.l, base + a.m,
+                   base + a.d_o, base + a.d_q, base + a.d_k, base + a.d_v, base + a.ws,
+                   a.total - a.ws, stream);
+  if (rc) return rc;
+  FA_CU(cudaMemcpyAsync(d_q, base + a.d_q, a.nq_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaMemcpyAsync(d_k, base + a.d_k, a.nk_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaMemcpyAsync(d_v, base + a.d_v, a.nv_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaStreamSynchronize(st));
+  return FA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// fa_launch.h — internal contract between the C-ABI front (fa_api.cu) and the kernel
+// families. Not installed; the public surface is include/fa_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "fa_rules.h"
+
+namespace fa {
+
+struct LaunchArgs {
+  int32_t dtype;  // 0 f16, 1 f32, 2 f64
+  int32_t d, v_d;
+  int64_t batch;
+  int32_t accumulate;
+  FaRule rule;
+  const void *q, *k, *v;
+  void *o, *l, *m;                // forward outputs / backward inputs
+  const void* d_o;
+  void *d_q, *d_k, *d_v;
+  void* workspace;
+  size_t workspace_bytes;
+};
+
+void count_launch();
+
+// generic SIMT family (fa_generic.cu)
+bool generic_supports(const LaunchArgs& a);
+size_t generic_workspace_bytes(int dtype, int64_t batch, int64_t nq, bool backward);
+cudaError_t generic_forward(const LaunchArgs& a, cudaStream_t stream);
+cudaError_t generic_backward(const LaunchArgs& a, cudaStream_t stream);
+
+// tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
+bool sm100_f16_forward_supports(const LaunchArgs& a);
+bool sm100_f16_backward_supports(const LaunchArgs& a);
+size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward);
+cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream);
+cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream);
+
+}  // namespace fa

@@ -1,0 +1,302 @@
+// fa_rules.h — the reference's sync modes and masking rules as one small POD that
+// host code and every kernel evaluate with the SAME inline functions.
+//
+// Behaviour restated from the reference (nothing copied; CuTe is not used):
+//   sync modes  -> per-dim (stride, offset) + power-of-two reference grid
+//                  flash_attention/kernel/sync_methods.cc:8-111
+//   order map   -> order = sum_i (off_i + c_i*stride_i) * prod_{e<i} ref_e
+//                  flash_attention/kernel/sync_methods.h:56-85
+//   rules       -> Full / Causal / Local Check()   flash_attention/kernel/flash_attention.h:45-140
+//   padding     -> q < size && k < size            flash_attention/kernel/flash_attention.cu:927
+// The tile classifier (skip / partial / full) is new: it is conservative by
+// construction (interval arithmetic on coordinates), unlike the reference's
+// LocalAttentionPolicy::IsSkipped bounding box (flash_attention.h:98-115), which can
+// under-cover when a Q tile wraps a 2-D row.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FA_HD __host__ __device__ __forceinline__
+#else
+#define FA_HD inline
+#endif
+
+enum { FA_TILE_SKIP = 0, FA_TILE_PARTIAL = 1, FA_TILE_FULL = 2 };
+
+struct FaSeqMap {
+  int32_t n0;       // innermost extent (TF last axis); 1-D: local length of this call
+  int32_t n1;       // outer extent (1 for 1-D)
+  int32_t stride0, stride1;
+  int32_t off0, off1;
+  int32_t base0;    // ring: global index of local element 0 (1-D only)
+  int32_t total;    // number of local elements = n0*n1
+};
+
+struct FaRule {
+  int32_t dims;         // 1 or 2
+  int32_t rule;         // 0 full, 1 causal, 2 local
+  int32_t window;       // local
+  int32_t log2_stride;  // local
+  int32_t causal;       // causal rule, or local with is_causal
+  int32_t ref_log2_0;   // log2 of the innermost reference extent
+  int32_t ref0, ref1;   // reference grid extents (powers of two)
+  FaSeqMap q, k;
+};
+
+struct FaPos {
+  int32_t c0, c1;   // coordinates in the reference grid (c1 = 0 for 1-D)
+  int32_t order;    // (c1 << ref_log2_0) + c0
+};
+
+FA_HD int32_t fa_ceil_log2(int32_t n) {
+  int32_t l = 0;
+  while ((int64_t(1) << l) < n) ++l;
+  return l;
+}
+
+// Builds the rule POD. Returns 0, or a negative FA_EINVAL_* (values from fa_b200.h).
+// q_shape/k_shape are in TF order (outer, inner).
+inline int fa_make_rule(int32_t seq_dims, int32_t rule, int32_t window, int32_t log2_stride,
+                        int32_t is_causal, int32_t sync_mode, const int32_t* q_shape,
+                        const int32_t* k_shape, int32_t q_base, int32_t k_base,
+                        int32_t q_full, int32_t k_full, FaRule* out) {
+  if (seq_dims != 1 && seq_dims != 2) return -3;
+  if (rule < 0 || rule > 2) return -4;
+  if (sync_mode < 0 || sync_mode > 2) return -5;
+  if (rule == 2) {
+    if (window < 1) return -6;
+    if (log2_stride < 0 || log2_stride >= 31) return -7;
+    int64_t sw = int64_t(window) << log2_stride;
+    if (sw > 0x7fffffffLL) return -7;
+  }
+  FaRule r;
+  r.dims = seq_dims;
+  r.rule = rule;
+  r.window = rule == 2 ? window : 1;
+  r.log2_stride = rule == 2 ? log2_stride : 0;
+  r.causal = (rule == 1) || (rule == 2 && is_causal);
+  // innermost-first, like the reference's SequenceDescriptorPack
+  int32_t qn[2] = {1, 1}, kn[2] = {1, 1}, qfull[2] = {1, 1}, kfull[2] = {1, 1};
+  for (int i = 0; i < seq_dims; ++i) {
+    qn[i] = q_shape[seq_dims - 1 - i];
+    kn[i] = k_shape[seq_dims - 1 - i];
+    if (qn[i] < 1 || kn[i] < 1) return -8;
+    qfull[i] = qn[i];
+    kfull[i] = kn[i];
+  }
+  if (seq_dims == 1) {
+    if (q_full > 0) qfull[0] = q_full;
+    if (k_full > 0) kfull[0] = k_full;
+    if (q_base < 0 || k_base < 0 || int64_t(q_base) + qn[0] > qfull[0] || int64_t(k_base) + kn[0] > kfull[0])
+      return -8;
+  } else if (q_base || k_base || q_full || k_full) {
+    return -8;
+  }
+  int32_t ref[2] = {1, 1}, qs[2] = {1, 1}, ks[2] = {1, 1}, qo[2] = {0, 0}, ko[2] = {0, 0};
+  for (int i = 0; i < seq_dims; ++i) {
+    int32_t mx = qfull[i] > kfull[i] ? qfull[i] : kfull[i];
+    int32_t lg = fa_ceil_log2(mx);
+    if (lg > 30) return -8;
+    ref[i] = int32_t(1) << lg;
+    if (sync_mode != 0) {
+      qs[i] = mx / qfull[i];
+      ks[i] = mx / kfull[i];
+      if (sync_mode == 2) {
+        qo[i] = qs[i] - 1;
+        ko[i] = ks[i] - 1;
+      }
+    }
+  }
+  if (int64_t(ref[0]) * ref[1] > 0x7fffffffLL) return -8;  // orders must fit int32
+  if (int64_t(qn[0]) * qn[1] > 0x7fffffffLL || int64_t(kn[0]) * kn[1] > 0x7fffffffLL) return -8;
+  r.ref0 = ref[0];
+  r.ref1 = ref[1];
+  r.ref_log2_0 = fa_ceil_log2(ref[0]);
+  r.q = FaSeqMap{qn[0], qn[1], qs[0], qs[1], qo[0], qo[1], q_base, qn[0] * qn[1]};
+  r.k = FaSeqMap{kn[0], kn[1], ks[0], ks[1], ko[0], ko[1], k_base, kn[0] * kn[1]};
+  *out = r;
+  return 0;
+}
+
+// Position of local element `idx` (row-major over the local sequence).
+FA_HD FaPos fa_pos(const FaRule& r, const FaSeqMap& s, int32_t idx) {
+  FaPos p;
+  if (r.dims == 1) {
+    p.c0 = s.off0 + (idx + s.base0) * s.stride0;
+    p.c1 = 0;
+    p.order = p.c0;
+  } else {
+    int32_t y = idx / s.n0;
+    int32_t x = idx - y * s.n0;
+    p.c0 = s.off0 + x * s.stride0;
+    p.c1 = s.off1 + y * s.stride1;
+    p.order = (p.c1 << r.ref_log2_0) + p.c0;
+  }
+  return p;
+}
+
+FA_HD int32_t fa_iabs(int32_t v) { return v < 0 ? -v : v; }
+
+// The element rule (reference Check()); padding is the caller's business.
+FA_HD bool fa_attend(const FaRule& r, const FaPos& q, const FaPos& k) {
+  if (r.rule == 0) return true;
+  if (r.causal && q.order < k.order) return false;
+  if (r.rule == 1) return true;
+  const int32_t rem = (int32_t(1) << r.log2_stride) - 1;
+  int32_t d0 = fa_iabs(q.c0 - k.c0);
+  if ((d0 & rem) != 0 || (d0 >> r.log2_stride) >= r.window) return false;
+  if (r.dims == 2) {
+    int32_t d1 = fa_iabs(q.c1 - k.c1);
+    if ((d1 & rem) != 0 || (d1 >> r.log2_stride) >= r.window) return false;
+  }
+  return true;
+}
+
+// Closed interval of coordinates/orders covered by local elements [lo, hi] (hi clamped
+// by the caller to total-1). Conservative for 2-D ranges that span several rows.
+struct FaBox {
+  int32_t c0_lo, c0_hi, c1_lo, c1_hi, ord_lo, ord_hi;
+};
+
+FA_HD FaBox fa_box(const FaRule& r, const FaSeqMap& s, int32_t lo, int32_t hi) {
+  FaBox b;
+  FaPos a = fa_pos(r, s, lo), z = fa_pos(r, s, hi);
+  b.ord_lo = a.order;
+  b.ord_hi = z.order;
+  b.c1_lo = a.c1;
+  b.c1_hi = z.c1;
+  if (r.dims == 1 || a.c1 == z.c1) {
+    b.c0_lo = a.c0;
+    b.c0_hi = z.c0;
+  } else {
+    b.c0_lo = s.off0;
+    b.c0_hi = s.off0 + (s.n0 - 1) * s.stride0;
+  }
+  return b;
+}
+
+// interval helpers: min and max of |a-b| for a in [alo,ahi], b in [blo,bhi]
+FA_HD int32_t fa_min_absdiff(int32_t alo, int32_t ahi, int32_t blo, int32_t bhi) {
+  if (ahi < blo) return blo - ahi;
+  if (bhi < alo) return alo - bhi;
+  return 0;
+}
+FA_HD int32_t fa_max_absdiff(int32_t alo, int32_t ahi, int32_t blo, int32_t bhi) {
+  int32_t a = ahi - blo, b = bhi - alo;
+  return a > b ? a : b;
+}
+
+// Classifies the block of local q rows [q_lo, q_hi] x local k columns [k_lo, k_hi]
+// (both already clamped to valid elements). SKIP => no pair attends. FULL => every pair
+// attends. Anything else is PARTIAL and must evaluate fa_attend per element.
+FA_HD int fa_classify(const FaRule& r, int32_t q_lo, int32_t q_hi, int32_t k_lo, int32_t k_hi) {
+  if (r.rule == 0) return FA_TILE_FULL;
+  FaBox q = fa_box(r, r.q, q_lo, q_hi), k = fa_box(r, r.k, k_lo, k_hi);
+  bool full = true;
+  if (r.causal) {
+    if (q.ord_hi < k.ord_lo) return FA_TILE_SKIP;
+    if (q.ord_lo < k.ord_hi) full = false;
+  }
+  if (r.rule == 2) {
+    const int64_t sw = int64_t(r.window) << r.log2_stride;  // |delta| must be < sw
+    if (int64_t(fa_min_absdiff(q.c0_lo, q.c0_hi, k.c0_lo, k.c0_hi)) >= sw) return FA_TILE_SKIP;
+    if (r.dims == 2 && int64_t(fa_min_absdiff(q.c1_lo, q.c1_hi, k.c1_lo, k.c1_hi)) >= sw) return FA_TILE_SKIP;
+    if (r.log2_stride != 0) {
+      full = false;
+    } else {
+      if (fa_max_absdiff(q.c0_lo, q.c0_hi, k.c0_lo, k.c0_hi) >= r.window) full = false;
+      if (r.dims == 2 && fa_max_absdiff(q.c1_lo, q.c1_hi, k.c1_lo, k.c1_hi) >= r.window) full = false;
+    }
+  }
+  return full ? FA_TILE_FULL : FA_TILE_PARTIAL;
+}
+
+// Range of K tiles [first, last] (inclusive, tiles of tile_k) that can be non-skipped for
+// the q rows [q_lo, q_hi]; tiles outside are SKIP for sure. Returns first > last if none.
+FA_HD void fa_k_tile_range(const FaRule& r, int32_t q_lo, int32_t q_hi, int32_t tile_k,
+                           int32_t* first, int32_t* last) {
+  const int32_t nkt = (r.k.total + tile_k - 1) / tile_k;
+  int32_t lo = 0, hi = r.k.total - 1;  // candidate local k index interval
+  if (r.rule != 0) {
+    FaBox q = fa_box(r, r.q, q_lo, q_hi);
+    // interval of the outermost K coordinate that can attend
+    int64_t c_lo = -(int64_t(1) << 40), c_hi = (int64_t(1) << 40);
+    const int32_t qo_lo = r.dims == 1 ? q.c0_lo : q.c1_lo, qo_hi = r.dims == 1 ? q.c0_hi : q.c1_hi;
+    if (r.causal) c_hi = qo_hi;  // order(q) >= order(k) implies outer coord of k <= that of q
+    if (r.rule == 2) {
+      const int64_t sw = int64_t(r.window) << r.log2_stride;
+      if (qo_lo - sw + 1 > c_lo) c_lo = qo_lo - sw + 1;
+      if (qo_hi + sw - 1 < c_hi) c_hi = qo_hi + sw - 1;
+    }
+    // outer coordinate -> local index interval
+    const int32_t st = r.dims == 1 ? r.k.stride0 : r.k.stride1;
+    const int32_t of = r.dims == 1 ? r.k.off0 : r.k.off1;
+    const int32_t n = r.dims == 1 ? r.k.n0 : r.k.n1;
+    const int32_t base = r.dims == 1 ? r.k.base0 : 0;
+    // smallest j with of + (j+base)*st >= c_lo ; largest j with of + (j+base)*st <= c_hi
+    int64_t jlo = c_lo - of <= 0 ? 0 : (c_lo - of + st - 1) / st;
+    int64_t jhi = c_hi - of < 0 ? -1 : (c_hi - of) / st;
+    jlo -= base;
+    jhi -= base;
+    if (jlo < 0) jlo = 0;
+    if (jhi > n - 1) jhi = n - 1;
+    if (jlo > jhi) {
+      *first = 1;
+      *last = 0;
+      return;
+    }
+    if (r.dims == 1) {
+      lo = int32_t(jlo);
+      hi = int32_t(jhi);
+    } else {
+      lo = int32_t(jlo) * r.k.n0;
+      hi = int32_t(jhi) * r.k.n0 + r.k.n0 - 1;
+    }
+  }
+  *first = lo / tile_k;
+  *last = hi / tile_k;
+  if (*last > nkt - 1) *last = nkt - 1;
+}
+
+// Same, transposed: range of Q tiles that can be non-skipped for the k columns [k_lo, k_hi].
+FA_HD void fa_q_tile_range(const FaRule& r, int32_t k_lo, int32_t k_hi, int32_t tile_q,
+                           int32_t* first, int32_t* last) {
+  const int32_t nqt = (r.q.total + tile_q - 1) / tile_q;
+  int32_t lo = 0, hi = r.q.total - 1;
+  if (r.rule != 0) {
+    FaBox k = fa_box(r, r.k, k_lo, k_hi);
+    int64_t c_lo = -(int64_t(1) << 40), c_hi = (int64_t(1) << 40);
+    const int32_t ko_lo = r.dims == 1 ? k.c0_lo : k.c1_lo, ko_hi = r.dims == 1 ? k.c0_hi : k.c1_hi;
+    if (r.causal) c_lo = ko_lo;
+    if (r.rule == 2) {
+      const int64_t sw = int64_t(r.window) << r.log2_stride;
+      if (ko_lo - sw + 1 > c_lo) c_lo = ko_lo - sw + 1;
+      if (ko_hi + sw - 1 < c_hi) c_hi = ko_hi + sw - 1;
+    }
+    const int32_t st = r.dims == 1 ? r.q.stride0 : r.q.stride1;
+    const int32_t of = r.dims == 1 ? r.q.off0 : r.q.off1;
+    const int32_t n = r.dims == 1 ? r.q.n0 : r.q.n1;
+    const int32_t base = r.dims == 1 ? r.q.base0 : 0;
+    int64_t jlo = c_lo - of <= 0 ? 0 : (c_lo - of + st - 1) / st;
+    int64_t jhi = c_hi - of < 0 ? -1 : (c_hi - of) / st;
+    jlo -= base;
+    jhi -= base;
+    if (jlo < 0) jlo = 0;
+    if (jhi > n - 1) jhi = n - 1;
+    if (jlo > jhi) {
+      *first = 1;
+      *last = 0;
+      return;
+    }
+    if (r.dims == 1) {
+      lo = int32_t(jlo);
+      hi = int32_t(jhi);
+    } else {
+      lo = int32_t(jlo) * r.q.n0;
+      hi = int32_t(jhi) * r.q.n0 + r.q.n0 - 1;
+    }
+  }
+  *first = lo / tile_q;
+  *last = hi / tile_q;
+  if (*last > nqt - 1) *last = nqt - 1;
+}

@@ -1,0 +1,257 @@
+'''
+Drop-in mirror of the reference's public module ``flash_attention/flash_attention.py``:
+the same six entry points, argument names, defaults and return convention
+
+  full_1d(Q, K, V, sync_mode='none_front', returning_l_m=False)          reference :80
+  causal_1d(Q, K, V, sync_mode, returning_l_m=False)                      reference :122
+  local_1d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode,  reference :163
+           returning_l_m=False)
+  full_2d / causal_2d / local_2d                                          reference :219,266,312
+
+with the same channel-first layouts ``batch_shape + (channel, sequence...)``, the same
+dtypes (float16 / float32 / float64; ``l`` is float32 for float16 inputs) and the
+registered gradient (only ``dO`` is propagated; gradients of ``l`` and ``m`` are
+ignored, reference :374-390).
+
+TensorFlow is not available in this image, so tensors are ``torch`` CUDA tensors (device
+memory + stream plumbing only; every computation happens in libfa_b200.so behind the C
+ABI of include/fa_b200.h) or host ``numpy`` arrays (staged through the C ABI's host-buffer
+entry points). The TensorFlow OpKernel shim that registers the reference's 30 ops on top
+of the same C ABI lives in ``csrc/tf_ops``.
+
+Masking rules and sync modes are documented in the reference module docstring
+(reference :1-69); the attended pattern is bit-identical (tests/test_pattern_*.py).
+'''
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+try:  # torch is plumbing (device memory, streams, autograd glue), not the product
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_NP_DTYPES = {np.dtype(np.float16): _capi.FA_F16, np.dtype(np.float32): _capi.FA_F32,
+              np.dtype(np.float64): _capi.FA_F64}
+_NP_L_DTYPE = {_capi.FA_F16: np.float32, _capi.FA_F32: np.float32, _capi.FA_F64: np.float64}
+
+
+def _torch_codes():
+    return {torch.float16: _capi.FA_F16, torch.float32: _capi.FA_F32, torch.float64: _capi.FA_F64}
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _dtype_code(x):
+    if _is_torch(x):
+        codes = _torch_codes()
+        if x.dtype not in codes:
+            raise _capi.InvalidArgumentError(-2, f"unsupported dtype {x.dtype}")
+        return codes[x.dtype]
+    dt = np.asarray(x).dtype
+    if dt not in _NP_DTYPES:
+        raise _capi.InvalidArgumentError(-2, f"unsupported dtype {dt}")
+    return _NP_DTYPES[dt]
+
+
+def _problem(seq_dims, rule, Q, K, V, sync_mode, window_size=1, log2_stride_size=0, is_causal=False):
+    code = _dtype_code(Q)
+    if _dtype_code(K) != code or _dtype_code(V) != code:
+        raise _capi.InvalidArgumentError(-2, "Q, K and V must have the same dtype")
+    return _capi.make_problem(code, seq_dims, rule, sync_mode, tuple(Q.shape), tuple(K.shape), tuple(V.shape),
+                              window_size, log2_stride_size, is_causal)
+
+
+def _out_shapes(p, Q, V):
+    sd = p.seq_dims
+    qs = tuple(Q.shape)
+    batch, seq = qs[: len(qs) - sd - 1], qs[len(qs) - sd:]
+    return batch + (p.v_d,) + seq, batch + seq
+
+
+# ------------------------------------------------------------------------------------ #
+# device path (torch CUDA tensors)
+# ------------------------------------------------------------------------------------ #
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    if nbytes == 0:
+        return None, 0
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf, buf.numel()
+
+
+def _forward_device(p, Q, K, V, out=None):
+    if not Q.is_cuda:
+        raise _capi.FlashAttentionError(-101, "torch inputs must live on a CUDA device (no CPU fallback)")
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    o_shape, lm_shape = _out_shapes(p, Q, V)
+    l_dtype = torch.float32 if Q.dtype == torch.float16 else Q.dtype
+    if out is None:
+        O = torch.empty(o_shape, dtype=Q.dtype, device=Q.device)
+        l = torch.empty(lm_shape, dtype=l_dtype, device=Q.device)
+        m = torch.empty(lm_shape, dtype=Q.dtype, device=Q.device)
+    else:
+        O, l, m = out
+    with torch.cuda.device(Q.device):
+        ws, ws_bytes = _workspace(_capi.lib.fa_workspace_bytes(C.byref(p), 0), Q.device)
+        stream = torch.cuda.current_stream(Q.device).cuda_stream
+        rc = _capi.lib.fa_forward(C.byref(p), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                  l.data_ptr(), m.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                  ws_bytes, stream)
+    _capi.check(rc, "fa_forward")
+    return O, l, m
+
+
+def _backward_device(p, Q, K, V, O, l, m, dO):
+    Q, K, V, O, l, m, dO = (t.contiguous() for t in (Q, K, V, O, l, m, dO))
+    _capi.check_backward_shapes(p, [tuple(t.shape) for t in (Q, K, V, O, l, m, dO)])
+    dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+    with torch.cuda.device(Q.device):
+        ws, ws_bytes = _workspace(_capi.lib.fa_workspace_bytes(C.byref(p), 1), Q.device)
+        stream = torch.cuda.current_stream(Q.device).cuda_stream
+        rc = _capi.lib.fa_backward(C.byref(p), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                   l.data_ptr(), m.data_ptr(), dO.data_ptr(), dQ.data_ptr(), dK.data_ptr(),
+                                   dV.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+    _capi.check(rc, "fa_backward")
+    return dQ, dK, dV
+
+
+if torch is not None:
+    class _AttentionFn(torch.autograd.Function):
+        """The registered gradient (reference: RegisterGradient on the 12 forward ops,
+        flash_attention.py:392-471, fed by _compute_gradients :374-390)."""
+
+        @staticmethod
+        def forward(ctx, Q, K, V, p):
+            O, l, m = _forward_device(p, Q, K, V)
+            ctx.save_for_backward(Q, K, V, O, l, m)
+            ctx.problem = p
+            ctx.mark_non_differentiable(l, m)
+            return O, l, m
+
+        @staticmethod
+        def backward(ctx, dO, _dl, _dm):
+            Q, K, V, O, l, m = ctx.saved_tensors
+            dQ, dK, dV = _backward_device(ctx.problem, Q, K, V, O, l, m, dO)
+            return dQ, dK, dV, None
+
+
+# ------------------------------------------------------------------------------------ #
+# host path (numpy arrays): copies inside the C ABI call
+# ------------------------------------------------------------------------------------ #
+_arena = {}
+
+
+def _device_arena(nbytes):
+    if torch is None or not torch.cuda.is_available():
+        raise _capi.FlashAttentionError(-101, "no CUDA device available (there is no CPU fallback)")
+    buf = _arena.get("buf")
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        _arena["buf"] = buf
+    return buf
+
+
+def _forward_host(p, Q, K, V):
+    Q, K, V = (np.ascontiguousarray(x) for x in (Q, K, V))
+    o_shape, lm_shape = _out_shapes(p, Q, V)
+    O = np.empty(o_shape, dtype=Q.dtype)
+    l = np.empty(lm_shape, dtype=_NP_L_DTYPE[p.dtype])
+    m = np.empty(lm_shape, dtype=Q.dtype)
+    nbytes = _capi.lib.fa_host_arena_bytes(C.byref(p), 0)
+    arena = _device_arena(nbytes)
+    rc = _capi.lib.fa_forward_host(C.byref(p), Q.ctypes.data, K.ctypes.data, V.ctypes.data, O.ctypes.data,
+                                   l.ctypes.data, m.ctypes.data, arena.data_ptr(), arena.numel(),
+                                   torch.cuda.current_stream().cuda_stream)
+    _capi.check(rc, "fa_forward_host")
+    return O, l, m
+
+
+def backward_host(p, Q, K, V, O, l, m, dO):
+    """Host-buffer backward (numpy in, numpy out)."""
+    Q, K, V, O, l, m, dO = (np.ascontiguousarray(x) for x in (Q, K, V, O, l, m, dO))
+    _capi.check_backward_shapes(p, [x.shape for x in (Q, K, V, O, l, m, dO)])
+    dQ, dK, dV = np.empty_like(Q), np.empty_like(K), np.empty_like(V)
+    arena = _device_arena(_capi.lib.fa_host_arena_bytes(C.byref(p), 1))
+    rc = _capi.lib.fa_backward_host(C.byref(p), Q.ctypes.data, K.ctypes.data, V.ctypes.data, O.ctypes.data,
+                                    l.ctypes.data, m.ctypes.data, dO.ctypes.data, dQ.ctypes.data,
+                                    dK.ctypes.data, dV.ctypes.data, arena.data_ptr(), arena.numel(),
+                                    torch.cuda.current_stream().cuda_stream)
+    _capi.check(rc, "fa_backward_host")
+    return dQ, dK, dV
+
+
+def _attend(p, Q, K, V, returning_l_m):
+    if _is_torch(Q):
+        if torch.is_grad_enabled() and (Q.requires_grad or K.requires_grad or V.requires_grad):
+            results = _AttentionFn.apply(Q, K, V, p)
+        else:
+            results = _forward_device(p, Q, K, V)
+    else:
+        results = _forward_host(p, Q, K, V)
+    return results if returning_l_m else results[0]
+
+
+# ------------------------------------------------------------------------------------ #
+# public API — same names, argument order and defaults as the reference
+# ------------------------------------------------------------------------------------ #
+def full_1d(Q, K, V, sync_mode='none_front', returning_l_m=False):
+    '''Full attention (no masking) on 1d sequences. Reference: flash_attention.py:80-119.'''
+    return _attend(_problem(1, 'full', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+
+
+def causal_1d(Q, K, V, sync_mode, returning_l_m=False):
+    '''Causal attention on 1d sequences. Reference: flash_attention.py:122-160.'''
+    return _attend(_problem(1, 'causal', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+
+
+def local_1d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False):
+    '''Local attention on 1d sequences; window length 2*window_size-1, stride 2**log2_stride_size.
+    Reference: flash_attention.py:163-216.'''
+    return _attend(_problem(1, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal),
+                   Q, K, V, returning_l_m)
+
+
+def full_2d(Q, K, V, sync_mode='none_front', returning_l_m=False):
+    '''Full attention on 2d sequences. Reference: flash_attention.py:219-263.'''
+    return _attend(_problem(2, 'full', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+
+
+def causal_2d(Q, K, V, sync_mode, returning_l_m=False):
+    '''Causal attention on 2d sequences (row-major order). Reference: flash_attention.py:266-309.'''
+    return _attend(_problem(2, 'causal', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+
+
+def local_2d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False):
+    '''Local attention on 2d sequences. Reference: flash_attention.py:312-370.'''
+    return _attend(_problem(2, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal),
+                   Q, K, V, returning_l_m)
+
+
+# backward ops, callable directly like the reference's `_fa_kernel.*_attention_backward{1,2}d[_float16]`
+def attention_backward(seq_dims, rule, Q, K, V, O, l, m, dO, sync_mode, window_size=1, log2_stride_size=0,
+                       is_causal=False):
+    p = _problem(seq_dims, rule, Q, K, V, sync_mode, window_size, log2_stride_size, is_causal)
+    if _is_torch(Q):
+        return _backward_device(p, Q, K, V, O, l, m, dO)
+    return backward_host(p, Q, K, V, O, l, m, dO)
+
+
+def estimate_forward_flops(seq_dims, rule, q_shape, k_shape, v_shape, dtype, sync_mode, window_size=1,
+                           log2_stride_size=0, is_causal=False, shared_mem_bytes=0):
+    '''The reference's Estimate{Full,Causal,Local}AttentionForward{1,2}dFlops ops
+    (flash_attention.py:475-562, flash_attention_forward.cc:390-474), host only.'''
+    code = _NP_DTYPES[np.dtype(dtype)]
+    p = _capi.make_problem(code, seq_dims, rule, sync_mode, tuple(q_shape), tuple(k_shape), tuple(v_shape),
+                           window_size, log2_stride_size, is_causal)
+    return _capi.estimate_forward_flops(p, shared_mem_bytes)
