@@ -75,8 +75,8 @@ typedef struct fa_problem_t {
   int32_t q_shape[2];       /* TF axis order (outer, inner); 1-D uses q_shape[0]             */
   int32_t k_shape[2];
   /* K/V-ring support (one long sequence sharded over GPUs): this call sees rows
-   * [q_coord_base, q_coord_base + q_shape) of a longer logical sequence whose full
-   * extent is q_full_shape (same for k). All zeros = not sharded (the reference
+   * [q_index_base, q_index_base + q_shape[0]) of a longer logical sequence whose full
+   * length is q_full_len (same for k). All zeros = not sharded (the reference
    * has no such notion; the rule is evaluated on global coordinates). 1-D only. */
   int32_t q_index_base;
   int32_t k_index_base;
@@ -167,10 +167,10 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
 /* ---- diagnostics ---------------------------------------------------------------- */
 const char* fa_strerror(int status);
 int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on this thread */
-/* Which kernel family the last fa_forward/fa_backward on this thread dispatched to:
+/* Which kernel family the last fa_forward/fa_backward in this process dispatched to:
  * 0 none, 1 generic SIMT, 2 tcgen05 f16, 3 3xTF32 tcgen05, 4 DMMA f64.               */
 int fa_last_path(void);
-/* Number of kernel launches issued by this library on this thread since the last reset. */
+/* Number of kernel launches issued by this library in this process since the last reset. */
 int64_t fa_launch_count(int reset);
 /* Force a kernel family (testing): 0 auto, 1 generic only.                             */
 void fa_set_path_override(int path);

@@ -5,17 +5,19 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/fa_b200.h"
 #include "fa_launch.h"
 
 namespace fa {
-static thread_local int64_t g_launches = 0;
+// process-wide (autograd runs the backward on another thread than the forward)
+static std::atomic<int64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
-static thread_local int g_last_path = 0;
-static int g_path_override = 0;
-void count_launch() { ++g_launches; }
+static std::atomic<int> g_last_path{0};
+static std::atomic<int> g_path_override{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace fa
 
 namespace {
@@ -82,9 +84,7 @@ const char* fa_strerror(int s) {
 int fa_last_cuda_error(void) { return fa::g_last_cuda; }
 int fa_last_path(void) { return fa::g_last_path; }
 int64_t fa_launch_count(int reset) {
-  int64_t v = fa::g_launches;
-  if (reset) fa::g_launches = 0;
-  return v;
+  return reset ? fa::g_launches.exchange(0) : fa::g_launches.load();
 }
 void fa_set_path_override(int path) { fa::g_path_override = path; }
 
