@@ -1,7 +1,482 @@
-// placeholder until the tcgen05 forward lands (next commit)
+// fa_fwd_f16_sm100.cu — Blackwell-native fp16 forward: TMA -> swizzled smem -> tcgen05.mma with
+// TMEM accumulators, warp-specialised (1 TMA producer warp, 1 MMA issuer warp, 2 softmax
+// warpgroups that ping-pong over two 128-row Q tiles).
+//
+// Replaces the reference's ForwardImpl (flash_attention/kernel/flash_attention.cu:425-1077), a
+// scalar-FMA kernel that walks K tiles in the outer loop and read-modify-writes O/l/m in HBM under a
+// spin lock. Here each CTA owns 256 query rows of one batch element, streams only the K/V tiles the
+// rule does not skip, keeps S/P and O in tensor memory and writes O, l, m exactly once.
+//
+// Layout facts this design leans on (channel-first tensors, sequence contiguous):
+//   S = Q K^T : A = Q tile, B = K tile, both "MN-major" in shared memory (the 64-element swizzle
+//               row runs along the sequence, 8 channels form one 1024-byte swizzle atom)
+//   O = P V   : A = P (fp16, written by the softmax warps into TMEM over S), B = V tile, K-major
+// so no transposes are needed anywhere.
+#include "fa_common.cuh"
 #include "fa_launch.h"
+#include "sm100_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
 namespace fa {
-bool sm100_f16_forward_supports(const LaunchArgs&) { return false; }
+namespace sm100 {
+
+using namespace ptx;
+
+constexpr int kBlockM = 128;     // query rows per tile == TMEM lanes
+constexpr int kBlockN = 128;     // keys per tile
+constexpr int kQTiles = 2;       // Q tiles per CTA (ping-pong)
+constexpr int kStages = 4;       // K/V ring depth (each stage holds one K or one V tile)
+constexpr int kThreads = 384;    // 8 softmax warps + producer + mma + alloc + spare
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units; lazy O rescale
+
+struct alignas(64) FwdParams {
+  CUtensorMap map_q, map_k, map_v, map_o;
+  FaRule rule;
+  float* l;
+  __half* m;
+  int32_t nq, nk, n_qpairs;
+  int32_t batch;
+  float scale_log2;
+};
+
+template <int D, int VD>
+struct FwdCfg {
+  static constexpr int kCh = D > VD ? D : VD;
+  static constexpr int kQTileBytes = kBlockM * kCh * 2;   // doubles as the O staging tile
+  static constexpr int kStageBytes = kBlockN * kCh * 2;
+  static constexpr int kBarOffset = kQTiles * kQTileBytes + kStages * kStageBytes;
+  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
+  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;  // + alignment slack
+};
+
+// live = not skipped for the union of the CTA's rows
+__device__ __forceinline__ bool tile_live(const FaRule& r, int q_lo, int q_hi, int kt, int nk) {
+  const int k0 = kt * kBlockN;
+  return fa_classify(r, q_lo, q_hi, k0, min(k0 + kBlockN, nk) - 1) != FA_TILE_SKIP;
+}
+
+// incremental walk over the positions of consecutive K entries
+struct KWalker {
+  int32_t x, c0, c1;
+  __device__ __forceinline__ void init(const FaRule& r, int32_t idx) {
+    if (r.dims == 1) {
+      x = idx;
+      c0 = r.k.off0 + (idx + r.k.base0) * r.k.stride0;
+      c1 = 0;
+    } else {
+      int32_t y = idx / r.k.n0;
+      x = idx - y * r.k.n0;
+      c0 = r.k.off0 + x * r.k.stride0;
+      c1 = r.k.off1 + y * r.k.stride1;
+    }
+  }
+  __device__ __forceinline__ FaPos pos(const FaRule& r) const {
+    FaPos p;
+    p.c0 = c0;
+    p.c1 = c1;
+    p.order = (c1 << r.ref_log2_0) + c0;
+    return p;
+  }
+  __device__ __forceinline__ void next(const FaRule& r) {
+    ++x;
+    c0 += r.k.stride0;
+    if (r.dims == 2 && x == r.k.n0) {
+      x = 0;
+      c0 = r.k.off0;
+      c1 += r.k.stride1;
+    }
+  }
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant__ FwdParams p) {
+  using Cfg = FwdCfg<D, VD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base;
+  const uint32_t kv_smem = smem_base + kQTiles * Cfg::kQTileBytes;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_q_full = bars;                        // [2]
+  const uint32_t bar_kv_full = bars + 16;                  // [kStages]
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * kStages; // [kStages]
+  const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;  // [2]
+  const uint32_t bar_p_ready = bar_s_full + 16;            // [2]
+  const uint32_t bar_o_final = bar_p_ready + 16;           // [2]
+  const uint32_t tmem_slot = bar_o_final + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+
+  // heavy (late) query rows first, all batch elements of one row block before the next
+  const int pair = p.n_qpairs - 1 - int(blockIdx.x / p.batch);
+  const int b = int(blockIdx.x % p.batch);
+  const int q0 = pair * (kQTiles * kBlockM);
+  const int q_hi = min(q0 + kQTiles * kBlockM, p.nq) - 1;
+  int kt_first, kt_last;
+  fa_k_tile_range(rule, q0, q_hi, kBlockN, &kt_first, &kt_last);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_o);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_q_full + 8 * i, 1);
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, kBlockM);
+        mbar_init(bar_o_final + 8 * i, 1);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_kv_full + 8 * s, 1);
+        mbar_init(bar_kv_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        for (int i = 0; i < kQTiles; ++i) {
+          mbar_arrive_expect_tx(bar_q_full + 8 * i, kBlockM * D * 2);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(q_smem + i * Cfg::kQTileBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
+                        q0 + i * kBlockM + h * 64, b * D);
+        }
+        int t = 0;
+        for (int kt = kt_first; kt <= kt_last; ++kt) {
+          if (!tile_live(rule, q0, q_hi, kt, p.nk)) continue;
+          {
+            const int s = t % kStages, u = t / kStages;
+            mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * D * 2);
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
+                          kt * kBlockN + h * 64, b * D);
+            ++t;
+          }
+          {
+            const int s = t % kStages, u = t / kStages;
+            mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * VD * 2);
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
+                          kt * kBlockN + h * 64, b * VD);
+            ++t;
+          }
+        }
+      }
+    } else if (warp == 9) {
+      // ===================== MMA issuer =====================
+      if (elect_one()) {
+        int n = 0;
+        for (int kt = kt_first; kt <= kt_last; ++kt) n += tile_live(rule, q0, q_hi, kt, p.nk) ? 1 : 0;
+        constexpr uint32_t idesc_qk = idesc_f16(kBlockM, kBlockN, true, true);
+        constexpr uint32_t idesc_pv = idesc_f16(kBlockM, VD, false, false);
+        auto issue_qk = [&](int i, int stage) {
+          const uint32_t a0 = q_smem + i * Cfg::kQTileBytes;
+          const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            // MN-major SW128: 16 channels = two 1024-byte atoms; LBO = next 64 rows (next TMA box)
+            const uint64_t da = smem_desc_sw128(a0 + ks * 2048, D * 128, 1024);
+            const uint64_t db = smem_desc_sw128(b0 + ks * 2048, D * 128, 1024);
+            mma_ss(tmem_base + i * kBlockN, da, db, idesc_qk, ks > 0);
+          }
+        };
+        auto issue_pv = [&](int i, int stage, bool accumulate) {
+          const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBlockN / 16; ++ks) {
+            // K-major SW128: 16 keys = 32 bytes inside the 128-byte row; second box after 64 keys
+            const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
+            mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
+                   (accumulate || ks > 0) ? 1u : 0u);
+          }
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_full + 0, 0);
+          for (int i = 0; i < kQTiles; ++i) {
+            mbar_wait(bar_q_full + 8 * i, 0);
+            tc_fence_after();
+            issue_qk(i, 0);
+            mma_commit(bar_s_full + 8 * i);
+          }
+          mma_commit(bar_kv_empty + 0);
+          for (int j = 0; j < n; ++j) {
+            const int tv = 2 * j + 1, sv = tv % kStages;
+            const int tk = 2 * j + 2, sk = tk % kStages;
+            mbar_wait(bar_kv_full + 8 * sv, (tv / kStages) & 1);
+            for (int i = 0; i < kQTiles; ++i) {
+              mbar_wait(bar_p_ready + 8 * i, j & 1);
+              tc_fence_after();
+              issue_pv(i, sv, j > 0);
+              if (i == kQTiles - 1) mma_commit(bar_kv_empty + 8 * sv);
+              if (j + 1 < n) {
+                if (i == 0) {
+                  mbar_wait(bar_kv_full + 8 * sk, (tk / kStages) & 1);
+                  tc_fence_after();
+                }
+                issue_qk(i, sk);
+                mma_commit(bar_s_full + 8 * i);
+                if (i == kQTiles - 1) mma_commit(bar_kv_empty + 8 * sk);
+              } else {
+                mma_commit(bar_o_final + 8 * i);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    setmaxnreg_inc<224>();
+    const int i = warp >> 2;                    // which Q tile
+    const int r = threadIdx.x & 127;            // row inside the tile
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + i * kBlockN;
+    const uint32_t t_o = tmem_base + lane_addr + 256 + i * 128;
+    const int tq0 = q0 + i * kBlockM;
+    const int tq_hi = min(tq0 + kBlockM, p.nq) - 1;
+    const bool tile_valid = tq0 < p.nq;
+    const int qi = tq0 + r;
+    const bool q_valid = qi < p.nq;
+    const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
+    const float scale_log2 = p.scale_log2;
+    const float NEG_INF = __int_as_float(0xff800000);
+    float m_ref = NEG_INF;   // running reference max (log2 units) the accumulators are scaled to
+    float m_true = NEG_INF;  // true running max (log2 units)
+    float l_sum = 0.f;
+    int j = 0;
+    for (int kt = kt_first; kt <= kt_last; ++kt) {
+      if (!tile_live(rule, q0, q_hi, kt, p.nk)) continue;
+      const int k0 = kt * kBlockN;
+      const int k_hi = min(k0 + kBlockN, p.nk) - 1;
+      const int cls = tile_valid ? fa_classify(rule, tq0, tq_hi, k0, k_hi) : FA_TILE_SKIP;
+      const bool ragged = k0 + kBlockN > p.nk;
+      mbar_wait(bar_s_full + 8 * i, j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
+      tmem_wait_ld();
+
+      if (cls == FA_TILE_SKIP) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) s[c] = NEG_INF;
+      } else if (cls == FA_TILE_PARTIAL || ragged) {
+        if (rule.dims == 1 && rule.rule != 2) {
+          // 1-D full/causal: the attended keys of a row are a prefix of the tile
+          int limit = k_hi - k0;  // last valid column
+          if (rule.causal) {
+            // k attended iff k.off + (k0+c+base)*stride <= q.c0
+            const int num = qpos.c0 - rule.k.off0;
+            const int jmax = num < 0 ? -1 : num / rule.k.stride0;  // global k index bound
+            limit = min(limit, jmax - rule.k.base0 - k0);
+          }
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] = c <= limit ? s[c] : NEG_INF;
+        } else {
+          KWalker w;
+          w.init(rule, k0);
+          const int nvalid = k_hi - k0 + 1;
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
+            const bool ok = c < nvalid && fa_attend(rule, qpos, w.pos(rule));
+            s[c] = ok ? s[c] : NEG_INF;
+            w.next(rule);
+          }
+        }
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
+      const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
+      m_true = fmaxf(m_true, mx2);
+      if (j == 0) {
+        m_ref = mx2;
+      } else {
+        const bool need = mx2 > m_ref + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx2);
+          const float alpha = (m_new == NEG_INF) ? 1.f : ex2(m_ref - m_new);
+          m_ref = m_new;
+          l_sum *= alpha;
+#pragma unroll
+          for (int c = 0; c < VD / 32; ++c) {
+            float o[32];
+            tmem_ld32f(t_o + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] *= alpha;
+            tmem_st32f(t_o + c * 32, o);
+          }
+        }
+      }
+      const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
+      uint32_t pk[64];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 2) {
+        const float p0 = ex2(fmaf(s[c], scale_log2, -m_use));
+        const float p1 = ex2(fmaf(s[c + 1], scale_log2, -m_use));
+        sum += p0 + p1;
+        pk[c >> 1] = pack_half2(p0, p1);
+      }
+      l_sum += sum;
+      tmem_st32(t_s, &pk[0]);
+      tmem_st32(t_s + 32, &pk[32]);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready + 8 * i);
+      ++j;
+    }
+
+    // ---- epilogue: O = acc / l -> fp16 -> smem [VD][64] x2 -> TMA store; l, m -> global ----
+    uint8_t* stage_gen = smem_gen + i * Cfg::kQTileBytes;
+    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (VD * 64) + (r & 63);
+    if (j > 0) {
+      mbar_wait(bar_o_final + 8 * i, 0);
+      tc_fence_after();
+      const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#pragma unroll
+      for (int c = 0; c < VD / 32; ++c) {
+        float o[32];
+        tmem_ld32f(t_o + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(l_sum > 0.f ? o[e] * inv : 0.f);
+      }
+    } else {
+      // no key tile survives for this CTA: wait for Q to land before reusing its buffer
+      mbar_wait(bar_q_full + 8 * i, 0);
+#pragma unroll 8
+      for (int c = 0; c < VD; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+    }
+    if (q_valid) {
+      const int64_t idx = int64_t(b) * p.nq + qi;
+      if (l_sum > 0.f) {
+        const __half m_h = __float2half_rn(m_true * kLn2);
+        p.m[idx] = m_h;
+        p.l[idx] = l_sum * ex2(m_ref - __half2float(m_h) * kLog2e);
+      } else {
+        p.m[idx] = sentinel<__half>();
+        p.l[idx] = 0.f;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + i, kBlockM);
+    if (r == 0 && tile_valid) {
+      for (int h = 0; h < 2; ++h)
+        if (tq0 + h * 64 < p.nq)
+          tma_store_2d(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b * VD);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  }();
+  return fn;
+}
+
+// 2-D view [rows = batch*channels][cols = sequence] of a channel-first fp16 tensor
+bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                 bool swizzle128) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(cols) * 2};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int D, int VD>
+cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
+  using Cfg = FwdCfg<D, VD>;
+  FwdParams p;
+  const int nq = a.rule.q.total, nk = a.rule.k.total;
+  if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
+      !make_map_2d(&p.map_k, a.k, a.batch * D, nk, 64, D, true) ||
+      !make_map_2d(&p.map_v, a.v, a.batch * VD, nk, 64, VD, true) ||
+      !make_map_2d(&p.map_o, a.o, a.batch * VD, nq, 64, VD, false))
+    return cudaErrorInvalidValue;
+  p.rule = a.rule;
+  p.l = (float*)a.l;
+  p.m = (__half*)a.m;
+  p.nq = nq;
+  p.nk = nk;
+  p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
+  p.batch = int32_t(a.batch);
+  p.scale_log2 = kLog2e / sqrtf(float(D));
+  auto kern = fwd_kernel<D, VD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  kern<<<unsigned(int64_t(p.n_qpairs) * p.batch), kThreads, Cfg::kSmemBytes, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace sm100
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool sm100_f16_forward_supports(const LaunchArgs& a) {
+  if (a.dtype != 0 || a.accumulate) return false;
+  if (!((a.d == 64 || a.d == 128) && (a.v_d == 64 || a.v_d == 128))) return false;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (nq % 8 || nk % 8) return false;  // TMA: row pitch must be a multiple of 16 bytes
+  if (!aligned16(a.q) || !aligned16(a.k) || !aligned16(a.v) || !aligned16(a.o)) return false;
+  if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
+  const int64_t pairs = (nq + 255) / 256;
+  if (pairs * a.batch > 0x7fffffffLL) return false;
+  return true;
+}
+
 size_t sm100_f16_workspace_bytes(const LaunchArgs&, bool) { return 0; }
-cudaError_t sm100_f16_forward(const LaunchArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+
+cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
+  if (a.d == 128 && a.v_d == 128) return sm100::launch_fwd<128, 128>(a, stream);
+  if (a.d == 64 && a.v_d == 64) return sm100::launch_fwd<64, 64>(a, stream);
+  if (a.d == 128 && a.v_d == 64) return sm100::launch_fwd<128, 64>(a, stream);
+  return sm100::launch_fwd<64, 128>(a, stream);
+}
+
 }  // namespace fa
