@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C1|C3|C4]
+
+Workload (config.workload): BASELINE.json configs[1] — causal_1d fp16 forward + backward,
+batch x heads = 16 x 16, head_dim 128, seq 8192 (GPT-style self-attention), inputs U(-2,2) already
+resident in HBM. One "step" = one forward + one backward pass of the hot path over that batch.
+With N > 1 (torchrun, one process per GPU) every rank runs the same batch (batch x head sharding,
+no communication, "weak" scaling); value = total unmasked FLOPs / max-over-ranks time.
+
+Metric: attention fwd/bwd TFLOPS counting only unmasked FLOPs
+  fwd = 2 * nnz * (d + v_d) * batch, bwd = 2 * nnz * (3 d + 2 v_d) * batch  (BASELINE.md §3).
+
+The product path is libfa_b200.so through its C ABI (ctypes); torch only owns device memory,
+streams and the process group. oracle/ is used solely for the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (fn, dtype, batch_shape, d, v_d, q_shape, k_shape, rule, sync, window, log2_stride, causal)
+    "C2": dict(desc="causal_1d fp16 fwd+bwd, batch*heads 16x16, head_dim 128, seq 8192", seq_dims=1,
+               dtype="float16", batch=(16, 16), d=128, v_d=128, q=(8192,), k=(8192,), rule="causal",
+               sync="none_front", w=1, s=0, c=0),
+    "C1": dict(desc="local_1d fp32 README example Q[8,32,1024] K[8,32,2048] V[8,16,2048] w32 s0 scale_front",
+               seq_dims=1, dtype="float32", batch=(8,), d=32, v_d=16, q=(1024,), k=(2048,), rule="local",
+               sync="scale_front", w=32, s=0, c=0),
+    "C3": dict(desc="local_2d fp16 causal 64x64 grid, window 8, none_front, head_dim 64, 16x16 heads", seq_dims=2,
+               dtype="float16", batch=(16, 16), d=64, v_d=64, q=(64, 64), k=(64, 64), rule="local",
+               sync="none_front", w=8, s=0, c=1),
+    "C4": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp16 head_dim 64, 256 heads", seq_dims=1,
+               dtype="float16", batch=(16, 16), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
+               sync="scale_end", w=1, s=0, c=0),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"tensor_burst": d.get("bf16_tflops"), "tensor_sustained": d.get("bf16_tflops_sustained"),
+                "hbm": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor_burst": 1590.0, "tensor_sustained": 1400.0, "hbm": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def flops_of(w, nnz):
+    b = int(np.prod(w["batch"]))
+    return 2.0 * nnz * (w["d"] + w["v_d"]) * b, 2.0 * nnz * (3 * w["d"] + 2 * w["v_d"]) * b
+
+
+def cpu_reference_leg(w, nnz, steps, warmup, heads):
+    """The reference's CPU path (its tests' dense attention; oracle port) on a bounded sample."""
+    import torch
+    from oracle import dense_torch_cpu as cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nq, nk = int(np.prod(w["q"])), int(np.prod(w["k"]))
+    mask = cpu.mask_tensor(w["q"], w["k"], w["sync"], w["rule"], w["w"], w["s"], bool(w["c"]))
+    sec = cpu.time_fwd_bwd(heads, w["d"], w["v_d"], nq, nk, mask, steps=steps, warmup=warmup)
+    fl = 2.0 * nnz * (w["d"] + w["v_d"]) * heads + 2.0 * nnz * (3 * w["d"] + 2 * w["v_d"]) * heads
+    return {"value": fl / sec / 1e12, "unit": "TFLOPS", "cores": cores, "kind": "port",
+            "sample": f"{heads} of {int(np.prod(w['batch']))} heads of the same workload, full {nq}x{nk} "
+                      f"logits per head, fwd + autodiff bwd in fp32 with torch CPU ops (TensorFlow absent), "
+                      f"{sec:.2f} s per step", "sec_per_step": sec}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-heads", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-refkernel", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from tf_flash_attention_b200 import _capi
+    code = {"float16": 0, "float32": 1, "float64": 2}[w["dtype"]]
+    prob = _capi.make_problem(code, w["seq_dims"], w["rule"], w["sync"], w["batch"] + (w["d"],) + w["q"],
+                              w["batch"] + (w["d"],) + w["k"], w["batch"] + (w["v_d"],) + w["k"], w["w"], w["s"],
+                              w["c"])
+    nnz = _capi.count_attended(prob)
+    fwd_flops, bwd_flops = flops_of(w, nnz)
+    step_flops = fwd_flops + (0 if args.fwd_only else bwd_flops)
+    config = {"workload": f"{args.workload}: {w['desc']}", "batch_heads": int(np.prod(w["batch"])),
+              "head_dim": w["d"], "seq_q": int(np.prod(w["q"])), "seq_k": int(np.prod(w["k"])),
+              "nnz_per_head": nnz, "flops_per_step": step_flops, "fwd_flops": fwd_flops, "bwd_flops": bwd_flops,
+              "pass": "fwd" if args.fwd_only else "fwd+bwd", "parallelism": f"batch x head sharding, {world} rank(s), "
+              "no communication", "l2": "inputs larger than the 126 MB L2 (no flush needed)"}
+
+    # ---------------- reference arm: the reference's CPU path on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        heads = max(1, args.cpu_heads)
+        leg = cpu_reference_leg(w, nnz, max(1, args.steps), max(0, args.warmup), heads)
+        line = {"impl": "reference", "metric": "attention fwd+bwd TFLOPS (unmasked FLOPs)", "value": leg["value"],
+                "unit": "TFLOPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": leg["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (CPU; fp16 inputs computed in fp32)", "data": "synthetic U(-2,2)",
+                "config": config, "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": leg["value"], "unit": "TFLOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------- our arm -------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdt = {"float16": torch.float16, "float32": torch.float32, "float64": torch.float64}[w["dtype"]]
+    ldt = torch.float32 if tdt == torch.float16 else tdt
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def u(shape):
+        return (torch.rand(shape, generator=g, device=dev, dtype=torch.float32) * 4 - 2).to(tdt)
+
+    Q, K = u(w["batch"] + (w["d"],) + w["q"]), u(w["batch"] + (w["d"],) + w["k"])
+    V, dO = u(w["batch"] + (w["v_d"],) + w["k"]), u(w["batch"] + (w["v_d"],) + w["q"])
+    O = torch.empty_like(dO)
+    l = torch.empty(w["batch"] + w["q"], dtype=ldt, device=dev)
+    m = torch.empty(w["batch"] + w["q"], dtype=tdt, device=dev)
+    dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+    ws_bytes = max(_capi.lib.fa_workspace_bytes(C.byref(prob), 1), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    def fwd():
+        _capi.check(_capi.lib.fa_forward(C.byref(prob), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                         l.data_ptr(), m.data_ptr(), ws.data_ptr(), ws_bytes, sp), "fa_forward")
+
+    def bwd():
+        _capi.check(_capi.lib.fa_backward(C.byref(prob), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
+                                          l.data_ptr(), m.data_ptr(), dO.data_ptr(), dQ.data_ptr(), dK.data_ptr(),
+                                          dV.data_ptr(), ws.data_ptr(), ws_bytes, sp), "fa_backward")
+
+    def step():
+        fwd()
+        if not args.fwd_only:
+            bwd()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    fwd_path = None
+    fwd()
+    fwd_path = _capi.PATH_NAMES[_capi.lib.fa_last_path()]
+    bwd_path = None
+    if not args.fwd_only:
+        bwd()
+        bwd_path = _capi.PATH_NAMES[_capi.lib.fa_last_path()]
+    torch.cuda.synchronize()
+
+    # timed region: exactly K steps, CUDA events on the launching stream, barrier + sync both sides
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    _capi.lib.fa_launch_count(1)
+    _capi.lib.fa_kernel_timing(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _capi.lib.fa_kernel_timing(0)
+    launches = int(_capi.lib.fa_launch_count(0))
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    kt = _capi.kernel_timings()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = step_flops * world / (ms_per_step * 1e-3) / 1e12
+
+    # per-kernel durations -> roofline of the dominant kernel
+    per = {}
+    for name, ms in kt:
+        per.setdefault(name, []).append(ms)
+    kernels = {n: {"launches": len(v), "avg_ms": float(np.mean(v)), "share": float(np.sum(v)) / ms_total}
+               for n, v in per.items()}
+    peaks = measured_peaks()
+    roofline = None
+    if kernels:
+        dom = max(kernels, key=lambda n: kernels[n]["share"])
+        bwd_names = [n for n in kernels if "bwd" in n]
+        if dom in ("fwd_f16_sm100", "generic_fwd"):
+            ach = fwd_flops / (kernels[dom]["avg_ms"] * 1e-3) / 1e12
+            what = f"{dom}: 2*nnz*(d+v_d)*batch FLOPs per launch"
+        else:
+            # the backward kernels are reported together: algorithmic bwd FLOPs / sum of their durations
+            tb = sum(kernels[n]["avg_ms"] for n in bwd_names)
+            ach = bwd_flops / (tb * 1e-3) / 1e12
+            dom = "+".join(sorted(bwd_names))
+            what = f"{dom}: 2*nnz*(3d+2v_d)*batch FLOPs per backward pass"
+        peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
+                    "algorithmic": what}
+        if "fwd_f16_sm100" in kernels:
+            fa_ = fwd_flops / (kernels["fwd_f16_sm100"]["avg_ms"] * 1e-3) / 1e12
+            roofline["fwd_kernel"] = {"achieved": fa_, "frac": fa_ / peak, "frac_of_burst": fa_ / (peaks["tensor_burst"] or peak),
+                                      "frac_of_nominal_2250": fa_ / 2250.0}
+
+    line = {"metric": "attention fwd+bwd TFLOPS (unmasked FLOPs)" if not args.fwd_only else "attention fwd TFLOPS (unmasked FLOPs)",
+            "value": value, "unit": "TFLOPS", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 (fp32 accumulate)" if w["dtype"] == "float16" else w["dtype"], "data": "synthetic U(-2,2), seed 1234",
+            "config": config, "sequences_per_s": float(np.prod(w["batch"])) * world / (ms_per_step * 1e-3),
+            "paths": {"fwd": fwd_path, "bwd": bwd_path}, "kernels": kernels, "roofline": roofline,
+            "clocks": clocks, "gpu_launches": launches, "pct_of_nominal_fp16_peak": 100.0 * value / world / 2250.0}
+
+    # ---------------- end-to-end through the host-buffer C ABI (rank-local) ----------------
+    if not args.no_e2e:
+        del dQ, dK, dV, ws
+        hq, hk, hv, hdo = (x.cpu().pin_memory() for x in (Q, K, V, dO))
+        ho = torch.empty_like(hdo).pin_memory()
+        hl = torch.empty(l.shape, dtype=ldt).pin_memory()
+        hm = torch.empty(m.shape, dtype=tdt).pin_memory()
+        hdq, hdk, hdv = (torch.empty_like(x).pin_memory() for x in (hq, hk, hv))
+        del Q, K, V, dO, O, l, m
+        torch.cuda.empty_cache()
+        nb_f = _capi.lib.fa_host_arena_bytes(C.byref(prob), 0)
+        nb_b = _capi.lib.fa_host_arena_bytes(C.byref(prob), 1)
+        arena = torch.empty(max(nb_f, nb_b), dtype=torch.uint8, device=dev)
+
+        def e2e_step():
+            _capi.check(_capi.lib.fa_forward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
+                                                  ho.data_ptr(), hl.data_ptr(), hm.data_ptr(), arena.data_ptr(),
+                                                  arena.numel(), sp), "fa_forward_host")
+            if not args.fwd_only:
+                _capi.check(_capi.lib.fa_backward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
+                                                       ho.data_ptr(), hl.data_ptr(), hm.data_ptr(), hdo.data_ptr(),
+                                                       hdq.data_ptr(), hdk.data_ptr(), hdv.data_ptr(),
+                                                       arena.data_ptr(), arena.numel(), sp), "fa_backward_host")
+
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        nb = lambda x: x.numel() * x.element_size()  # noqa: E731
+        h2d = nb(hq) + nb(hk) + nb(hv)
+        d2h = nb(ho) + nb(hl) + nb(hm)
+        if not args.fwd_only:
+            h2d += nb(hq) + nb(hk) + nb(hv) + nb(ho) + nb(hl) + nb(hm) + nb(hdo)
+            d2h += nb(hdq) + nb(hdk) + nb(hdv)
+        line["e2e"] = {"value": step_flops * world / sec / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
+                       "api": "fa_forward_host + fa_backward_host (C ABI, pinned host buffers, copies inside the call)"}
+        del arena
+
+    # ---------------- CPU baseline (rank 0, N = 1) ------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        leg = cpu_reference_leg(w, nnz, 1, 0, max(1, args.cpu_heads))
+        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0 and world == 1 and not args.no_refkernel:
+        try:
+            from oracle import refkernel
+            line["ref_kernel_baseline"] = refkernel.bench(w, nnz, heads=8, fwd_only=args.fwd_only)
+        except Exception as e:  # the reference build is optional (oracle/_ref)
+            line["ref_kernel_baseline"] = {"unavailable": str(e)[:200]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

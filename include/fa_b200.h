@@ -172,6 +172,11 @@ int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on th
 int fa_last_path(void);
 /* Number of kernel launches issued by this library in this process since the last reset. */
 int64_t fa_launch_count(int reset);
+/* Per-kernel device timing for bench.py: when enabled every kernel this library launches is
+ * bracketed by CUDA events on the launching stream. fa_kernel_timings() synchronises on them,
+ * returns up to max_entries (name, milliseconds) pairs in launch order and clears the list.   */
+void fa_kernel_timing(int enable);
+int fa_kernel_timings(int max_entries, const char** names, float* ms);
 /* Force a kernel family (testing): 0 auto, 1 generic only.                             */
 void fa_set_path_override(int path);
 const char* fa_version(void);

@@ -87,6 +87,8 @@ def _load():
         "fa_last_path": (C.c_int, []),
         "fa_launch_count": (i64, [C.c_int]),
         "fa_set_path_override": (None, [C.c_int]),
+        "fa_kernel_timing": (None, [C.c_int]),
+        "fa_kernel_timings": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
         "fa_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -190,3 +192,11 @@ def estimate_forward_flops(p, shared_mem_bytes=0):
     f = C.c_float(0)
     check(lib.fa_estimate_forward_flops(C.byref(p), shared_mem_bytes, C.byref(f)), "fa_estimate_forward_flops")
     return f.value
+
+
+def kernel_timings(max_entries=4096):
+    """[(kernel name, ms)] of every launch since fa_kernel_timing(1) / the last call."""
+    names = (C.c_char_p * max_entries)()
+    ms = (C.c_float * max_entries)()
+    n = lib.fa_kernel_timings(max_entries, names, ms)
+    return [(names[i].decode(), float(ms[i])) for i in range(n)]

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/fa_b200.h"
@@ -18,6 +19,28 @@ static thread_local int g_last_cuda = 0;
 static std::atomic<int> g_last_path{0};
 static std::atomic<int> g_path_override{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-kernel timing ------------------------------------------------------------
+struct TimedLaunch { const char* name; cudaEvent_t start, stop; };
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+static std::vector<TimedLaunch> g_timed;
+
+ScopedKernel::ScopedKernel(const char* name, cudaStream_t stream) : stream_(stream), slot_(-1) {
+  count_launch();
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  TimedLaunch t{name, nullptr, nullptr};
+  if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
+  cudaEventRecord(t.start, stream);
+  std::lock_guard<std::mutex> g(g_timing_mu);
+  slot_ = int(g_timed.size());
+  g_timed.push_back(t);
+}
+ScopedKernel::~ScopedKernel() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> g(g_timing_mu);
+  cudaEventRecord(g_timed[slot_].stop, stream_);
+}
 }  // namespace fa
 
 namespace {
@@ -87,6 +110,26 @@ int64_t fa_launch_count(int reset) {
   return reset ? fa::g_launches.exchange(0) : fa::g_launches.load();
 }
 void fa_set_path_override(int path) { fa::g_path_override = path; }
+
+void fa_kernel_timing(int enable) { fa::g_timing.store(enable ? 1 : 0); }
+
+int fa_kernel_timings(int max_entries, const char** names, float* ms) {
+  std::lock_guard<std::mutex> g(fa::g_timing_mu);
+  int n = 0;
+  for (auto& t : fa::g_timed) {
+    float v = -1.f;
+    if (cudaEventSynchronize(t.stop) == cudaSuccess) cudaEventElapsedTime(&v, t.start, t.stop);
+    if (n < max_entries) {
+      if (names) names[n] = t.name;
+      if (ms) ms[n] = v;
+      ++n;
+    }
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  fa::g_timed.clear();
+  return n;
+}
 
 size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
   fa::LaunchArgs a{};

@@ -449,8 +449,8 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   auto kern = fwd_kernel<D, VD>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
+  ScopedKernel timed("fwd_f16_sm100", stream);
   kern<<<unsigned(int64_t(p.n_qpairs) * p.batch), kThreads, Cfg::kSmemBytes, stream>>>(p);
-  count_launch();
   return cudaGetLastError();
 }
 

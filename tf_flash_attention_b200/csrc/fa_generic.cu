@@ -487,11 +487,12 @@ static size_t dkdv_smem(int d, int v_d, int BM) {
 }
 
 template <typename K, typename P>
-static cudaError_t launch(K kernel, const P& params, int64_t grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch(const char* name, K kernel, const P& params, int64_t grid, size_t smem,
+                          cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
+  ScopedKernel timed(name, stream);
   kernel<<<unsigned(grid), NT, smem, stream>>>(params);
-  count_launch();
   return cudaGetLastError();
 }
 
@@ -516,7 +517,7 @@ cudaError_t forward_t(const LaunchArgs& a, cudaStream_t stream) {
 #define FA_FWD(BM_, NS_)                                                                   \
   do {                                                                                     \
     p.n_rtiles = (p.nq + BM_ - 1) / BM_;                                                   \
-    return launch(fwd_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                   \
+    return launch("generic_fwd", fwd_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                   \
                   fwd_smem<T>(a.d, a.v_d, BM_), stream);                                   \
   } while (0)
   if (ns <= 2 && fwd_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_FWD(BIG, 2);
@@ -540,11 +541,14 @@ cudaError_t backward_t(const LaunchArgs& a, cudaStream_t stream) {
   {
     int64_t total = p.batch * p.nq;
     int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 8));
-    bwd_prep_kernel<T><<<blocks, 256, 0, stream>>>((const T*)a.o, (const T*)a.d_o,
-                                                   (const typename LOf<T>::type*)a.l, (const T*)a.m,
-                                                   lse, dsum, p.batch, p.v_d, p.nq);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    {
+      ScopedKernel timed("bwd_prep", stream);
+      bwd_prep_kernel<T><<<blocks, 256, 0, stream>>>((const T*)a.o, (const T*)a.d_o,
+                                                     (const typename LOf<T>::type*)a.l, (const T*)a.m,
+                                                     lse, dsum, p.batch, p.v_d, p.nq);
+      e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return e;
   }
   constexpr int BIG = Tiles<T>::kBig, SMALL = Tiles<T>::kSmall;
@@ -552,11 +556,11 @@ cudaError_t backward_t(const LaunchArgs& a, cudaStream_t stream) {
 #define FA_BWD(BM_, NS_)                                                                      \
   do {                                                                                        \
     p.n_rtiles = (p.nq + BM_ - 1) / BM_;                                                      \
-    cudaError_t e = launch(bwd_dq_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,          \
+    cudaError_t e = launch("generic_bwd_dq", bwd_dq_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,          \
                            dq_smem<T>(a.d, a.v_d, BM_), stream);                              \
     if (e != cudaSuccess) return e;                                                           \
     p.n_rtiles = (p.nk + BM_ - 1) / BM_;                                                      \
-    return launch(bwd_dkdv_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                 \
+    return launch("generic_bwd_dkdv", bwd_dkdv_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                 \
                   dkdv_smem<T>(a.d, a.v_d, BM_), stream);                                     \
   } while (0)
   if (ns <= 2 && dkdv_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_BWD(BIG, 2);

@@ -27,6 +27,15 @@ struct LaunchArgs {
 
 void count_launch();
 
+// Counts one kernel launch and, when kernel timing is on (fa_kernel_timing), brackets it with
+// CUDA events on the launching stream so that bench.py can report per-kernel durations.
+struct ScopedKernel {
+  ScopedKernel(const char* name, cudaStream_t stream);
+  ~ScopedKernel();
+  cudaStream_t stream_;
+  int slot_;
+};
+
 // generic SIMT family (fa_generic.cu)
 bool generic_supports(const LaunchArgs& a);
 size_t generic_workspace_bytes(int dtype, int64_t batch, int64_t nq, bool backward);
