@@ -1,0 +1,119 @@
+"""GPU parity tests for the tcgen05 / TMEM / TMA fp16 kernels (forward, dQ, dK/dV), called through
+the C ABI and compared with the dense oracle. Shapes satisfy the fast path's constraints
+(d, v_d in {64,128}; sequence lengths multiples of 8) and the test asserts that the tcgen05 family
+was the one dispatched (fa_last_path() == 2), so a silent fallback cannot pass."""
+import numpy as np
+import pytest
+
+from oracle import dense_attention as da
+from tests.helpers import max_abs_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+from tf_flash_attention_b200 import _capi  # noqa: E402
+from tf_flash_attention_b200 import flash_attention as fa  # noqa: E402
+
+TOL = 2e-3  # BASELINE.json: fp16 max-abs on O and on the gradients (scaled by max(1,|ref|) for gradients)
+
+
+def _run(dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=0, grads=True):
+    rng = np.random.default_rng(seed)
+    Q, K, V, dO = da.random_inputs(rng, np.float16, batch, d, vd, qs, ks)
+    ref = da.attention(Q, K, V, dims, rule, mode, w, s, c, dO=dO)
+    tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+    if rule == "full":
+        O, l, m = (fa.full_1d if dims == 1 else fa.full_2d)(tq, tk, tv, mode, True)
+    elif rule == "causal":
+        O, l, m = (fa.causal_1d if dims == 1 else fa.causal_2d)(tq, tk, tv, mode, True)
+    else:
+        O, l, m = (fa.local_1d if dims == 1 else fa.local_2d)(tq, tk, tv, w, s, c, mode, True)
+    torch.cuda.synchronize()
+    assert _capi.lib.fa_last_path() == 2, "forward did not take the tcgen05 path"
+    tag = f"{dims}d {rule} {mode} w{w} s{s} c{c} b{batch} d{d} vd{vd} q{qs} k{ks}"
+    On = O.detach().cpu().numpy()
+    assert max_abs_err(On, ref["O"]) <= TOL, f"O {tag}"
+    ln, mn = l.cpu().numpy().astype(np.float64), m.cpu().numpy()
+    empty = ~np.isfinite(ref["m"])
+    if empty.any():
+        assert np.all(ln[empty] == 0) and np.all(mn[empty].view(np.uint8) == 0xFA)
+        assert np.all(On[np.broadcast_to(np.expand_dims(empty, -dims - 1), On.shape)] == 0)
+    live = ~empty
+    lse = mn.astype(np.float64)[live] + np.log(ln[live])
+    assert np.max(np.abs(lse - (ref["m"][live] + np.log(ref["l"][live])))) <= 2e-2, f"lse {tag}"
+    assert np.max(np.abs(mn.astype(np.float64)[live] - ref["m"][live]) / np.maximum(1, np.abs(ref["m"][live]))) <= 2e-3
+    if grads:
+        dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+        torch.cuda.synchronize()
+        assert _capi.lib.fa_last_path() == 2, "backward did not take the tcgen05 path"
+        for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+            assert scaled_err(g.cpu().numpy(), ref[name]) <= TOL, f"{name} {tag}: {scaled_err(g.cpu().numpy(), ref[name])}"
+
+
+CASES = [
+    # dims rule mode w s c batch d vd q k
+    (1, "full", "none_front", 1, 0, 0, (1,), 128, 128, (256,), (128,)),
+    (1, "full", "scale_front", 1, 0, 0, (2,), 128, 128, (512,), (640,)),
+    (1, "full", "scale_end", 1, 0, 0, (2,), 64, 64, (128,), (1024,)),          # C4-like cross attention
+    (1, "causal", "none_front", 1, 0, 0, (2, 2), 128, 128, (1024,), (1024,)),  # C2-like
+    (1, "causal", "none_front", 1, 0, 0, (3,), 64, 64, (768,), (768,)),
+    (1, "causal", "scale_front", 1, 0, 0, (2,), 64, 128, (264,), (1032,)),
+    (1, "causal", "scale_end", 1, 0, 0, (2,), 128, 64, (128,), (1024,)),
+    (1, "causal", "scale_end", 1, 0, 0, (2,), 64, 64, (1000,), (88,)),         # more queries than keys
+    (1, "full", "none_front", 1, 0, 0, (2,), 64, 128, (200,), (328,)),         # ragged tiles
+    (1, "local", "scale_front", 32, 0, 0, (2,), 64, 64, (512,), (1024,)),      # C1-like window
+    (1, "local", "none_front", 5, 2, 1, (1,), 128, 128, (520,), (520,)),       # strided + causal
+    (1, "local", "none_front", 2, 0, 0, (2,), 64, 64, (640,), (128,)),         # rows with no keys
+    (1, "local", "scale_end", 40, 1, 0, (1,), 128, 128, (384,), (768,)),
+    (2, "full", "none_front", 1, 0, 0, (1,), 64, 64, (16, 24), (24, 16)),
+    (2, "causal", "scale_front", 1, 0, 0, (1,), 128, 128, (16, 24), (32, 24)),
+    (2, "causal", "scale_end", 1, 0, 0, (2,), 64, 64, (8, 40), (24, 40)),
+    (2, "local", "none_front", 4, 0, 1, (2,), 64, 64, (24, 32), (24, 32)),     # C3-like
+    (2, "local", "scale_front", 3, 1, 0, (1,), 64, 128, (20, 24), (40, 24)),
+    (2, "local", "none_front", 8, 0, 1, (1,), 64, 64, (64, 64), (64, 64)),     # C3 at full grid size
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-w{c[3]}s{c[4]}c{c[5]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_tcgen05_paths_match_oracle(case):
+    _run(*case, seed=hash(case) % 1000)
+
+
+def test_full_size_c2_one_head_vs_chunked_oracle():
+    """BASELINE.json configs[1] at full size for one head: S = 8192, d = 128, causal."""
+    rng = np.random.default_rng(1234)
+    Q, K, V, dO = da.random_inputs(rng, np.float16, (1,), 128, 128, (8192,), (8192,))
+    ref = da.forward_backward_chunked(Q[0], K[0], V[0], dO[0], (8192,), (8192,), "none_front", "causal")
+    tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+    O = fa.causal_1d(tq, tk, tv, "none_front")
+    assert _capi.lib.fa_last_path() == 2
+    assert max_abs_err(O.detach().cpu().numpy()[0], ref["O"]) <= TOL
+    dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+    assert _capi.lib.fa_last_path() == 2
+    for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert scaled_err(g.cpu().numpy()[0], ref[name]) <= TOL, name
+
+
+def test_full_size_properties_c2():
+    """Size-independent properties at the full C2 batch (16 x 16 heads would take the oracle hours):
+    (1) V = ones  ->  O = 1 on every row (softmax rows sum to one);
+    (2) linearity in V: O(V1 + V2) = O(V1) + O(V2);
+    (3) causal prefix: the first 1024 rows do not depend on later keys;
+    (4) batch elements are independent: permuting heads permutes outputs bit-exactly."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, d, S = 8, 128, 8192
+
+    def u(*shape):
+        return (torch.rand(shape, generator=g, device="cuda") * 4 - 2).half()
+    Q, K, V1, V2 = u(B, d, S), u(B, d, S), u(B, d, S), u(B, d, S)
+    ones = torch.ones_like(V1)
+    O1 = fa.causal_1d(Q, K, ones, "none_front")
+    assert _capi.lib.fa_last_path() == 2
+    assert float((O1.float() - 1).abs().max()) <= 2e-3
+    Oa, Ob = fa.causal_1d(Q, K, V1, "none_front"), fa.causal_1d(Q, K, V2, "none_front")
+    Oab = fa.causal_1d(Q, K, (V1.float() * 0.5 + V2.float() * 0.5).half(), "none_front")
+    assert float((Oab.float() - 0.5 * (Oa.float() + Ob.float())).abs().max()) <= 4e-3
+    Op = fa.causal_1d(Q[:, :, :1024].contiguous(), K[:, :, :1024].contiguous(), V1[:, :, :1024].contiguous(), "none_front")
+    assert float((Op.float() - Oa[:, :, :1024].float()).abs().max()) <= 2e-3
+    perm = torch.randperm(B, device="cuda")
+    Oq = fa.causal_1d(Q[perm].contiguous(), K[perm].contiguous(), V1[perm].contiguous(), "none_front")
+    assert torch.equal(Oq, Oa[perm])

@@ -1,6 +1,771 @@
-// placeholder until the tcgen05 backward lands
+// fa_bwd_f16_sm100.cu — Blackwell-native fp16 backward: two tcgen05/TMEM/TMA kernels.
+//
+// Replaces the reference's BackwardImpl (flash_attention/kernel/flash_attention.cu:1079-1967), which
+// keeps a K/V tile per CTA, loops over Q tiles under a global spin lock and read-modify-writes dQ in
+// HBM with scalar FMAs. Here the work is split so that no inter-CTA communication is needed:
+//
+//   bwd_dq_kernel   : CTA = 2 x 128 query rows (ping-pong), streams 64-key K/V tiles
+//        S  = Q K^T        (SS, both operands MN-major straight from the channel-first layout)
+//        dP = dO V^T       (SS, MN-major)
+//        dS = P o (dP - D) , P = exp2(S*scale*log2e - LSE2)      (softmax warps, TMEM -> regs -> TMEM)
+//        dQ += dS K        (TS: dS from TMEM, K tile re-read K-major)
+//   bwd_dkdv_kernel : CTA = 128 keys, streams 64-query Q/dO tiles into two ping-pong slots
+//        S^T = K Q^T, dP^T = V dO^T  (SS, MN-major)
+//        dV += P^T dO, dK += dS^T Q  (TS: P^T / dS^T from TMEM; dO / Q tiles re-read K-major)
+// Formulas as in the reference: P = exp(s*scale - m)/l (flash_attention.cu:1838-1841),
+// dS = P (dP - D) scale (:1544-1546), D = rowsum(dO o O) (:1882-1891).
+#include "fa_common.cuh"
 #include "fa_launch.h"
+#include "sm100_ptx.cuh"
+
 namespace fa {
-bool sm100_f16_backward_supports(const LaunchArgs&) { return false; }
-cudaError_t sm100_f16_backward(const LaunchArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+namespace sm100 {
+
+using namespace ptx;
+
+bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                 bool swizzle128);  // fa_fwd_f16_sm100.cu
+
+constexpr int kBM = 128;        // rows owned by one softmax warpgroup (TMEM lanes)
+constexpr int kBN = 64;         // streamed tile width
+constexpr int kBwdThreads = 384;
+constexpr float kLog2eB = 1.4426950408889634f;
+constexpr int kStatPad = 64;    // padding (floats) behind the LSE2 / D arrays for the bulk copies
+
+struct alignas(64) BwdParams {
+  CUtensorMap map_q, map_k, map_v, map_do;   // SW128 loads, box 64 x channels
+  CUtensorMap map_dq, map_dk, map_dv;        // plain stores, box 64 x channels
+  FaRule rule;
+  const float* lse2;   // [batch*nq + pad]  (m + log l) * log2(e), +inf on empty rows
+  const float* dsum;   // [batch*nq + pad]  rowsum(dO o O)
+  int32_t nq, nk, n_blocks, batch;
+  float scale_log2, scale;
+};
+
+// ---- preprocess: LSE2 and D -------------------------------------------------------------------
+__global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restrict__ d_o,
+                             const float* __restrict__ l, const __half* __restrict__ m, float* __restrict__ lse2,
+                             float* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq) {
+  const int64_t total = batch * nq;
+  // two adjacent query positions per thread -> half2 loads, coalesced along the sequence
+  for (int64_t i2 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 2; i2 < total;
+       i2 += int64_t(gridDim.x) * blockDim.x * 2) {
+    const int64_t b = i2 / nq, r = i2 - b * nq;  // nq is even (multiple of 8)
+    const __half2* op = reinterpret_cast<const __half2*>(o + b * v_d * int64_t(nq) + r);
+    const __half2* dp = reinterpret_cast<const __half2*>(d_o + b * v_d * int64_t(nq) + r);
+    float a0 = 0.f, a1 = 0.f;
+    const int64_t pitch2 = nq / 2;
+#pragma unroll 4
+    for (int c = 0; c < v_d; ++c) {
+      const float2 x = __half22float2(op[c * pitch2]);
+      const float2 y = __half22float2(dp[c * pitch2]);
+      a0 = fmaf(x.x, y.x, a0);
+      a1 = fmaf(x.y, y.y, a1);
+    }
+    dsum[i2] = a0;
+    dsum[i2 + 1] = a1;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float lv = l[i2 + e];
+      const __half mv = m[i2 + e];
+      lse2[i2 + e] = (lv > 0.f && !is_sentinel<__half>(mv)) ? (__half2float(mv) + logf(lv)) * kLog2eB
+                                                             : __int_as_float(0x7f800000);
+    }
+  }
+}
+
+__device__ __forceinline__ bool block_live(const FaRule& r, int q_lo, int q_hi, int k_lo, int k_hi) {
+  return fa_classify(r, q_lo, q_hi, k_lo, k_hi) != FA_TILE_SKIP;
+}
+
+// incremental walk over consecutive entries of one sequence map
+struct SeqWalker {
+  int32_t x, c0, c1;
+  __device__ __forceinline__ void init(const FaRule& r, const FaSeqMap& s, int32_t idx) {
+    if (r.dims == 1) {
+      x = idx;
+      c0 = s.off0 + (idx + s.base0) * s.stride0;
+      c1 = 0;
+    } else {
+      int32_t y = idx / s.n0;
+      x = idx - y * s.n0;
+      c0 = s.off0 + x * s.stride0;
+      c1 = s.off1 + y * s.stride1;
+    }
+  }
+  __device__ __forceinline__ FaPos pos(const FaRule& r) const {
+    FaPos p;
+    p.c0 = c0;
+    p.c1 = c1;
+    p.order = (c1 << r.ref_log2_0) + c0;
+    return p;
+  }
+  __device__ __forceinline__ void next(const FaRule& r, const FaSeqMap& s) {
+    ++x;
+    c0 += s.stride0;
+    if (r.dims == 2 && x == s.n0) {
+      x = 0;
+      c0 = s.off0;
+      c1 += s.stride1;
+    }
+  }
+};
+
+// =================================================================================================
+// dQ kernel
+// =================================================================================================
+template <int D, int VD>
+struct DqCfg {
+  static constexpr int kStages = 3;
+  static constexpr int kQBytes = kBM * D * 2;       // also the dQ staging tile
+  static constexpr int kDoBytes = kBM * VD * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kVBytes = kBN * VD * 2;
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kRingOffset = 2 * (kQBytes + kDoBytes);
+  static constexpr int kBarOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
+  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_constant__ BwdParams p) {
+  using Cfg = DqCfg<D, VD>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base;                       // [2][kQBytes]
+  const uint32_t do_smem = smem_base + 2 * Cfg::kQBytes;   // [2][kDoBytes]
+  const uint32_t ring = smem_base + Cfg::kRingOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_q_full = bars;
+  const uint32_t bar_kv_full = bars + 16;
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * kStages;
+  const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;
+  const uint32_t bar_p_ready = bar_s_full + 16;
+  const uint32_t bar_final = bar_p_ready + 16;
+  const uint32_t tmem_slot = bar_final + 16;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int pair = p.n_blocks - 1 - int(blockIdx.x / p.batch);  // heavy (late) rows first
+  const int b = int(blockIdx.x % p.batch);
+  const int q0 = pair * (2 * kBM);
+  const int q_hi = min(q0 + 2 * kBM, p.nq) - 1;
+  int kt_first, kt_last;
+  fa_k_tile_range(rule, q0, q_hi, kBN, &kt_first, &kt_last);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_do);
+      prefetch_tensormap(&p.map_dq);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_q_full + 8 * i, 1);
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, kBM);
+        mbar_init(bar_final + 8 * i, 1);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_kv_full + 8 * s, 1);
+        mbar_init(bar_kv_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: S_i [i*64, +64)  dP_i [128+i*64, +64)  dQ_i [256+i*128, +D)
+
+  auto live = [&](int kt) {
+    const int k0 = kt * kBN;
+    return block_live(rule, q0, q_hi, k0, min(k0 + kBN, p.nk) - 1);
+  };
+
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
+      if (elect_one()) {
+        for (int i = 0; i < 2; ++i) {
+          mbar_arrive_expect_tx(bar_q_full + 8 * i, Cfg::kQBytes + Cfg::kDoBytes);
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(q_smem + i * Cfg::kQBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
+                        q0 + i * kBM + h * 64, b * D);
+            tma_load_2d(do_smem + i * Cfg::kDoBytes + h * (VD * 128), &p.map_do, bar_q_full + 8 * i,
+                        q0 + i * kBM + h * 64, b * VD);
+          }
+        }
+        int t = 0;
+        for (int kt = kt_first; kt <= kt_last; ++kt) {
+          if (!live(kt)) continue;
+          const int s = t % kStages, u = t / kStages;
+          mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
+          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b * D);
+          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b * VD);
+          ++t;
+        }
+      }
+    } else if (warp == 9) {
+      if (elect_one()) {
+        int n = 0;
+        for (int kt = kt_first; kt <= kt_last; ++kt) n += live(kt) ? 1 : 0;
+        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, true, true);
+        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, false);
+        auto issue_s_dp = [&](int i, int stage) {
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + Cfg::kKBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base + i * kBN, smem_desc_sw128(q_smem + i * Cfg::kQBytes + ks * 2048, D * 128, 1024),
+                   smem_desc_sw128(k_s + ks * 2048, D * 128, 1024), idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < VD / 16; ++ks)
+            mma_ss(tmem_base + 128 + i * kBN,
+                   smem_desc_sw128(do_smem + i * Cfg::kDoBytes + ks * 2048, VD * 128, 1024),
+                   smem_desc_sw128(v_s + ks * 2048, VD * 128, 1024), idesc_s, ks > 0);
+        };
+        auto issue_dq = [&](int i, int stage, bool accumulate) {
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + ks * 8,
+                   smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_full + 0, 0);
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(bar_q_full + 8 * i, 0);
+            tc_fence_after();
+            issue_s_dp(i, 0);
+            mma_commit(bar_s_full + 8 * i);
+          }
+          for (int j = 0; j < n; ++j) {
+            const int sj = j % kStages, sn = (j + 1) % kStages;
+            for (int i = 0; i < 2; ++i) {
+              mbar_wait(bar_p_ready + 8 * i, j & 1);
+              tc_fence_after();
+              issue_dq(i, sj, j > 0);
+              if (i == 1) mma_commit(bar_kv_empty + 8 * sj);
+              if (j + 1 < n) {
+                if (i == 0) {
+                  mbar_wait(bar_kv_full + 8 * sn, ((j + 1) / kStages) & 1);
+                  tc_fence_after();
+                }
+                issue_s_dp(i, sn);
+                mma_commit(bar_s_full + 8 * i);
+              } else {
+                mma_commit(bar_final + 8 * i);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<224>();
+    const int i = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + i * kBN;
+    const uint32_t t_dp = tmem_base + lane_addr + 128 + i * kBN;
+    const uint32_t t_dq = tmem_base + lane_addr + 256 + i * 128;
+    const int tq0 = q0 + i * kBM;
+    const int tq_hi = min(tq0 + kBM, p.nq) - 1;
+    const bool tile_valid = tq0 < p.nq;
+    const int qi = tq0 + r;
+    const bool q_valid = qi < p.nq;
+    const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float scale_log2 = p.scale_log2;
+    int j = 0;
+    for (int kt = kt_first; kt <= kt_last; ++kt) {
+      if (!live(kt)) continue;
+      const int k0 = kt * kBN;
+      const int k_hi = min(k0 + kBN, p.nk) - 1;
+      const int cls = tile_valid ? fa_classify(rule, tq0, tq_hi, k0, k_hi) : FA_TILE_SKIP;
+      const bool ragged = k0 + kBN > p.nk;
+      mbar_wait(bar_s_full + 8 * i, j & 1);
+      tc_fence_after();
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_dp, &dp[0]);
+      tmem_ld32f(t_dp + 32, &dp[32]);
+      tmem_wait_ld();
+      uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
+      if (cls == FA_TILE_SKIP) {
+        okmask_lo = okmask_hi = 0u;
+      } else if (cls == FA_TILE_PARTIAL || ragged) {
+        uint64_t mk = 0;
+        if (rule.dims == 1 && rule.rule != 2) {
+          int limit = k_hi - k0;
+          if (rule.causal) {
+            const int num = qpos.c0 - rule.k.off0;
+            const int jmax = num < 0 ? -1 : num / rule.k.stride0;
+            limit = min(limit, jmax - rule.k.base0 - k0);
+          }
+          mk = limit < 0 ? 0ull : (limit >= 63 ? ~0ull : ((1ull << (limit + 1)) - 1ull));
+        } else {
+          SeqWalker w;
+          w.init(rule, rule.k, k0);
+          const int nvalid = k_hi - k0 + 1;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            if (c < nvalid && fa_attend(rule, qpos, w.pos(rule))) mk |= 1ull << c;
+            w.next(rule, rule.k);
+          }
+        }
+        okmask_lo = uint32_t(mk);
+        okmask_hi = uint32_t(mk >> 32);
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
+        float p0 = ex2(fmaf(s[c], scale_log2, -lse2));
+        float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
+        p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
+        p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
+        pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
+      }
+      tmem_st32(t_s, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready + 8 * i);
+      ++j;
+    }
+    // epilogue: dQ = scale * acc -> fp16 -> smem [D][64] x2 -> TMA store
+    __half* stage_h = reinterpret_cast<__half*>(smem_gen + i * Cfg::kQBytes) + (r >> 6) * (D * 64) + (r & 63);
+    if (j > 0) {
+      mbar_wait(bar_final + 8 * i, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        float o[32];
+        tmem_ld32f(t_dq + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
+      }
+    } else {
+      mbar_wait(bar_q_full + 8 * i, 0);
+#pragma unroll 8
+      for (int c = 0; c < D; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + i, kBM);
+    if (r == 0 && tile_valid) {
+      for (int h = 0; h < 2; ++h)
+        if (tq0 + h * 64 < p.nq)
+          tma_store_2d(&p.map_dq, q_smem + i * Cfg::kQBytes + h * (D * 128), tq0 + h * 64, b * D);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================
+// dK / dV kernel
+// =================================================================================================
+template <int D, int VD>
+struct DkvCfg {
+  static constexpr int kStages = 4;
+  static constexpr int kKBytes = kBM * D * 2;     // resident K tile, also dK staging
+  static constexpr int kVBytes = kBM * VD * 2;    // resident V tile, also dV staging
+  static constexpr int kQBytes = kBN * D * 2;     // streamed Q sub-tile
+  static constexpr int kDoBytes = kBN * VD * 2;
+  static constexpr int kStatBytes = 2 * kBN * 4;  // LSE2[64] + D[64]
+  static constexpr int kStageBytes = kQBytes + kDoBytes;
+  static constexpr int kRingOffset = kKBytes + kVBytes;
+  static constexpr int kStatOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kBarOffset = kStatOffset + kStages * kStatBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 2 + 2 + 1;
+  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_constant__ BwdParams p) {
+  using Cfg = DkvCfg<D, VD>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t k_smem = smem_base;
+  const uint32_t v_smem = smem_base + Cfg::kKBytes;
+  const uint32_t ring = smem_base + Cfg::kRingOffset;
+  const uint32_t stat_smem = smem_base + Cfg::kStatOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_kv_res = bars;                          // resident K/V landed
+  const uint32_t bar_full = bars + 8;                        // [kStages]
+  const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
+  const uint32_t bar_s_full = bar_empty + 8 * kStages;       // [2]
+  const uint32_t bar_p_ready = bar_s_full + 16;              // [2]
+  const uint32_t bar_final = bar_p_ready + 16;               // [1]
+  const uint32_t tmem_slot = bar_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+  const float* stat_gen = reinterpret_cast<const float*>(smem_gen + Cfg::kStatOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int kblk = int(blockIdx.x / p.batch);  // early key tiles are the heavy ones under causal
+  const int b = int(blockIdx.x % p.batch);
+  const int k0 = kblk * kBM;
+  const int k_hi = min(k0 + kBM, p.nk) - 1;
+  int qt_first, qt_last;
+  fa_q_tile_range(rule, k0, k_hi, kBN, &qt_first, &qt_last);
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_do);
+      prefetch_tensormap(&p.map_dk);
+      prefetch_tensormap(&p.map_dv);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      mbar_init(bar_kv_res, 1);
+      mbar_init(bar_final, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, kBM);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: S^T_x [x*64, +64)  dP^T_x [128+x*64, +64)  dV [256, +VD)  dK [384, +D)
+
+  auto live = [&](int qt) {
+    const int q0 = qt * kBN;
+    return block_live(rule, q0, min(q0 + kBN, p.nq) - 1, k0, k_hi);
+  };
+
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
+          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+        }
+        int t = 0;
+        for (int qt = qt_first; qt <= qt_last; ++qt) {
+          if (!live(qt)) continue;
+          const int s = t % kStages, u = t / kStages;
+          mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
+          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
+          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
+          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
+          ++t;
+        }
+      }
+    } else if (warp == 9) {
+      if (elect_one()) {
+        int n = 0;
+        for (int qt = qt_first; qt <= qt_last; ++qt) n += live(qt) ? 1 : 0;
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
+        auto issue_st_dpt = [&](int x, int stage) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
+                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < VD / 16; ++ks)
+            mma_ss(tmem_base + 128 + x * kBN, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
+                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+        };
+        auto issue_dv_dk = [&](int x, int stage, bool accumulate) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+                   idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(q_s + ks * 32, 16, 1024),
+                   idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_res, 0);
+          for (int t = 0; t < 2 && t < n; ++t) {
+            mbar_wait(bar_full + 8 * (t % kStages), (t / kStages) & 1);
+            tc_fence_after();
+            issue_st_dpt(t & 1, t % kStages);
+            mma_commit(bar_s_full + 8 * (t & 1));
+          }
+          for (int t = 0; t < n; ++t) {
+            const int x = t & 1, st = t % kStages;
+            mbar_wait(bar_p_ready + 8 * x, (t >> 1) & 1);
+            tc_fence_after();
+            issue_dv_dk(x, st, t > 0);
+            mma_commit(bar_empty + 8 * st);
+            if (t + 2 < n) {
+              const int t2 = t + 2, s2 = t2 % kStages;
+              mbar_wait(bar_full + 8 * s2, (t2 / kStages) & 1);
+              tc_fence_after();
+              issue_st_dpt(x, s2);
+              mma_commit(bar_s_full + 8 * x);
+            }
+          }
+          mma_commit(bar_final);
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<224>();
+    const int x = warp >> 2;                 // ping-pong slot this warpgroup serves
+    const int r = threadIdx.x & 127;         // key row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + x * kBN;
+    const uint32_t t_dp = tmem_base + lane_addr + 128 + x * kBN;
+    const int ki = k0 + r;
+    const bool k_valid = ki < p.nk;
+    const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
+    const float scale_log2 = p.scale_log2;
+    int t = 0;   // index over live sub-tiles (all), this WG handles those with (t & 1) == x
+    for (int qt = qt_first; qt <= qt_last; ++qt) {
+      if (!live(qt)) continue;
+      if ((t & 1) != x) {
+        ++t;
+        continue;
+      }
+      const int st = t % kStages;
+      const int q0 = qt * kBN;
+      const int q_hi = min(q0 + kBN, p.nq) - 1;
+      const int cls = fa_classify(rule, q0, q_hi, k0, k_hi);
+      const bool ragged = (q0 + kBN > p.nq) || (k0 + kBM > p.nk);
+      mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
+      mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
+      tc_fence_after();
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_dp, &dp[0]);
+      tmem_ld32f(t_dp + 32, &dp[32]);
+      tmem_wait_ld();
+      uint64_t mk = ~0ull;
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        mk = 0;
+        if (k_valid) {
+          const int nvalid = q_hi - q0 + 1;
+          if (rule.dims == 1 && rule.rule != 2) {
+            int cmin = 0;
+            if (rule.causal) {
+              // q attended iff q.off + (q0+c+base)*stride >= k.c0
+              const int num = kpos.c0 - rule.q.off0;
+              const int jmin = num <= 0 ? 0 : (num + rule.q.stride0 - 1) / rule.q.stride0;  // global q index
+              cmin = max(0, jmin - rule.q.base0 - q0);
+            }
+            const uint64_t upto = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+            const uint64_t below = cmin >= 64 ? ~0ull : ((1ull << cmin) - 1ull);
+            mk = upto & ~below;
+          } else {
+            SeqWalker w;
+            w.init(rule, rule.q, q0);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              if (c < nvalid && fa_attend(rule, w.pos(rule), kpos)) mk |= 1ull << c;
+              w.next(rule, rule.q);
+            }
+          }
+        }
+      }
+      const uint32_t okmask_lo = uint32_t(mk), okmask_hi = uint32_t(mk >> 32);
+      const float2* stats = reinterpret_cast<const float2*>(stat_gen + st * (2 * kBN));
+      const float* lse_s = stat_gen + st * (2 * kBN);
+      const float* dsum_s = lse_s + kBN;
+      (void)stats;
+      uint32_t pk[32], dk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
+        float p0 = ex2(fmaf(s[c], scale_log2, -lse_s[c]));
+        float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse_s[c + 1]));
+        p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
+        p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
+        pk[c >> 1] = pack_half2(p0, p1);
+        dk[c >> 1] = pack_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]));
+      }
+      tmem_st32(t_s, pk);
+      tmem_st32(t_dp, dk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready + 8 * x);
+      ++t;
+    }
+    // how many live sub-tiles exist in total (t counted them all)
+    // epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK
+    const int CH = x == 0 ? VD : D;
+    const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 256 : 384);
+    const float out_scale = x == 0 ? 1.f : p.scale;
+    uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
+    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
+    if (t > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+      for (int c = 0; c < CH / 32; ++c) {
+        float o[32];
+        tmem_ld32f(t_acc + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+      }
+    } else {
+      mbar_wait(bar_kv_res, 0);
+      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + x, kBM);
+    if (r == 0) {
+      for (int h = 0; h < 2; ++h)
+        if (k0 + h * 64 < p.nk) {
+          if (x == 0)
+            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+          else
+            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+        }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+template <int D, int VD>
+cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
+  BwdParams p;
+  const int nq = a.rule.q.total, nk = a.rule.k.total;
+  float* lse2 = reinterpret_cast<float*>(a.workspace);
+  float* dsum = lse2 + (a.batch * int64_t(nq) + kStatPad);
+  if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
+      !make_map_2d(&p.map_k, a.k, a.batch * D, nk, 64, D, true) ||
+      !make_map_2d(&p.map_v, a.v, a.batch * VD, nk, 64, VD, true) ||
+      !make_map_2d(&p.map_do, a.d_o, a.batch * VD, nq, 64, VD, true) ||
+      !make_map_2d(&p.map_dq, a.d_q, a.batch * D, nq, 64, D, false) ||
+      !make_map_2d(&p.map_dk, a.d_k, a.batch * D, nk, 64, D, false) ||
+      !make_map_2d(&p.map_dv, a.d_v, a.batch * VD, nk, 64, VD, false))
+    return cudaErrorInvalidValue;
+  p.rule = a.rule;
+  p.lse2 = lse2;
+  p.dsum = dsum;
+  p.nq = nq;
+  p.nk = nk;
+  p.batch = int32_t(a.batch);
+  p.scale = 1.f / sqrtf(float(D));
+  p.scale_log2 = p.scale * kLog2eB;
+  {
+    const int64_t total = a.batch * int64_t(nq);
+    const int blocks = int(std::min<int64_t>((total / 2 + 255) / 256, 148 * 16));
+    ScopedKernel timed("bwd_prep_f16", stream);
+    bwd_prep_f16<<<blocks, 256, 0, stream>>>((const __half*)a.o, (const __half*)a.d_o, (const float*)a.l,
+                                             (const __half*)a.m, lse2, dsum, a.batch, VD, nq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  {
+    auto kern = bwd_dq_kernel<D, VD>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D, VD>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    p.n_blocks = (nq + 2 * kBM - 1) / (2 * kBM);
+    ScopedKernel timed("bwd_dq_f16_sm100", stream);
+    kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DqCfg<D, VD>::kSmemBytes, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  {
+    auto kern = bwd_dkdv_kernel<D, VD>;
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D, VD>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    p.n_blocks = (nk + kBM - 1) / kBM;
+    ScopedKernel timed("bwd_dkdv_f16_sm100", stream);
+    kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DkvCfg<D, VD>::kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+  }
+}
+
+size_t bwd_workspace_bytes(int64_t batch, int64_t nq) { return size_t(2) * (batch * nq + kStatPad) * sizeof(float); }
+
+}  // namespace sm100
+
+static bool aligned16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool sm100_f16_backward_supports(const LaunchArgs& a) {
+  if (a.dtype != 0) return false;
+  if (!((a.d == 64 || a.d == 128) && (a.v_d == 64 || a.v_d == 128))) return false;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (nq % 8 || nk % 8) return false;
+  if (!aligned16b(a.q) || !aligned16b(a.k) || !aligned16b(a.v) || !aligned16b(a.d_o) || !aligned16b(a.d_q) ||
+      !aligned16b(a.d_k) || !aligned16b(a.d_v) || !aligned16b(a.o) || !aligned16b(a.workspace))
+    return false;
+  if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
+  if (((nq + 255) / 256) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
+  if (a.workspace_bytes < sm100::bwd_workspace_bytes(a.batch, nq)) return false;
+  return true;
+}
+
+size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) {
+  return sm100::bwd_workspace_bytes(a.batch, a.rule.q.total);
+}
+
+cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream) {
+  if (a.d == 128 && a.v_d == 128) return sm100::launch_bwd<128, 128>(a, stream);
+  if (a.d == 64 && a.v_d == 64) return sm100::launch_bwd<64, 64>(a, stream);
+  if (a.d == 128 && a.v_d == 64) return sm100::launch_bwd<128, 64>(a, stream);
+  return sm100::launch_bwd<64, 128>(a, stream);
+}
+
 }  // namespace fa

@@ -470,7 +470,10 @@ bool sm100_f16_forward_supports(const LaunchArgs& a) {
   return true;
 }
 
-size_t sm100_f16_workspace_bytes(const LaunchArgs&, bool) { return 0; }
+size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a);  // fa_bwd_f16_sm100.cu
+size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
+  return backward ? sm100_f16_bwd_workspace_bytes(a) : 0;
+}
 
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
   if (a.d == 128 && a.v_d == 128) return sm100::launch_fwd<128, 128>(a, stream);
