@@ -274,15 +274,12 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
       const bool ragged = k0 + kBlockN > p.nk;
       mbar_wait(bar_s_full + 8 * i, j & 1);
       tc_fence_after();
-      float s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
-      tmem_wait_ld();
-
+      // attended-column bitmask of this row for this tile (all ones on FULL tiles)
+      uint32_t okm[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      const bool masked = cls != FA_TILE_FULL || ragged;
       if (cls == FA_TILE_SKIP) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c) s[c] = NEG_INF;
-      } else if (cls == FA_TILE_PARTIAL || ragged) {
+        okm[0] = okm[1] = okm[2] = okm[3] = 0u;
+      } else if (masked) {
         if (rule.dims == 1 && rule.rule != 2) {
           // 1-D full/causal: the attended keys of a row are a prefix of the tile
           int limit = k_hi - k0;  // last valid column
@@ -293,22 +290,47 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
             limit = min(limit, jmax - rule.k.base0 - k0);
           }
 #pragma unroll
-          for (int c = 0; c < 128; ++c) s[c] = c <= limit ? s[c] : NEG_INF;
+          for (int c = 0; c < 4; ++c) {
+            const int n = limit + 1 - 32 * c;  // attended columns inside this 32-wide chunk
+            okm[c] = n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+          }
         } else {
           KWalker w;
           w.init(rule, k0);
           const int nvalid = k_hi - k0 + 1;
 #pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            const bool ok = c < nvalid && fa_attend(rule, qpos, w.pos(rule));
-            s[c] = ok ? s[c] : NEG_INF;
-            w.next(rule);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t bits = 0;
+#pragma unroll 8
+            for (int e = 0; e < 32; ++e) {
+              if (c * 32 + e < nvalid && fa_attend(rule, qpos, w.pos(rule))) bits |= 1u << e;
+              w.next(rule);
+            }
+            okm[c] = bits;
           }
         }
       }
-      float mx = s[0];
+      // pass 1: row max over the tile, 32 columns at a time (TMEM reads are cheap; keeping the
+      // whole 128-column row in registers spilled)
+      float mx = NEG_INF;
+      {
+        float a[32], bb[32];
+        tmem_ld32f(t_s, a);
 #pragma unroll
-      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
+        for (int c = 0; c < 4; ++c) {
+          float* cur = (c & 1) ? bb : a;
+          float* nxt = (c & 1) ? a : bb;
+          tmem_wait_ld();
+          if (c + 1 < 4) tmem_ld32f(t_s + (c + 1) * 32, nxt);
+          if (masked) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (okm[c] >> e) & 1u ? cur[e] : NEG_INF);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, cur[e]);
+          }
+        }
+      }
       const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
@@ -332,18 +354,35 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
         }
       }
       const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
-      uint32_t pk[64];
-      float sum = 0.f;
+      // pass 2: P = exp2(S*scale*log2e - m) -> fp16 pairs written over S (P column c never passes
+      // the S columns already consumed: 16(c+1) <= 32(c+1))
+      {
+        float a[32], bb[32];
+        float sum0 = 0.f, sum1 = 0.f;
+        tmem_ld32f(t_s, a);
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = ex2(fmaf(s[c], scale_log2, -m_use));
-        const float p1 = ex2(fmaf(s[c + 1], scale_log2, -m_use));
-        sum += p0 + p1;
-        pk[c >> 1] = pack_half2(p0, p1);
+        for (int c = 0; c < 4; ++c) {
+          float* cur = (c & 1) ? bb : a;
+          float* nxt = (c & 1) ? a : bb;
+          tmem_wait_ld();
+          if (c + 1 < 4) tmem_ld32f(t_s + (c + 1) * 32, nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = ex2(fmaf(cur[e], scale_log2, -m_use));
+            float p1 = ex2(fmaf(cur[e + 1], scale_log2, -m_use));
+            if (masked) {
+              p0 = (okm[c] >> e) & 1u ? p0 : 0.f;
+              p1 = (okm[c] >> (e + 1)) & 1u ? p1 : 0.f;
+            }
+            sum0 += p0;
+            sum1 += p1;
+            pk[e >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st16(t_s + c * 16, pk);
+        }
+        l_sum += sum0 + sum1;
       }
-      l_sum += sum;
-      tmem_st32(t_s, &pk[0]);
-      tmem_st32(t_s + 32, &pk[32]);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * i);
