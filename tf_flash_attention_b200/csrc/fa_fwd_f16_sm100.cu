@@ -15,6 +15,7 @@
 #include "fa_common.cuh"
 #include "fa_launch.h"
 #include "sm100_ptx.cuh"
+#include "sm100_tiles.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -49,46 +50,8 @@ struct FwdCfg {
   static constexpr int kStageBytes = kBlockN * kCh * 2;
   static constexpr int kBarOffset = kQTiles * kQTileBytes + kStages * kStageBytes;
   static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
-  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;  // + alignment slack
-};
-
-// live = not skipped for the union of the CTA's rows
-__device__ __forceinline__ bool tile_live(const FaRule& r, int q_lo, int q_hi, int kt, int nk) {
-  const int k0 = kt * kBlockN;
-  return fa_classify(r, q_lo, q_hi, k0, min(k0 + kBlockN, nk) - 1) != FA_TILE_SKIP;
-}
-
-// incremental walk over the positions of consecutive K entries
-struct KWalker {
-  int32_t x, c0, c1;
-  __device__ __forceinline__ void init(const FaRule& r, int32_t idx) {
-    if (r.dims == 1) {
-      x = idx;
-      c0 = r.k.off0 + (idx + r.k.base0) * r.k.stride0;
-      c1 = 0;
-    } else {
-      int32_t y = idx / r.k.n0;
-      x = idx - y * r.k.n0;
-      c0 = r.k.off0 + x * r.k.stride0;
-      c1 = r.k.off1 + y * r.k.stride1;
-    }
-  }
-  __device__ __forceinline__ FaPos pos(const FaRule& r) const {
-    FaPos p;
-    p.c0 = c0;
-    p.c1 = c1;
-    p.order = (c1 << r.ref_log2_0) + c0;
-    return p;
-  }
-  __device__ __forceinline__ void next(const FaRule& r) {
-    ++x;
-    c0 += r.k.stride0;
-    if (r.dims == 2 && x == r.k.n0) {
-      x = 0;
-      c0 = r.k.off0;
-      c1 += r.k.stride1;
-    }
-  }
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;  // + alignment slack
 };
 
 template <int D, int VD>
@@ -112,13 +75,21 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
 
-  // heavy (late) query rows first, all batch elements of one row block before the next
-  const int pair = p.n_qpairs - 1 - int(blockIdx.x / p.batch);
-  const int b = int(blockIdx.x % p.batch);
+  // CTAs of one batch element are adjacent (its K/V stay L2-resident while ~5 heads are in
+  // flight); inside a head the heavy (late) query rows go first
+  const int b = int(blockIdx.x / p.n_qpairs);
+  const int pair = p.n_qpairs - 1 - int(blockIdx.x % p.n_qpairs);
   const int q0 = pair * (kQTiles * kBlockM);
   const int q_hi = min(q0 + kQTiles * kBlockM, p.nq) - 1;
   int kt_first, kt_last;
   fa_k_tile_range(rule, q0, q_hi, kBlockN, &kt_first, &kt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[2] = {q0, q0 + kBlockM};
+    const int hi[2] = {min(q0 + kBlockM, p.nq) - 1, min(q0 + 2 * kBlockM, p.nq) - 1};
+    const bool valid[2] = {q0 < p.nq, q0 + kBlockM < p.nq};
+    build_schedule(sched, rule, true, lo, hi, valid, 2, kt_first, kt_last, kBlockN, p.nk, kThreads / 32);
+  }
 
   if (warp == 8) {
     if (elect_one()) {
@@ -162,8 +133,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
                         q0 + i * kBlockM + h * 64, b * D);
         }
         int t = 0;
-        for (int kt = kt_first; kt <= kt_last; ++kt) {
-          if (!tile_live(rule, q0, q_hi, kt, p.nk)) continue;
+        TileIter it;
+        it.init(sched, 2, kt_first, kt_last);
+        int kt, tw, tb;
+        while (it.next(&kt, &tw, &tb)) {
           {
             const int s = t % kStages, u = t / kStages;
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
@@ -187,8 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
     } else if (warp == 9) {
       // ===================== MMA issuer =====================
       if (elect_one()) {
-        int n = 0;
-        for (int kt = kt_first; kt <= kt_last; ++kt) n += tile_live(rule, q0, q_hi, kt, p.nk) ? 1 : 0;
+        TileIter it;
+        it.init(sched, 2, kt_first, kt_last);
+        const int n = it.count();
         constexpr uint32_t idesc_qk = idesc_f16(kBlockM, kBlockN, true, true);
         constexpr uint32_t idesc_pv = idesc_f16(kBlockM, VD, false, false);
         auto issue_qk = [&](int i, int stage) {
@@ -266,71 +240,45 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
     float m_true = NEG_INF;  // true running max (log2 units)
     float l_sum = 0.f;
     int j = 0;
-    for (int kt = kt_first; kt <= kt_last; ++kt) {
-      if (!tile_live(rule, q0, q_hi, kt, p.nk)) continue;
+    TileIter it;
+    it.init(sched, 2, kt_first, kt_last);
+    int kt, tw, tb;
+    while (it.next(&kt, &tw, &tb)) {
       const int k0 = kt * kBlockN;
       const int k_hi = min(k0 + kBlockN, p.nk) - 1;
-      const int cls = tile_valid ? fa_classify(rule, tq0, tq_hi, k0, k_hi) : FA_TILE_SKIP;
+      const int cls = it.cls(i, tw, tb);
       const bool ragged = k0 + kBlockN > p.nk;
       mbar_wait(bar_s_full + 8 * i, j & 1);
       tc_fence_after();
-      // attended-column bitmask of this row for this tile (all ones on FULL tiles)
-      uint32_t okm[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      // S row -> registers (one row per thread)
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
+      // attended-column bitmask of this row for this tile (only built for PARTIAL / ragged tiles)
       const bool masked = cls != FA_TILE_FULL || ragged;
-      if (cls == FA_TILE_SKIP) {
-        okm[0] = okm[1] = okm[2] = okm[3] = 0u;
-      } else if (masked) {
-        if (rule.dims == 1 && rule.rule != 2) {
-          // 1-D full/causal: the attended keys of a row are a prefix of the tile
-          int limit = k_hi - k0;  // last valid column
-          if (rule.causal) {
-            // k attended iff k.off + (k0+c+base)*stride <= q.c0
-            const int num = qpos.c0 - rule.k.off0;
-            const int jmax = num < 0 ? -1 : num / rule.k.stride0;  // global k index bound
-            limit = min(limit, jmax - rule.k.base0 - k0);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int n = limit + 1 - 32 * c;  // attended columns inside this 32-wide chunk
-            okm[c] = n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
-          }
-        } else {
-          KWalker w;
-          w.init(rule, k0);
+      if (masked) {
+        uint32_t okm[4] = {0u, 0u, 0u, 0u};
+        if (cls != FA_TILE_SKIP) {
           const int nvalid = k_hi - k0 + 1;
+          if (rule.dims == 1 && rule.rule != 2) {
+            int lo, hi;
+            interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t bits = 0;
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) {
-              if (c * 32 + e < nvalid && fa_attend(rule, qpos, w.pos(rule))) bits |= 1u << e;
-              w.next(rule);
-            }
-            okm[c] = bits;
-          }
-        }
-      }
-      // pass 1: row max over the tile, 32 columns at a time (TMEM reads are cheap; keeping the
-      // whole 128-column row in registers spilled)
-      float mx = NEG_INF;
-      {
-        float a[32], bb[32];
-        tmem_ld32f(t_s, a);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float* cur = (c & 1) ? bb : a;
-          float* nxt = (c & 1) ? a : bb;
-          tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld32f(t_s + (c + 1) * 32, nxt);
-          if (masked) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, (okm[c] >> e) & 1u ? cur[e] : NEG_INF);
+            for (int c = 0; c < 4; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
           } else {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, cur[e]);
+            for (int c = 0; c < 4; ++c) okm[c] = element_mask32(rule, true, qpos, k0, 32 * c, nvalid);
           }
         }
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 128; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
+      } else {
+        tmem_wait_ld();
       }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
       const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
@@ -342,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
           const float alpha = (m_new == NEG_INF) ? 1.f : ex2(m_ref - m_new);
           m_ref = m_new;
           l_sum *= alpha;
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < VD / 32; ++c) {
             float o[32];
             tmem_ld32f(t_o + c * 32, o);
@@ -354,35 +302,22 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
         }
       }
       const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
-      // pass 2: P = exp2(S*scale*log2e - m) -> fp16 pairs written over S (P column c never passes
-      // the S columns already consumed: 16(c+1) <= 32(c+1))
-      {
-        float a[32], bb[32];
-        float sum0 = 0.f, sum1 = 0.f;
-        tmem_ld32f(t_s, a);
+      // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float* cur = (c & 1) ? bb : a;
-          float* nxt = (c & 1) ? a : bb;
-          tmem_wait_ld();
-          if (c + 1 < 4) tmem_ld32f(t_s + (c + 1) * 32, nxt);
-          uint32_t pk[16];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = ex2(fmaf(cur[e], scale_log2, -m_use));
-            float p1 = ex2(fmaf(cur[e + 1], scale_log2, -m_use));
-            if (masked) {
-              p0 = (okm[c] >> e) & 1u ? p0 : 0.f;
-              p1 = (okm[c] >> (e + 1)) & 1u ? p1 : 0.f;
-            }
-            sum0 += p0;
-            sum1 += p1;
-            pk[e >> 1] = pack_half2(p0, p1);
-          }
-          tmem_st16(t_s + c * 16, pk);
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
+          const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
+          sum0 += p0;
+          sum1 += p1;
+          pk[e >> 1] = pack_half2(p0, p1);
         }
-        l_sum += sum0 + sum1;
+        tmem_st16(t_s + c * 16, pk);
       }
+      l_sum += sum0 + sum1;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * i);
