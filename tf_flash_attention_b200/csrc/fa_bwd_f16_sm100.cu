@@ -17,6 +17,7 @@
 #include "fa_common.cuh"
 #include "fa_launch.h"
 #include "sm100_ptx.cuh"
+#include "sm100_tiles.cuh"
 
 namespace fa {
 namespace sm100 {
@@ -74,43 +75,6 @@ __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restr
   }
 }
 
-__device__ __forceinline__ bool block_live(const FaRule& r, int q_lo, int q_hi, int k_lo, int k_hi) {
-  return fa_classify(r, q_lo, q_hi, k_lo, k_hi) != FA_TILE_SKIP;
-}
-
-// incremental walk over consecutive entries of one sequence map
-struct SeqWalker {
-  int32_t x, c0, c1;
-  __device__ __forceinline__ void init(const FaRule& r, const FaSeqMap& s, int32_t idx) {
-    if (r.dims == 1) {
-      x = idx;
-      c0 = s.off0 + (idx + s.base0) * s.stride0;
-      c1 = 0;
-    } else {
-      int32_t y = idx / s.n0;
-      x = idx - y * s.n0;
-      c0 = s.off0 + x * s.stride0;
-      c1 = s.off1 + y * s.stride1;
-    }
-  }
-  __device__ __forceinline__ FaPos pos(const FaRule& r) const {
-    FaPos p;
-    p.c0 = c0;
-    p.c1 = c1;
-    p.order = (c1 << r.ref_log2_0) + c0;
-    return p;
-  }
-  __device__ __forceinline__ void next(const FaRule& r, const FaSeqMap& s) {
-    ++x;
-    c0 += s.stride0;
-    if (r.dims == 2 && x == s.n0) {
-      x = 0;
-      c0 = s.off0;
-      c1 += s.stride1;
-    }
-  }
-};
-
 // =================================================================================================
 // dQ kernel
 // =================================================================================================
@@ -125,7 +89,8 @@ struct DqCfg {
   static constexpr int kRingOffset = 2 * (kQBytes + kDoBytes);
   static constexpr int kBarOffset = kRingOffset + kStages * kStageBytes;
   static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
-  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
 template <int D, int VD>
@@ -151,12 +116,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
-  const int pair = p.n_blocks - 1 - int(blockIdx.x / p.batch);  // heavy (late) rows first
-  const int b = int(blockIdx.x % p.batch);
+  const int b = int(blockIdx.x / p.n_blocks);                     // head-major: K/V stay in L2
+  const int pair = p.n_blocks - 1 - int(blockIdx.x % p.n_blocks);  // heavy (late) rows first
   const int q0 = pair * (2 * kBM);
   const int q_hi = min(q0 + 2 * kBM, p.nq) - 1;
   int kt_first, kt_last;
   fa_k_tile_range(rule, q0, q_hi, kBN, &kt_first, &kt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[2] = {q0, q0 + kBM};
+    const int hi[2] = {min(q0 + kBM, p.nq) - 1, min(q0 + 2 * kBM, p.nq) - 1};
+    const bool valid[2] = {q0 < p.nq, q0 + kBM < p.nq};
+    build_schedule(sched, rule, true, lo, hi, valid, 2, kt_first, kt_last, kBN, p.nk, kBwdThreads / 32);
+  }
 
   if (warp == 8) {
     if (elect_one()) {
@@ -190,11 +162,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_gen;
   // TMEM columns: S_i [i*64, +64)  dP_i [128+i*64, +64)  dQ_i [256+i*128, +D)
 
-  auto live = [&](int kt) {
-    const int k0 = kt * kBN;
-    return block_live(rule, q0, q_hi, k0, min(k0 + kBN, p.nk) - 1);
-  };
-
   if (warp >= 8) {
     setmaxnreg_dec<56>();
     if (warp == 8) {
@@ -209,8 +176,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           }
         }
         int t = 0;
-        for (int kt = kt_first; kt <= kt_last; ++kt) {
-          if (!live(kt)) continue;
+        TileIter it;
+        it.init(sched, 2, kt_first, kt_last);
+        int kt, tw, tb;
+        while (it.next(&kt, &tw, &tb)) {
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
@@ -221,8 +190,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       }
     } else if (warp == 9) {
       if (elect_one()) {
-        int n = 0;
-        for (int kt = kt_first; kt <= kt_last; ++kt) n += live(kt) ? 1 : 0;
+        TileIter it;
+        it.init(sched, 2, kt_first, kt_last);
+        const int n = it.count();
         constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, true, true);
         constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, false);
         auto issue_s_dp = [&](int i, int stage) {
@@ -292,11 +262,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
     const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
     const float scale_log2 = p.scale_log2;
     int j = 0;
-    for (int kt = kt_first; kt <= kt_last; ++kt) {
-      if (!live(kt)) continue;
+    TileIter it;
+    it.init(sched, 2, kt_first, kt_last);
+    int kt, tw, tb;
+    while (it.next(&kt, &tw, &tb)) {
       const int k0 = kt * kBN;
       const int k_hi = min(k0 + kBN, p.nk) - 1;
-      const int cls = tile_valid ? fa_classify(rule, tq0, tq_hi, k0, k_hi) : FA_TILE_SKIP;
+      const int cls = it.cls(i, tw, tb);
       const bool ragged = k0 + kBN > p.nk;
       mbar_wait(bar_s_full + 8 * i, j & 1);
       tc_fence_after();
@@ -305,33 +277,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       tmem_ld32f(t_s + 32, &s[32]);
       tmem_ld32f(t_dp, &dp[0]);
       tmem_ld32f(t_dp + 32, &dp[32]);
-      tmem_wait_ld();
       uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
       if (cls == FA_TILE_SKIP) {
         okmask_lo = okmask_hi = 0u;
       } else if (cls == FA_TILE_PARTIAL || ragged) {
-        uint64_t mk = 0;
+        const int nvalid = k_hi - k0 + 1;
         if (rule.dims == 1 && rule.rule != 2) {
-          int limit = k_hi - k0;
-          if (rule.causal) {
-            const int num = qpos.c0 - rule.k.off0;
-            const int jmax = num < 0 ? -1 : num / rule.k.stride0;
-            limit = min(limit, jmax - rule.k.base0 - k0);
-          }
-          mk = limit < 0 ? 0ull : (limit >= 63 ? ~0ull : ((1ull << (limit + 1)) - 1ull));
+          int lo, hi;
+          interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
+          okmask_lo = interval_bits32(lo, hi, 0);
+          okmask_hi = interval_bits32(lo, hi, 32);
         } else {
-          SeqWalker w;
-          w.init(rule, rule.k, k0);
-          const int nvalid = k_hi - k0 + 1;
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            if (c < nvalid && fa_attend(rule, qpos, w.pos(rule))) mk |= 1ull << c;
-            w.next(rule, rule.k);
-          }
+          okmask_lo = element_mask32(rule, true, qpos, k0, 0, nvalid);
+          okmask_hi = element_mask32(rule, true, qpos, k0, 32, nvalid);
         }
-        okmask_lo = uint32_t(mk);
-        okmask_hi = uint32_t(mk >> 32);
       }
+      tmem_wait_ld();
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
@@ -400,7 +361,8 @@ struct DkvCfg {
   static constexpr int kStatOffset = kRingOffset + kStages * kStageBytes;
   static constexpr int kBarOffset = kStatOffset + kStages * kStatBytes;
   static constexpr int kNumBars = 1 + 2 * kStages + 2 + 2 + 1;
-  static constexpr int kSmemBytes = kBarOffset + kNumBars * 8 + 16 + 1024;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -435,12 +397,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
-  const int kblk = int(blockIdx.x / p.batch);  // early key tiles are the heavy ones under causal
-  const int b = int(blockIdx.x % p.batch);
+  const int b = int(blockIdx.x / p.n_blocks);     // head-major: Q/dO stay in L2
+  const int kblk = int(blockIdx.x % p.n_blocks);  // early key tiles are the heavy ones under causal
   const int k0 = kblk * kBM;
   const int k_hi = min(k0 + kBM, p.nk) - 1;
   int qt_first, qt_last;
   fa_q_tile_range(rule, k0, k_hi, kBN, &qt_first, &qt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {k0};
+    const int hi[1] = {k_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, false, lo, hi, valid, 1, qt_first, qt_last, kBN, p.nq, kBwdThreads / 32);
+  }
 
   if (warp == 8) {
     if (elect_one()) {
@@ -475,11 +444,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot_gen;
   // TMEM columns: S^T_x [x*64, +64)  dP^T_x [128+x*64, +64)  dV [256, +VD)  dK [384, +D)
 
-  auto live = [&](int qt) {
-    const int q0 = qt * kBN;
-    return block_live(rule, q0, min(q0 + kBN, p.nq) - 1, k0, k_hi);
-  };
-
   if (warp >= 8) {
     setmaxnreg_dec<56>();
     if (warp == 8) {
@@ -490,8 +454,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
         }
         int t = 0;
-        for (int qt = qt_first; qt <= qt_last; ++qt) {
-          if (!live(qt)) continue;
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        int qt, tw, tb;
+        while (it.next(&qt, &tw, &tb)) {
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
@@ -505,8 +471,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       }
     } else if (warp == 9) {
       if (elect_one()) {
-        int n = 0;
-        for (int qt = qt_first; qt <= qt_last; ++qt) n += live(qt) ? 1 : 0;
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        const int n = it.count();
         constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
         constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
         constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
@@ -570,8 +537,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
     const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
     const float scale_log2 = p.scale_log2;
     int t = 0;   // index over live sub-tiles (all), this WG handles those with (t & 1) == x
-    for (int qt = qt_first; qt <= qt_last; ++qt) {
-      if (!live(qt)) continue;
+    TileIter it;
+    it.init(sched, 1, qt_first, qt_last);
+    int qt, tw, tb;
+    while (it.next(&qt, &tw, &tb)) {
       if ((t & 1) != x) {
         ++t;
         continue;
@@ -579,7 +548,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       const int st = t % kStages;
       const int q0 = qt * kBN;
       const int q_hi = min(q0 + kBN, p.nq) - 1;
-      const int cls = fa_classify(rule, q0, q_hi, k0, k_hi);
+      const int cls = it.cls(0, tw, tb);
       const bool ragged = (q0 + kBN > p.nq) || (k0 + kBM > p.nk);
       mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
       mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
@@ -589,39 +558,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       tmem_ld32f(t_s + 32, &s[32]);
       tmem_ld32f(t_dp, &dp[0]);
       tmem_ld32f(t_dp + 32, &dp[32]);
-      tmem_wait_ld();
-      uint64_t mk = ~0ull;
+      uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
       if (cls == FA_TILE_PARTIAL || ragged) {
-        mk = 0;
+        okmask_lo = okmask_hi = 0u;
         if (k_valid) {
           const int nvalid = q_hi - q0 + 1;
           if (rule.dims == 1 && rule.rule != 2) {
-            int cmin = 0;
-            if (rule.causal) {
-              // q attended iff q.off + (q0+c+base)*stride >= k.c0
-              const int num = kpos.c0 - rule.q.off0;
-              const int jmin = num <= 0 ? 0 : (num + rule.q.stride0 - 1) / rule.q.stride0;  // global q index
-              cmin = max(0, jmin - rule.q.base0 - q0);
-            }
-            const uint64_t upto = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
-            const uint64_t below = cmin >= 64 ? ~0ull : ((1ull << cmin) - 1ull);
-            mk = upto & ~below;
+            int lo, hi;
+            interval_1d(rule, false, kpos, q0, nvalid, &lo, &hi);
+            okmask_lo = interval_bits32(lo, hi, 0);
+            okmask_hi = interval_bits32(lo, hi, 32);
           } else {
-            SeqWalker w;
-            w.init(rule, rule.q, q0);
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-              if (c < nvalid && fa_attend(rule, w.pos(rule), kpos)) mk |= 1ull << c;
-              w.next(rule, rule.q);
-            }
+            okmask_lo = element_mask32(rule, false, kpos, q0, 0, nvalid);
+            okmask_hi = element_mask32(rule, false, kpos, q0, 32, nvalid);
           }
         }
       }
-      const uint32_t okmask_lo = uint32_t(mk), okmask_hi = uint32_t(mk >> 32);
-      const float2* stats = reinterpret_cast<const float2*>(stat_gen + st * (2 * kBN));
+      tmem_wait_ld();
       const float* lse_s = stat_gen + st * (2 * kBN);
       const float* dsum_s = lse_s + kBN;
-      (void)stats;
       uint32_t pk[32], dk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {

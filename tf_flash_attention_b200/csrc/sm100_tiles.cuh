@@ -134,7 +134,7 @@ struct SeqWalker {
 // 32-bit attended mask of columns [col0, col0+32) of a streamed tile starting at stream index s0,
 // for one fixed resident position. Generic (any rule / dims); kept out of line so that the big
 // unrolled softmax loops stay small in the instruction cache.
-__device__ __noinline__ uint32_t element_mask32(const FaRule& rule, bool resident_is_q, FaPos res, int s0,
+static __device__ __noinline__ uint32_t element_mask32(const FaRule& rule, bool resident_is_q, FaPos res, int s0,
                                                int col0, int nvalid) {
   const FaSeqMap& sm = resident_is_q ? rule.k : rule.q;
   SeqWalker w;
