@@ -166,3 +166,24 @@ def test_no_cpu_fallback():
     x = np.zeros((1, 8, 16), dtype=np.float32)
     with pytest.raises(_capi.FlashAttentionError):
         fa.full_1d(x, x, x)
+
+
+def test_estimate_forward_flops_matches_reference():
+    """fa_estimate_forward_flops against the reference's own EstimateForwardFlops (golden values
+    produced by tests/golden/make_flops_golden.py from oracle/_ref/libref_fa.so): bit-identical."""
+    import json
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "flops_golden.json")))
+    assert len(cases) >= 60
+    for c in cases:
+        qs, ks = tuple(c["q_shape"]), tuple(c["k_shape"])
+        p = _capi.make_problem(c["dtype"], c["dims"], c["rule"], c["sync_mode"], (c["batch"], c["d"]) + qs,
+                               (c["batch"], c["d"]) + ks, (c["batch"], c["v_d"]) + ks, c["window_size"],
+                               c["log2_stride_size"], c["is_causal"])
+        assert _capi.estimate_forward_flops(p, c["smem"]) == c["flops"], c
+    dt = {0: np.float16, 1: np.float32, 2: np.float64}
+    c = cases[0]
+    got = fa.estimate_forward_flops(c["dims"], c["rule"], (c["batch"], c["d"]) + tuple(c["q_shape"]),
+                                    (c["batch"], c["d"]) + tuple(c["k_shape"]),
+                                    (c["batch"], c["v_d"]) + tuple(c["k_shape"]), dt[c["dtype"]], c["sync_mode"],
+                                    c["window_size"], c["log2_stride_size"], c["is_causal"])
+    assert got == c["flops"]

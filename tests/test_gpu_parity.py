@@ -7,6 +7,8 @@ the oracle finishes in seconds) with the BASELINE.json tolerances: max-abs 2e-3 
 
 fp16 note: an fp16 *output* cannot carry 2e-3 absolute once |x| >= 4 (half-ulp
 there is 3.9e-3), so for fp16 gradients the bound is applied as |err| <= 2e-3 * max(1, |ref|)."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -108,7 +110,7 @@ def _random_shapes(rng, dims, dtype):
 @pytest.mark.parametrize("dims", [1, 2])
 def test_reference_matrix_random_shapes(dims, attn, sync_mode, dtype):
     cfg = ATTN[attn]
-    seed = hash((dims, attn, sync_mode, np.dtype(dtype).name)) % (2 ** 31)
+    seed = zlib.crc32(f"{dims}-{attn}-{sync_mode}-{np.dtype(dtype).name}".encode()) % (2 ** 31)
     rng = np.random.default_rng(seed)
     for run in range(2):
         batch, d, qs, ks = _random_shapes(rng, dims, dtype)
