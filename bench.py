@@ -44,6 +44,9 @@ WORKLOADS = {
     "C4": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp16 head_dim 64, 256 heads", seq_dims=1,
                dtype="float16", batch=(16, 16), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
                sync="scale_end", w=1, s=0, c=0),
+    "C5": dict(desc="causal_1d fp16 single sequence 131072, head_dim 128, 16 heads, K/V ring over NCCL (fwd)",
+               seq_dims=1, dtype="float16", batch=(1, 16), d=128, v_d=128, q=(131072,), k=(131072,), rule="causal",
+               sync="none_front", w=1, s=0, c=0, ring=True),
 }
 
 
@@ -126,6 +129,65 @@ def cpu_reference_leg(w, nnz, steps, warmup, heads):
                       f"{sec:.2f} s per step", "sec_per_step": sec}
 
 
+def ring_bench(args, w, nnz, config, rank, world, local_rank):
+    """C5: one causal sequence of 131072 sharded zig-zag over the ranks; STRONG scaling (total work fixed).
+    Forward only (the ring backward is a later row of SURVEY.md section 8f)."""
+    import torch
+    import torch.distributed as dist
+    from tf_flash_attention_b200 import _capi, ring
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S = w["q"][0]
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    shard = S // world
+
+    def u(ch):
+        return (torch.rand(w["batch"] + (ch, shard), generator=g, device=dev) * 4 - 2).half()
+    Q, K, V = u(w["d"]), u(w["d"]), u(w["v_d"])
+    for _ in range(max(3, args.warmup)):
+        ring.ring_causal_1d(Q, K, V)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    _capi.lib.fa_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ring.ring_causal_1d(Q, K, V)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = int(_capi.lib.fa_launch_count(0))
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    fwd_flops = 2.0 * nnz * (w["d"] + w["v_d"]) * int(np.prod(w["batch"]))
+    value = fwd_flops / (ms * 1e-3) / 1e12
+    peaks = measured_peaks()
+    peak = (peaks["tensor_sustained"] or peaks["tensor_burst"]) * world
+    config = dict(config, flops_per_step=fwd_flops, parallelism=f"K/V ring, zig-zag chunks, {world} rank(s), NCCL send/recv")
+    config["pass"] = "fwd"
+    line = {"metric": "attention fwd TFLOPS (unmasked FLOPs), single sequence K/V ring", "value": value, "unit": "TFLOPS",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
+            "data": "synthetic U(-2,2)", "config": config, "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "fwd_f16_sm100 (per-block partials) + partial_merge",
+                         "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak, "traffic": None,
+                         "peak_source": peaks["source"] + f", sustained bf16 GEMM x {world} GPUs"}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,6 +236,9 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
+
+    if w.get("ring"):
+        return ring_bench(args, w, nnz, config, rank, world, local_rank)
 
     # ---------------- our arm -------------------------------------------------------------------
     import torch

@@ -118,6 +118,18 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward);
  * B200's 232448). Host only; writes *flops. */
 int fa_estimate_forward_flops(const fa_problem_t* p, int32_t shared_mem_bytes, float* flops);
 
+/* ---- partial results over disjoint key shards (K/V ring; new, the reference is single-GPU) ----- */
+
+/* Folds the partial result of one key shard (o_part, l_part, m_part exactly as fa_forward wrote
+ * them for problem *p) into running accumulators with the online-softmax algebra:
+ *   o_acc [batch, v_d, q], l_acc [batch, q], m_acc [batch, q]   float (double for FA_F64);
+ * o_acc is unnormalised (sum of exp(s - m_acc) * v). first != 0 initialises the accumulators. */
+int fa_partial_merge(const fa_problem_t* p, const void* o_part, const void* l_part, const void* m_part,
+                     void* o_acc, void* l_acc, void* m_acc, int first, void* stream);
+/* Emits O = o_acc / l_acc, l, m in the reference's output contract (sentinel on empty rows). */
+int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_acc, const void* m_acc,
+                        void* o, void* l, void* m, void* stream);
+
 /* ---- host-side helpers shared with the kernels (same code, fa_rules.h) ---------- */
 
 /* Number of attended (q,k) pairs per batch element under the bit-exact rule; the unit

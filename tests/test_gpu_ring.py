@@ -1,0 +1,27 @@
+"""GPU test of the K/V-ring product backend (C ABI: fa_forward with global index bases,
+fa_partial_merge, fa_partial_finalize). On one GPU the ring has a single rank that owns both chunks;
+the multi-rank exchange is covered on CPU by tests/test_ring_gloo.py and on 2+ GPUs by
+tools/ring_check.py under torchrun."""
+import numpy as np
+import pytest
+
+from oracle import dense_attention as da
+from tests.helpers import max_abs_err
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+from tf_flash_attention_b200 import _capi, ring  # noqa: E402
+
+
+@pytest.mark.parametrize("dtype,d,seq,tol", [(np.float16, 128, 2048, 2e-3), (np.float16, 64, 512, 2e-3),
+                                              (np.float32, 32, 384, 1e-5), (np.float64, 16, 256, 1e-12)])
+def test_single_rank_ring_equals_plain_causal(dtype, d, seq, tol):
+    rng = np.random.default_rng(3)
+    Q, K, V, _ = da.random_inputs(rng, dtype, (2, 2), d, d, (seq,), (seq,))
+    ref = da.attention(Q, K, V, 1, "causal", "none_front")
+    O, l, m = ring.ring_causal_1d(*(torch.from_numpy(x).cuda() for x in (Q, K, V)), returning_l_m=True)
+    assert max_abs_err(O.cpu().numpy(), ref["O"]) <= tol
+    lse = m.cpu().numpy().astype(np.float64) + np.log(l.cpu().numpy().astype(np.float64))
+    assert np.max(np.abs(lse - (ref["m"] + np.log(ref["l"])))) <= max(2e-2 if dtype == np.float16 else tol * 10, tol)
+    if dtype == np.float16:
+        assert _capi.lib.fa_last_path() == 2  # partial blocks ran on the tcgen05 kernel

@@ -1,0 +1,123 @@
+"""N > 1 host logic on CPU: the K/V ring driver (tf_flash_attention_b200/ring.py: zig-zag chunk
+ownership, per-step block plan, global index bases, double-buffered send/recv) run with world_size 2
+and 4 over the gloo backend. The compute stand-in is the NumPy oracle (test code only); the product
+backend (DeviceBackend -> C ABI) is exercised on GPUs by tests/test_gpu_ring.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dense_attention as da
+from oracle import pattern
+from tf_flash_attention_b200 import ring
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class OracleBackend:
+    """NumPy stand-in with the same interface as ring.DeviceBackend (float64 CPU tensors)."""
+
+    def __init__(self, batch, d, v_d, chunk):
+        self.batch, self.d, self.v_d, self.chunk = batch, d, v_d, chunk
+
+    def new_acc(self, like_q):
+        return [torch.zeros(self.batch, self.v_d, self.chunk, dtype=torch.float64),
+                torch.zeros(self.batch, self.chunk, dtype=torch.float64),
+                torch.full((self.batch, self.chunk), -np.inf, dtype=torch.float64)]
+
+    def new_out(self, like_q):
+        return self.new_acc(like_q)
+
+    def empty_like_kv(self, kv):
+        return [torch.empty_like(x) for x in kv]
+
+    def attend_partial(self, q, k, v, q_base, k_base, out):
+        qi = q_base + np.arange(self.chunk)
+        kj = k_base + np.arange(self.chunk)
+        mask = qi[:, None] >= kj[None, :]
+        O, l, m = da.forward(q.numpy(), k.numpy(), v.numpy(), mask)
+        out[0].copy_(torch.from_numpy(O)); out[1].copy_(torch.from_numpy(l)); out[2].copy_(torch.from_numpy(m))
+
+    def merge(self, part, acc, first):
+        o, l, m = (x.numpy() for x in part)
+        oa, la, ma = (x.numpy() for x in acc)
+        if first:
+            oa[...] = 0; la[...] = 0; ma[...] = -np.inf
+        m_new = np.maximum(ma, m)
+        safe = np.where(np.isfinite(m_new), m_new, 0.0)
+        wa = np.where(np.isfinite(ma), np.exp(ma - safe), 0.0)
+        wp = np.where(np.isfinite(m), np.exp(m - safe) * l, 0.0)
+        oa[...] = oa * wa[:, None, :] + o * wp[:, None, :]
+        la[...] = la * wa + wp
+        ma[...] = m_new
+
+    def finalize(self, acc, out):
+        oa, la, ma = acc
+        out[0].copy_(oa / torch.where(la > 0, la, torch.ones_like(la))[:, None, :])
+        out[1].copy_(la); out[2].copy_(ma)
+
+
+def _worker(rank, world, port, seq, d, v_d, batch, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)  # same full tensors on every rank
+    Q, K, V, _ = da.random_inputs(rng, np.float64, (batch,), d, v_d, (seq,), (seq,))
+    layout = ring.ZigZag(seq, world)
+    idx = layout.gather_index(rank)
+    c = layout.chunk
+    qs = [torch.from_numpy(np.ascontiguousarray(Q[:, :, idx[:c]])), torch.from_numpy(np.ascontiguousarray(Q[:, :, idx[c:]]))]
+    kv = [torch.from_numpy(np.ascontiguousarray(X[:, :, sl])) for X in (K, V) for sl in (idx[:c], idx[c:])]
+    outs = ring.ring_forward(OracleBackend(batch, d, v_d, c), layout, rank, qs, kv, dist, None, "causal")
+    O = np.concatenate([outs[0][0].numpy(), outs[1][0].numpy()], axis=-1)
+    ref = da.forward(Q, K, V, pattern.tests_mask((seq,), (seq,), "none_front", "causal"))[0][:, :, idx]
+    np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array([np.abs(O - ref).max()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ring_driver_matches_dense_oracle(world, tmp_path):
+    seq = 16 * world
+    mp.spawn(_worker, args=(world, _free_port(), seq, 8, 6, 2, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert float(np.load(tmp_path / f"err_{r}.npy")[0]) < 1e-12
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_step_plan_covers_the_causal_triangle_once(world):
+    layout = ring.ZigZag(64 * world, world)
+    seen = {}
+    per_rank_blocks = []
+    for rank in range(world):
+        n = 0
+        for step in range(world):
+            src, plan = ring.step_plan(layout, rank, step, "causal", False)
+            for qa, kb, qb, kb_base in plan:
+                key = (qb // layout.chunk, kb_base // layout.chunk)
+                assert key not in seen
+                seen[key] = (rank, step)
+                n += 1
+        per_rank_blocks.append(n)
+    want = {(a, b) for a in range(2 * world) for b in range(2 * world) if b <= a}
+    assert set(seen) == want
+    # zig-zag balance: every rank launches the same number of blocks
+    assert len(set(per_rank_blocks)) == 1
+    # ownership is a partition of the sequence
+    allidx = np.sort(np.concatenate([layout.gather_index(r) for r in range(world)]))
+    assert np.array_equal(allidx, np.arange(64 * world))
+
+
+def test_batch_head_sharding_is_embarrassingly_parallel():
+    """bench.py --gpus N gives every rank the same independent batch; nothing to exchange. This pins the
+    host-side invariant the scaling number relies on: flops are additive over ranks."""
+    from bench import WORKLOADS, flops_of
+    w = WORKLOADS["C2"]
+    f1 = sum(flops_of(w, 33558528))
+    assert abs(f1 - (4.398583382016e12 + 10.99645845504e12)) / f1 < 1e-9

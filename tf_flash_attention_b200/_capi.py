@@ -82,6 +82,8 @@ def _load():
         "fa_host_arena_bytes": (sz, [PP, C.c_int]),
         "fa_forward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "fa_partial_merge": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
+        "fa_partial_finalize": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp]),
         "fa_strerror": (C.c_char_p, [C.c_int]),
         "fa_last_cuda_error": (C.c_int, []),
         "fa_last_path": (C.c_int, []),

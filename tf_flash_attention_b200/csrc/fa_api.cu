@@ -189,6 +189,29 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   return e == cudaSuccess ? FA_OK : cuda_fail(e);
 }
 
+// ---- partial results over key shards (K/V ring) -------------------------------------------------
+int fa_partial_merge(const fa_problem_t* p, const void* o_part, const void* l_part, const void* m_part,
+                     void* o_acc, void* l_acc, void* m_acc, int first, void* stream) {
+  fa::LaunchArgs a{};
+  int rc = fill_args(p, &a);
+  if (rc) return rc;
+  if (p->batch == 0) return FA_OK;
+  if (!o_part || !l_part || !m_part || !o_acc || !l_acc || !m_acc) return FA_EINVAL_NULL;
+  cudaError_t e = fa::partial_merge(a, o_part, l_part, m_part, o_acc, l_acc, m_acc, first, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
+int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_acc, const void* m_acc, void* o,
+                        void* l, void* m, void* stream) {
+  fa::LaunchArgs a{};
+  int rc = fill_args(p, &a);
+  if (rc) return rc;
+  if (p->batch == 0) return FA_OK;
+  if (!o_acc || !l_acc || !m_acc || !o || !l || !m) return FA_EINVAL_NULL;
+  cudaError_t e = fa::partial_finalize(a, o_acc, l_acc, m_acc, o, l, m, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
 // ---- host helpers on the shared rule code ---------------------------------------------------
 
 int fa_count_attended(const fa_problem_t* p, int64_t* nnz) {

@@ -42,6 +42,12 @@ size_t generic_workspace_bytes(int dtype, int64_t batch, int64_t nq, bool backwa
 cudaError_t generic_forward(const LaunchArgs& a, cudaStream_t stream);
 cudaError_t generic_backward(const LaunchArgs& a, cudaStream_t stream);
 
+// partial-result algebra for K/V-ring sharding (fa_partial.cu)
+cudaError_t partial_merge(const LaunchArgs& a, const void* o_part, const void* l_part, const void* m_part,
+                          void* o_acc, void* l_acc, void* m_acc, int first, cudaStream_t stream);
+cudaError_t partial_finalize(const LaunchArgs& a, const void* o_acc, const void* l_acc, const void* m_acc, void* o,
+                             void* l, void* m, cudaStream_t stream);
+
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);
 bool sm100_f16_backward_supports(const LaunchArgs& a);
