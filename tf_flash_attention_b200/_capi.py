@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.abspath(os.path.dirname(__file__))
-LIB_PATH = os.path.join(_HERE, "libfa_b200.so")
+LIB_PATH = os.environ.get("FA_B200_LIB") or os.path.join(_HERE, "libfa_b200.so")  # env override: developer A/B builds
 
 FA_F16, FA_F32, FA_F64 = 0, 1, 2
 RULES = {"full": 0, "causal": 1, "local": 2}

@@ -272,11 +272,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       const bool ragged = k0 + kBN > p.nk;
       mbar_wait(bar_s_full + 8 * i, j & 1);
       tc_fence_after();
-      float s[64], dp[64];
-      tmem_ld32f(t_s, &s[0]);
-      tmem_ld32f(t_s + 32, &s[32]);
-      tmem_ld32f(t_dp, &dp[0]);
-      tmem_ld32f(t_dp + 32, &dp[32]);
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
       uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
       if (cls == FA_TILE_SKIP) {
         okmask_lo = okmask_hi = 0u;
@@ -292,6 +288,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           okmask_hi = element_mask32(rule, true, qpos, k0, 32, nvalid);
         }
       }
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_dp, &dp[0]);
+      tmem_ld32f(t_dp + 32, &dp[32]);
       tmem_wait_ld();
       uint32_t pk[32];
 #pragma unroll
@@ -553,11 +554,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
       mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
       tc_fence_after();
-      float s[64], dp[64];
-      tmem_ld32f(t_s, &s[0]);
-      tmem_ld32f(t_s + 32, &s[32]);
-      tmem_ld32f(t_dp, &dp[0]);
-      tmem_ld32f(t_dp + 32, &dp[32]);
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
       uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
       if (cls == FA_TILE_PARTIAL || ragged) {
         okmask_lo = okmask_hi = 0u;
@@ -574,6 +571,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           }
         }
       }
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_dp, &dp[0]);
+      tmem_ld32f(t_dp + 32, &dp[32]);
       tmem_wait_ld();
       const float* lse_s = stat_gen + st * (2 * kBN);
       const float* dsum_s = lse_s + kBN;

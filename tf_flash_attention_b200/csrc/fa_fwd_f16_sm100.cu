@@ -43,6 +43,17 @@ struct alignas(64) FwdParams {
   float scale_log2;
 };
 
+#ifdef FA_DBG_TIMELINE
+// developer-only (tools/timeline.py): clock64 stamps of CTA 0 -> g_dbg[role][j][event]
+__device__ long long* g_dbg = nullptr;
+#define FA_STAMP(role, j, ev)                                                     \
+  do {                                                                            \
+    if (g_dbg && blockIdx.x == 0 && (j) < 128) g_dbg[((role) * 128 + (j)) * 4 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FA_STAMP(role, j, ev)
+#endif
+
 template <int D, int VD>
 struct FwdCfg {
   static constexpr int kCh = D > VD ? D : VD;
@@ -202,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
             for (int i = 0; i < kQTiles; ++i) {
               mbar_wait(bar_p_ready + 8 * i, j & 1);
               tc_fence_after();
+              FA_STAMP(2 + i, j, 0);
               issue_pv(i, sv, j > 0);
               if (i == kQTiles - 1) mma_commit(bar_kv_empty + 8 * sv);
               if (j + 1 < n) {
@@ -211,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
                 }
                 issue_qk(i, sk);
                 mma_commit(bar_s_full + 8 * i);
+                FA_STAMP(2 + i, j, 1);
                 if (i == kQTiles - 1) mma_commit(bar_kv_empty + 8 * sk);
               } else {
                 mma_commit(bar_o_final + 8 * i);
@@ -250,32 +263,35 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
       const bool ragged = k0 + kBlockN > p.nk;
       mbar_wait(bar_s_full + 8 * i, j & 1);
       tc_fence_after();
+      if (r == 0) FA_STAMP(i, j, 0);
+      // attended-column bitmask of this row for this tile (only built for PARTIAL / ragged tiles).
+      // Built BEFORE the TMEM load is issued: nothing that could make the compiler move or spill the
+      // destination registers (e.g. the out-of-line mask builder) may sit between tcgen05.ld and
+      // tcgen05.wait::ld.
+      const bool masked = cls != FA_TILE_FULL || ragged;
+      uint32_t okm[4] = {0u, 0u, 0u, 0u};
+      if (masked && cls != FA_TILE_SKIP) {
+        const int nvalid = k_hi - k0 + 1;
+        if (rule.dims == 1 && rule.rule != 2) {
+          int lo, hi;
+          interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) okm[c] = element_mask32(rule, true, qpos, k0, 32 * c, nvalid);
+        }
+      }
       // S row -> registers (one row per thread)
       float s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
-      // attended-column bitmask of this row for this tile (only built for PARTIAL / ragged tiles)
-      const bool masked = cls != FA_TILE_FULL || ragged;
+      tmem_wait_ld();
       if (masked) {
-        uint32_t okm[4] = {0u, 0u, 0u, 0u};
-        if (cls != FA_TILE_SKIP) {
-          const int nvalid = k_hi - k0 + 1;
-          if (rule.dims == 1 && rule.rule != 2) {
-            int lo, hi;
-            interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) okm[c] = element_mask32(rule, true, qpos, k0, 32 * c, nvalid);
-          }
-        }
-        tmem_wait_ld();
 #pragma unroll
         for (int c = 0; c < 128; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
-      } else {
-        tmem_wait_ld();
       }
+      if (r == 0) FA_STAMP(i, j, 1);
       float mx = s[0];
 #pragma unroll
       for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
@@ -318,9 +334,11 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
         tmem_st16(t_s + c * 16, pk);
       }
       l_sum += sum0 + sum1;
+      if (r == 0) FA_STAMP(i, j, 2);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * i);
+      if (r == 0) FA_STAMP(i, j, 3);
       ++j;
     }
 
@@ -428,6 +446,9 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+#ifdef FA_DBG_TIMELINE
+extern "C" void fa_debug_set_buffer(void* buf) { cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)); }
+#endif
 }  // namespace sm100
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

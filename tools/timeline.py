@@ -1,0 +1,27 @@
+"""Developer tool: dump the per-event clock stamps of CTA 0 of the fwd kernel (FA_DBG_TIMELINE build)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tf_flash_attention_b200 import _capi, flash_attention as fa
+buf = torch.zeros(4 * 128 * 4, dtype=torch.int64, device="cuda")
+_capi.lib.fa_debug_set_buffer.argtypes = [C.c_void_p]
+_capi.lib.fa_debug_set_buffer(buf.data_ptr())
+B, d, S = 8, 128, 8192
+g = torch.Generator(device="cuda").manual_seed(0)
+Q, K, V = ((torch.rand((B, d, S), generator=g, device="cuda") * 4 - 2).half() for _ in range(3))
+for _ in range(3):
+    fa.causal_1d(Q, K, V, "none_front")
+torch.cuda.synchronize()
+t = buf.cpu().numpy().reshape(4, 128, 4)
+t0 = t[t > 0].min()
+names = ["WG0 S seen", "WG0 ld done", "WG0 exps done", "WG0 arrived", "WG1 S seen", "WG1 ld done", "WG1 exps done", "WG1 arrived", "MMA p0 seen", "MMA qk0 iss", "MMA p1 seen", "MMA qk1 iss"]
+print("j  " + " ".join(f"{n:>13s}" for n in names))
+for j in range(16, 40):
+    row = list(t[0, j]) + list(t[1, j]) + [t[2, j, 0], t[2, j, 1], t[3, j, 0], t[3, j, 1]]
+    print(f"{j:2d} " + " ".join(f"{(int(v) - int(t0)) if v else -1:13d}" for v in row))
+d = t[0, 2:60]
+print("WG0 avg: S->ld", (d[:, 1] - d[:, 0]).mean(), " ld->exps", (d[:, 2] - d[:, 1]).mean(), " exps->arrive", (d[:, 3] - d[:, 2]).mean(), " period", np.diff(d[:, 0]).mean())
+d = t[1, 2:60]
+print("WG1 avg: S->ld", (d[:, 1] - d[:, 0]).mean(), " ld->exps", (d[:, 2] - d[:, 1]).mean(), " exps->arrive", (d[:, 3] - d[:, 2]).mean())
+m0, m1 = t[2, 2:60], t[3, 2:60]
+print("MMA avg: p0 seen -> qk0 issued", (m0[:, 1] - m0[:, 0]).mean(), " p1 seen -> qk1 issued", (m1[:, 1] - m1[:, 0]).mean(), " WG0 arrive -> MMA sees", (m0[:, 0] - t[0, 2:60, 3]).mean(), " qk0 issued -> WG0 sees next S", (t[0, 3:61, 0] - m0[:, 1]).mean())
