@@ -50,6 +50,11 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per launch measured with `ncu --set full` on the GPU (profiles/r1_*_ncu*.md); bench.py cannot
+# run under a profiler, so the captured values are carried here for the workload they were taken on.
+NCU_TRAFFIC = {("C2", "fwd"): 2.153e9, ("C2", "bwd"): 6.98e9}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -328,21 +333,24 @@ def main():
                for n, v in per.items()}
     peaks = measured_peaks()
     roofline = None
+    traffic = None
     if kernels:
         dom = max(kernels, key=lambda n: kernels[n]["share"])
         bwd_names = [n for n in kernels if "bwd" in n]
         if dom in ("fwd_f16_sm100", "generic_fwd"):
             ach = fwd_flops / (kernels[dom]["avg_ms"] * 1e-3) / 1e12
             what = f"{dom}: 2*nnz*(d+v_d)*batch FLOPs per launch"
+            traffic = NCU_TRAFFIC.get((args.workload, "fwd"))
         else:
             # the backward kernels are reported together: algorithmic bwd FLOPs / sum of their durations
             tb = sum(kernels[n]["avg_ms"] for n in bwd_names)
             ach = bwd_flops / (tb * 1e-3) / 1e12
             dom = "+".join(sorted(bwd_names))
             what = f"{dom}: 2*nnz*(3d+2v_d)*batch FLOPs per backward pass"
+            traffic = NCU_TRAFFIC.get((args.workload, "bwd"))
         peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_ncu.md" if traffic else None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
                     "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic": what}
         if "fwd_f16_sm100" in kernels:
