@@ -67,18 +67,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region. nvidia-smi is started
+    early (before the warm-up) because its start-up can take longer than a short timed region; only the
+    rows read between mark_start() and mark_end() are used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def launch(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -87,16 +90,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def start(self):
+        if self.proc is None:
+            self.launch()
+        self.t0 = time.time()
 
     def stop(self):
+        self.t1 = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if self.t0 <= t <= self.t1 + 0.05]
+        if not rows:  # timed region shorter than one sampling period: take the closest sample after it
+            rows = [r for (t, r) in self.rows if t >= self.t0][:1]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -151,10 +163,11 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
     def u(ch):
         return (torch.rand(w["batch"] + (ch, shard), generator=g, device=dev) * 4 - 2).half()
     Q, K, V = u(w["d"]), u(w["d"]), u(w["v_d"])
+    sampler = ClockSampler(local_rank)
+    sampler.launch()
     for _ in range(max(3, args.warmup)):
         ring.ring_causal_1d(Q, K, V)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -285,6 +298,8 @@ def main():
         if not args.fwd_only:
             bwd()
 
+    sampler = ClockSampler(local_rank)
+    sampler.launch()
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
@@ -298,7 +313,6 @@ def main():
     torch.cuda.synchronize()
 
     # timed region: exactly K steps, CUDA events on the launching stream, barrier + sync both sides
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
