@@ -140,6 +140,10 @@ int fa_count_attended(const fa_problem_t* p, int64_t* nnz);
  * very same inline functions the kernels use. For tests / debugging. */
 int fa_pattern_mask(const fa_problem_t* p, uint8_t* mask);
 
+/* The same pattern assembled from the closed-form 32-column masks the tcgen05 kernels build per tile
+ * (queries resident: forward / dQ kernels; keys resident: dK/dV kernel). For tests.               */
+int fa_pattern_mask_fast(const fa_problem_t* p, int32_t tile, int32_t resident_is_q, uint8_t* mask);
+
 /* Orders of the Q and K entries in the shared power-of-two reference grid
  * (sync_methods.h:56-85); q_order[q], k_order[k], ref_shape[seq_dims] innermost first. */
 int fa_orders(const fa_problem_t* p, int32_t* q_order, int32_t* k_order, int32_t* ref_shape);

@@ -187,3 +187,31 @@ def test_estimate_forward_flops_matches_reference():
                                     (c["batch"], c["v_d"]) + tuple(c["k_shape"]), dt[c["dtype"]], c["sync_mode"],
                                     c["window_size"], c["log2_stride_size"], c["is_causal"])
     assert got == c["flops"]
+
+
+@pytest.mark.parametrize("tile,resident_is_q", [(64, 1), (128, 1), (64, 0)])
+def test_closed_form_tile_masks_match_reference(tile, resident_is_q):
+    """The 32-column masks the tcgen05 kernels build per PARTIAL tile (fa_fast_mask32: intervals per grid row
+    instead of 32 evaluations of the element rule) reproduce the reference pattern bit for bit, with
+    queries resident (forward / dQ kernels) and with keys resident (dK/dV kernel)."""
+    n = 0
+    for c in CASES:
+        if c["rule"] == "local" and c["log2_stride_size"] != 0:
+            continue  # strided windows use the element rule in the kernels as well
+        assert np.array_equal(_capi.pattern_mask_fast(_problem(c), tile, resident_is_q), c["mask"]), case_id(c)
+        n += 1
+    assert n >= 40
+    rng = np.random.default_rng(tile + resident_is_q)
+    for _ in range(150):
+        dims = int(rng.integers(1, 3))
+        if dims == 1:
+            qs, ks = (int(rng.integers(1, 300)),), (int(rng.integers(1, 300)),)
+        else:
+            qs = (int(rng.integers(1, 12)), int(rng.integers(1, 70)))
+            ks = (int(rng.integers(1, 12)), int(rng.integers(1, 70)))
+        rule = ["full", "causal", "local"][int(rng.integers(0, 3))]
+        mode = pattern.SYNC_MODES[int(rng.integers(0, 3))]
+        w, cz = int(rng.integers(1, 10)), bool(rng.integers(0, 2))
+        p = _capi.make_problem(0, dims, rule, mode, (1, 4) + qs, (1, 4) + ks, (1, 4) + ks, w, 0, cz)
+        assert np.array_equal(_capi.pattern_mask_fast(p, tile, resident_is_q),
+                              pattern.tests_mask(qs, ks, mode, rule, w, 0, cz)), (dims, qs, ks, rule, mode, w, cz)

@@ -85,6 +85,7 @@ CASES = [
     (2, "local", "none_front", 4, 0, 1, (2,), 64, 64, (24, 32), (24, 32)),     # C3-like
     (2, "local", "scale_front", 3, 1, 0, (1,), 64, 128, (20, 24), (40, 24)),
     (2, "local", "none_front", 8, 0, 1, (1,), 64, 64, (64, 64), (64, 64)),     # C3 at full grid size
+    (1, "full", "scale_end", 1, 0, 0, (2,), 64, 64, (1024,), (8192,)),         # C4 at full size (cross attention)
 ]
 
 

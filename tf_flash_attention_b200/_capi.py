@@ -74,6 +74,7 @@ def _load():
         "fa_estimate_forward_flops": (C.c_int, [PP, i32, C.POINTER(C.c_float)]),
         "fa_count_attended": (C.c_int, [PP, C.POINTER(i64)]),
         "fa_pattern_mask": (C.c_int, [PP, vp]),
+        "fa_pattern_mask_fast": (C.c_int, [PP, i32, i32, vp]),
         "fa_orders": (C.c_int, [PP, vp, vp, vp]),
         "fa_classify_tiles": (C.c_int, [PP, i32, i32, vp]),
         "fa_check_forward_shapes": (C.c_int, [i32, i32, C.POINTER(i64), i32, C.POINTER(i64), i32,
@@ -160,6 +161,15 @@ def pattern_mask(p):
     k = int(np.prod([p.k_shape[i] for i in range(p.seq_dims)]))
     out = np.zeros((q, k), dtype=np.uint8)
     check(lib.fa_pattern_mask(C.byref(p), out.ctypes.data), "fa_pattern_mask")
+    return out.astype(bool)
+
+
+def pattern_mask_fast(p, tile, resident_is_q):
+    import numpy as np
+    q = int(np.prod([p.q_shape[i] for i in range(p.seq_dims)]))
+    k = int(np.prod([p.k_shape[i] for i in range(p.seq_dims)]))
+    out = np.zeros((q, k), dtype=np.uint8)
+    check(lib.fa_pattern_mask_fast(C.byref(p), tile, int(resident_is_q), out.ctypes.data), "fa_pattern_mask_fast")
     return out.astype(bool)
 
 

@@ -262,6 +262,39 @@ int fa_pattern_mask(const fa_problem_t* p, uint8_t* mask) {
   return FA_OK;
 }
 
+// Same pattern as fa_pattern_mask but assembled from the closed-form 32-column masks the tcgen05
+// kernels use (fa_fast_mask32), both with queries resident (forward / dQ kernels) and with keys resident
+// (dK/dV kernel), tiles of `tile` streamed entries. Returns FA_EINVAL_RULE for rules that have no closed
+// form (local with log2_stride > 0 uses the element rule in the kernels as well).
+int fa_pattern_mask_fast(const fa_problem_t* p, int32_t tile, int32_t resident_is_q, uint8_t* mask) {
+  FaRule r;
+  int rc = make_rule(p, &r);
+  if (rc) return rc;
+  if (!mask || tile < 32 || tile % 32) return FA_EINVAL_NULL;
+  if (r.rule == 2 && r.log2_stride != 0) return FA_EINVAL_RULE;
+  const FaSeqMap& res_map = resident_is_q ? r.q : r.k;
+  const FaSeqMap& str_map = resident_is_q ? r.k : r.q;
+  for (int32_t i = 0; i < res_map.total; ++i) {
+    const FaPos rp = fa_pos(r, res_map, i);
+    for (int32_t s0 = 0; s0 < str_map.total; s0 += tile) {
+      const int32_t nvalid = std::min(tile, str_map.total - s0);
+      for (int32_t c0 = 0; c0 < tile; c0 += 32) {
+        const uint32_t bits = fa_fast_mask32(r, resident_is_q != 0, rp, s0, c0, nvalid);
+        for (int e = 0; e < 32; ++e) {
+          const int32_t j = s0 + c0 + e;
+          if (j >= str_map.total) {
+            if ((bits >> e) & 1u) return FA_EINVAL_SHAPE;  // a bit outside the sequence: bug
+            continue;
+          }
+          const int64_t idx = resident_is_q ? int64_t(i) * r.k.total + j : int64_t(j) * r.k.total + i;
+          mask[idx] = (bits >> e) & 1u;
+        }
+      }
+    }
+  }
+  return FA_OK;
+}
+
 int fa_orders(const fa_problem_t* p, int32_t* q_order, int32_t* k_order, int32_t* ref_shape) {
   FaRule r;
   int rc = make_rule(p, &r);
@@ -501,6 +534,37 @@ size_t fa_host_arena_bytes(const fa_problem_t* p, int is_backward) {
     if (e_ != cudaSuccess) return cuda_fail(e_);   \
   } while (0)
 
+namespace {
+// Host-buffer calls are pipelined over chunks of the batch on three streams: upload of chunk c+1,
+// compute of chunk c (on the caller's stream) and download of chunk c-1 overlap (PCIe is full duplex).
+struct HostPipe {
+  cudaStream_t in = nullptr, out = nullptr;
+  std::vector<cudaEvent_t> ev;
+  ~HostPipe() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (in) cudaStreamDestroy(in);
+    if (out) cudaStreamDestroy(out);
+  }
+  cudaError_t init(int n_events) {
+    cudaError_t e = cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    ev.resize(n_events);
+    for (auto& x : ev) {
+      x = nullptr;
+      e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+};
+int64_t pick_chunks(const fa_problem_t* p, size_t total_bytes) {
+  if (p->batch < 2 || total_bytes < (size_t(64) << 20)) return 1;
+  return std::min<int64_t>(p->batch, 8);
+}
+}  // namespace
+
 int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, void* o, void* l,
                     void* m, void* dev_arena, size_t dev_arena_bytes, void* stream) {
   Arena a;
@@ -508,22 +572,40 @@ int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const v
   if (rc) return rc;
   if (!dev_arena || dev_arena_bytes < a.total) return FA_EINVAL_WORKSPACE;
   if (!q || !k || !v || !o || !l || !m) return FA_EINVAL_NULL;
+  if (p->batch == 0) return FA_OK;
   char* base = (char*)dev_arena;
   cudaStream_t st = (cudaStream_t)stream;
-  FA_CU(cudaMemcpyAsync(base + a.q, q, a.nq_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.k, k, a.nk_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.v, v, a.nv_b, cudaMemcpyHostToDevice, st));
-  if (p->accumulate) {
-    FA_CU(cudaMemcpyAsync(base + a.o, o, a.no_b, cudaMemcpyHostToDevice, st));
-    FA_CU(cudaMemcpyAsync(base + a.l, l, a.nl_b, cudaMemcpyHostToDevice, st));
-    FA_CU(cudaMemcpyAsync(base + a.m, m, a.nm_b, cudaMemcpyHostToDevice, st));
+  const int64_t B = p->batch;
+  const int64_t nch = pick_chunks(p, a.nq_b + a.nk_b + a.nv_b + a.no_b);
+  HostPipe pipe;
+  FA_CU(pipe.init(int(2 * nch + 1)));
+  FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));          // uploads start after prior work on `stream`
+  FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
+  const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
+  for (int64_t c = 0; c < nch; ++c) {
+    const int64_t b0 = B * c / nch, nb = B * (c + 1) / nch - b0;
+    FA_CU(cudaMemcpyAsync(base + a.q + b0 * sq, (const char*)q + b0 * sq, nb * sq, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.k + b0 * sk, (const char*)k + b0 * sk, nb * sk, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.v + b0 * sv, (const char*)v + b0 * sv, nb * sv, cudaMemcpyHostToDevice, pipe.in));
+    if (p->accumulate) {
+      FA_CU(cudaMemcpyAsync(base + a.o + b0 * so, (char*)o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.l + b0 * sl, (char*)l + b0 * sl, nb * sl, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.m + b0 * sm, (char*)m + b0 * sm, nb * sm, cudaMemcpyHostToDevice, pipe.in));
+    }
+    FA_CU(cudaEventRecord(pipe.ev[2 * c], pipe.in));
+    FA_CU(cudaStreamWaitEvent(st, pipe.ev[2 * c], 0));
+    fa_problem_t sub = *p;
+    sub.batch = nb;
+    rc = fa_forward(&sub, base + a.q + b0 * sq, base + a.k + b0 * sk, base + a.v + b0 * sv, base + a.o + b0 * so,
+                    base + a.l + b0 * sl, base + a.m + b0 * sm, base + a.ws, a.total - a.ws, stream);
+    if (rc) return rc;
+    FA_CU(cudaEventRecord(pipe.ev[2 * c + 1], st));
+    FA_CU(cudaStreamWaitEvent(pipe.out, pipe.ev[2 * c + 1], 0));
+    FA_CU(cudaMemcpyAsync((char*)o + b0 * so, base + a.o + b0 * so, nb * so, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)l + b0 * sl, base + a.l + b0 * sl, nb * sl, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)m + b0 * sm, base + a.m + b0 * sm, nb * sm, cudaMemcpyDeviceToHost, pipe.out));
   }
-  rc = fa_forward(p, base + a.q, base + a.k, base + a.v, base + a.o, base + a.l, base + a.m,
-                  base + a.ws, a.total - a.ws, stream);
-  if (rc) return rc;
-  FA_CU(cudaMemcpyAsync(o, base + a.o, a.no_b, cudaMemcpyDeviceToHost, st));
-  FA_CU(cudaMemcpyAsync(l, base + a.l, a.nl_b, cudaMemcpyDeviceToHost, st));
-  FA_CU(cudaMemcpyAsync(m, base + a.m, a.nm_b, cudaMemcpyDeviceToHost, st));
+  FA_CU(cudaStreamSynchronize(pipe.out));
   FA_CU(cudaStreamSynchronize(st));
   return FA_OK;
 }
@@ -536,22 +618,40 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
   if (rc) return rc;
   if (!dev_arena || dev_arena_bytes < a.total) return FA_EINVAL_WORKSPACE;
   if (!q || !k || !v || !o || !l || !m || !d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
+  if (p->batch == 0) return FA_OK;
   char* base = (char*)dev_arena;
   cudaStream_t st = (cudaStream_t)stream;
-  FA_CU(cudaMemcpyAsync(base + a.q, q, a.nq_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.k, k, a.nk_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.v, v, a.nv_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.o, o, a.no_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.l, l, a.nl_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.m, m, a.nm_b, cudaMemcpyHostToDevice, st));
-  FA_CU(cudaMemcpyAsync(base + a.d_o, d_o, a.no_b, cudaMemcpyHostToDevice, st));
-  rc = fa_backward(p, base + a.q, base + a.k, base + a.v, base + a.o, base + a.l, base + a.m,
-                   base + a.d_o, base + a.d_q, base + a.d_k, base + a.d_v, base + a.ws,
-                   a.total - a.ws, stream);
-  if (rc) return rc;
-  FA_CU(cudaMemcpyAsync(d_q, base + a.d_q, a.nq_b, cudaMemcpyDeviceToHost, st));
-  FA_CU(cudaMemcpyAsync(d_k, base + a.d_k, a.nk_b, cudaMemcpyDeviceToHost, st));
-  FA_CU(cudaMemcpyAsync(d_v, base + a.d_v, a.nv_b, cudaMemcpyDeviceToHost, st));
+  const int64_t B = p->batch;
+  const int64_t nch = pick_chunks(p, 2 * (a.nq_b + a.nk_b + a.nv_b + a.no_b));
+  HostPipe pipe;
+  FA_CU(pipe.init(int(2 * nch + 1)));
+  FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));
+  FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
+  const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
+  for (int64_t c = 0; c < nch; ++c) {
+    const int64_t b0 = B * c / nch, nb = B * (c + 1) / nch - b0;
+    FA_CU(cudaMemcpyAsync(base + a.q + b0 * sq, (const char*)q + b0 * sq, nb * sq, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.k + b0 * sk, (const char*)k + b0 * sk, nb * sk, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.v + b0 * sv, (const char*)v + b0 * sv, nb * sv, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.o + b0 * so, (const char*)o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.l + b0 * sl, (const char*)l + b0 * sl, nb * sl, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.m + b0 * sm, (const char*)m + b0 * sm, nb * sm, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.d_o + b0 * so, (const char*)d_o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaEventRecord(pipe.ev[2 * c], pipe.in));
+    FA_CU(cudaStreamWaitEvent(st, pipe.ev[2 * c], 0));
+    fa_problem_t sub = *p;
+    sub.batch = nb;
+    rc = fa_backward(&sub, base + a.q + b0 * sq, base + a.k + b0 * sk, base + a.v + b0 * sv, base + a.o + b0 * so,
+                     base + a.l + b0 * sl, base + a.m + b0 * sm, base + a.d_o + b0 * so, base + a.d_q + b0 * sq,
+                     base + a.d_k + b0 * sk, base + a.d_v + b0 * sv, base + a.ws, a.total - a.ws, stream);
+    if (rc) return rc;
+    FA_CU(cudaEventRecord(pipe.ev[2 * c + 1], st));
+    FA_CU(cudaStreamWaitEvent(pipe.out, pipe.ev[2 * c + 1], 0));
+    FA_CU(cudaMemcpyAsync((char*)d_q + b0 * sq, base + a.d_q + b0 * sq, nb * sq, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)d_k + b0 * sk, base + a.d_k + b0 * sk, nb * sk, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)d_v + b0 * sv, base + a.d_v + b0 * sv, nb * sv, cudaMemcpyDeviceToHost, pipe.out));
+  }
+  FA_CU(cudaStreamSynchronize(pipe.out));
   FA_CU(cudaStreamSynchronize(st));
   return FA_OK;
 }

@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           okmask_lo = interval_bits32(lo, hi, 0);
           okmask_hi = interval_bits32(lo, hi, 32);
         } else {
-          okmask_lo = element_mask32(rule, true, qpos, k0, 0, nvalid);
-          okmask_hi = element_mask32(rule, true, qpos, k0, 32, nvalid);
+          okmask_lo = tile_mask32(rule, true, qpos, k0, 0, nvalid);
+          okmask_hi = tile_mask32(rule, true, qpos, k0, 32, nvalid);
         }
       }
       float s[64], dp[64];
@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
             okmask_lo = interval_bits32(lo, hi, 0);
             okmask_hi = interval_bits32(lo, hi, 32);
           } else {
-            okmask_lo = element_mask32(rule, false, kpos, q0, 0, nvalid);
-            okmask_hi = element_mask32(rule, false, kpos, q0, 32, nvalid);
+            okmask_lo = tile_mask32(rule, false, kpos, q0, 0, nvalid);
+            okmask_hi = tile_mask32(rule, false, kpos, q0, 32, nvalid);
           }
         }
       }

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
           for (int c = 0; c < 4; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) okm[c] = element_mask32(rule, true, qpos, k0, 32 * c, nvalid);
+          for (int c = 0; c < 4; ++c) okm[c] = tile_mask32(rule, true, qpos, k0, 32 * c, nvalid);
         }
       }
       // S row -> registers (one row per thread)

@@ -300,3 +300,68 @@ FA_HD void fa_q_tile_range(const FaRule& r, int32_t k_lo, int32_t k_hi, int32_t 
   *last = hi / tile_q;
   if (*last > nqt - 1) *last = nqt - 1;
 }
+
+// ---- closed-form 32-column masks (used by the tcgen05 kernels; host-testable) --------------------
+FA_HD int32_t fa_imin(int32_t a, int32_t b) { return a < b ? a : b; }
+FA_HD int32_t fa_imax(int32_t a, int32_t b) { return a > b ? a : b; }
+// floor / ceil division by a positive divisor
+FA_HD int32_t fa_fdiv(int32_t a, int32_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+FA_HD int32_t fa_cdiv(int32_t a, int32_t b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
+
+// bits e in [0,32) with lo <= col0 + e <= hi
+FA_HD uint32_t interval_bits32(int32_t lo, int32_t hi, int32_t col0) {
+  const int32_t a = fa_imax(lo - col0, 0), b = fa_imin(hi - col0, 31);
+  if (a > b) return 0u;
+  const uint32_t upto_b = b >= 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u);
+  const uint32_t below_a = (1u << a) - 1u;
+  return upto_b & ~below_a;
+}
+
+// 32-bit attended mask of streamed entries [s0+col0, s0+col0+32) (only the first `nvalid` entries of
+// the tile starting at s0 exist) against one fixed resident position, for rules whose attended set
+// is an interval per grid row: full, causal, and local with log2_stride == 0; 1-D and 2-D; any sync
+// mode. For one grid row y of the streamed sequence the attended x are
+//   { x : |res.c0 - cx| < W and causal(order) },  cx = off0 + x*stride0,  provided |res.c1 - cy| < W,
+// an x-interval, so a chunk costs a few integer ops per grid row it touches instead of 32 evaluations
+// of the element rule.
+FA_HD uint32_t fa_fast_mask32(const FaRule& rule, bool resident_is_q, const FaPos& res, int32_t s0,
+                              int32_t col0, int32_t nvalid) {
+  const FaSeqMap& sm = resident_is_q ? rule.k : rule.q;
+  const int32_t W = rule.rule == 2 ? rule.window : 0x3fffffff;
+  const int32_t j0 = s0 + col0;
+  const int32_t jend = fa_imin(j0 + 31, s0 + nvalid - 1);
+  if (jend < j0) return 0u;
+  if (rule.rule == 0) return interval_bits32(0, jend - j0, 0);
+  if (rule.dims == 1) {
+    int32_t clo = res.c0 - W + 1, chi = res.c0 + W - 1;
+    if (rule.causal) {
+      if (resident_is_q) chi = fa_imin(chi, res.c0);  // k.c0 <= q.c0
+      else clo = fa_imax(clo, res.c0);                // q.c0 >= k.c0
+    }
+    const int32_t jlo = fa_cdiv(clo - sm.off0, sm.stride0) - sm.base0;
+    const int32_t jhi = fa_fdiv(chi - sm.off0, sm.stride0) - sm.base0;
+    return interval_bits32(fa_imax(jlo, j0) - j0, fa_imin(jhi, jend) - j0, 0);
+  }
+  uint32_t bits = 0;
+  const int32_t y_first = j0 / sm.n0, y_last = jend / sm.n0;
+  for (int32_t y = y_first; y <= y_last; ++y) {
+    const int32_t cy = sm.off1 + y * sm.stride1;
+    if (fa_iabs(res.c1 - cy) >= W) continue;
+    int32_t clo = res.c0 - W + 1, chi = res.c0 + W - 1;
+    if (rule.causal) {
+      if (resident_is_q) {  // order(q) >= order(k)
+        if (cy > res.c1) continue;
+        if (cy == res.c1) chi = fa_imin(chi, res.c0);
+      } else {
+        if (cy < res.c1) continue;
+        if (cy == res.c1) clo = fa_imax(clo, res.c0);
+      }
+    }
+    const int32_t xlo = fa_imax(fa_cdiv(clo - sm.off0, sm.stride0), 0);
+    const int32_t xhi = fa_imin(fa_fdiv(chi - sm.off0, sm.stride0), sm.n0 - 1);
+    if (xlo > xhi) continue;
+    const int32_t row0 = y * sm.n0;
+    bits |= interval_bits32(fa_imax(row0 + xlo, j0) - j0, fa_imin(row0 + xhi, jend) - j0, 0);
+  }
+  return bits;
+}

@@ -169,13 +169,11 @@ __device__ __forceinline__ void interval_1d(const FaRule& rule, bool resident_is
   }
 }
 
-__device__ __forceinline__ uint32_t interval_bits32(int lo, int hi, int col0) {
-  // bits e in [0,32) with lo <= col0+e <= hi
-  const int a = max(lo - col0, 0), b = min(hi - col0, 31);
-  if (a > b) return 0u;
-  const uint32_t upto_b = b >= 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u);
-  const uint32_t below_a = (1u << a) - 1u;
-  return upto_b & ~below_a;
+// mask builder used by all tcgen05 kernels: closed form whenever the rule allows it
+__device__ __forceinline__ uint32_t tile_mask32(const FaRule& rule, bool resident_is_q, const FaPos& res, int s0,
+                                               int col0, int nvalid) {
+  if (rule.rule != 2 || rule.log2_stride == 0) return fa_fast_mask32(rule, resident_is_q, res, s0, col0, nvalid);
+  return element_mask32(rule, resident_is_q, res, s0, col0, nvalid);
 }
 
 }  // namespace sm100
