@@ -44,6 +44,12 @@ WORKLOADS = {
     "C4": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp16 head_dim 64, 256 heads", seq_dims=1,
                dtype="float16", batch=(16, 16), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
                sync="scale_end", w=1, s=0, c=0),
+    "C4f32": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp32 (3xTF32 forward) head_dim 64, 64 heads",
+                  seq_dims=1, dtype="float32", batch=(8, 8), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
+                  sync="scale_end", w=1, s=0, c=0),
+    "C4f64": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp64 (DFMA) head_dim 64, 16 heads",
+                  seq_dims=1, dtype="float64", batch=(4, 4), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
+                  sync="scale_end", w=1, s=0, c=0),
     "C5": dict(desc="causal_1d fp16 single sequence 131072, head_dim 128, 16 heads, K/V ring over NCCL (fwd)",
                seq_dims=1, dtype="float16", batch=(1, 16), d=128, v_d=128, q=(131072,), k=(131072,), rule="causal",
                sync="none_front", w=1, s=0, c=0, ring=True),
@@ -279,7 +285,7 @@ def main():
     l = torch.empty(w["batch"] + w["q"], dtype=ldt, device=dev)
     m = torch.empty(w["batch"] + w["q"], dtype=tdt, device=dev)
     dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
-    ws_bytes = max(_capi.lib.fa_workspace_bytes(C.byref(prob), 1), 1)
+    ws_bytes = max(_capi.lib.fa_workspace_bytes(C.byref(prob), 1), _capi.lib.fa_workspace_bytes(C.byref(prob), 0), 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -351,7 +357,7 @@ def main():
     if kernels:
         dom = max(kernels, key=lambda n: kernels[n]["share"])
         bwd_names = [n for n in kernels if "bwd" in n]
-        if dom in ("fwd_f16_sm100", "generic_fwd"):
+        if dom in ("fwd_f16_sm100", "generic_fwd", "fwd_f32_3xtf32_sm100"):
             ach = fwd_flops / (kernels[dom]["avg_ms"] * 1e-3) / 1e12
             what = f"{dom}: 2*nnz*(d+v_d)*batch FLOPs per launch"
             traffic = NCU_TRAFFIC.get((args.workload, "fwd"))

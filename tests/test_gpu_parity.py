@@ -208,7 +208,9 @@ def test_accumulate_merges_key_shards():
         tv = torch.from_numpy(np.ascontiguousarray(V[:, :, k0:k1])).cuda()
         p = _capi.make_problem(1, 1, "causal", "none_front", (3, 32, 192), (3, 32, k1 - k0), (3, 32, k1 - k0))
         p.k_index_base, p.k_full_len, p.q_full_len, p.accumulate = k0, 192, 192, int(step > 0)
+        need = _capi.lib.fa_workspace_bytes(C.byref(p), 0)
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device="cuda")
         rc = _capi.lib.fa_forward(C.byref(p), tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), O.data_ptr(),
-                                  l.data_ptr(), m.data_ptr(), None, 0, torch.cuda.current_stream().cuda_stream)
+                                  l.data_ptr(), m.data_ptr(), ws.data_ptr(), need, torch.cuda.current_stream().cuda_stream)
         _capi.check(rc)
     assert max_abs_err(O.cpu().numpy(), ref["O"]) <= 1e-5

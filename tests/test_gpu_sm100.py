@@ -137,3 +137,47 @@ def test_full_size_properties_c2():
     perm = torch.randperm(B, device="cuda")
     Oq = fa.causal_1d(Q[perm].contiguous(), K[perm].contiguous(), V1[perm].contiguous(), "none_front")
     assert torch.equal(Oq, Oa[perm])
+
+
+F32_CASES = [
+    (1, "full", "none_front", 1, 0, 0, (2,), 64, 64, (256,), (320,)),
+    (1, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (512,), (512,)),
+    (1, "full", "scale_end", 1, 0, 0, (2,), 64, 64, (1024,), (8192,)),          # C4 fp32 variant at full size
+    (1, "local", "scale_front", 32, 0, 0, (8,), 32, 16, (1024,), (2048,)),      # C1 (README example)
+    (1, "causal", "scale_front", 1, 0, 0, (2,), 32, 32, (100,), (204,)),        # ragged tiles
+    (1, "local", "none_front", 2, 0, 0, (2,), 32, 32, (640,), (128,)),          # rows with no keys
+    (2, "local", "none_front", 4, 0, 1, (2,), 64, 64, (24, 32), (24, 32)),
+    (2, "causal", "scale_end", 1, 0, 0, (1,), 32, 32, (8, 40), (24, 40)),
+]
+
+
+@pytest.mark.parametrize("case", F32_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_fp32_3xtf32_forward_matches_oracle(case):
+    """fp32 forward on the tensor cores (tcgen05 kind::tf32, 3xTF32 split): BASELINE.json bar 1e-5 max-abs on O;
+    the (generic fp32) backward then consumes its l, m."""
+    dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) % 1000)
+    Q, K, V, dO = da.random_inputs(rng, np.float32, batch, d, vd, qs, ks)
+    ref = da.attention(Q, K, V, dims, rule, mode, w, s, c, dO=dO)
+    tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+    if rule == "full":
+        O, l, m = (fa.full_1d if dims == 1 else fa.full_2d)(tq, tk, tv, mode, True)
+    elif rule == "causal":
+        O, l, m = (fa.causal_1d if dims == 1 else fa.causal_2d)(tq, tk, tv, mode, True)
+    else:
+        O, l, m = (fa.local_1d if dims == 1 else fa.local_2d)(tq, tk, tv, w, s, c, mode, True)
+    torch.cuda.synchronize()
+    assert _capi.lib.fa_last_path() == 3, "fp32 forward did not take the 3xTF32 tcgen05 path"
+    On = O.detach().cpu().numpy()
+    assert max_abs_err(On, ref["O"]) <= 1e-5
+    ln, mn = l.cpu().numpy().astype(np.float64), m.cpu().numpy()
+    empty = ~np.isfinite(ref["m"])
+    if empty.any():
+        assert np.all(ln[empty] == 0) and np.all(mn[empty].view(np.uint8) == 0xFA)
+        assert np.all(On[np.broadcast_to(np.expand_dims(empty, -dims - 1), On.shape)] == 0)
+    live = ~empty
+    lse = mn.astype(np.float64)[live] + np.log(ln[live])
+    assert np.max(np.abs(lse - (ref["m"][live] + np.log(ref["l"][live])))) <= 1e-5
+    dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+    for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert scaled_err(g.cpu().numpy(), ref[name]) <= 1e-5, name

@@ -137,6 +137,13 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
   size_t g = fa::generic_workspace_bytes(p->dtype, p->batch, a.rule.q.total, is_backward != 0);
   size_t s = 0;
   if (p->dtype == FA_F16) s = fa::sm100_f16_workspace_bytes(a, is_backward != 0);
+  if (p->dtype == FA_F32 && !is_backward) {
+    // hi / lo TF32 copies of Q, K, V for the 3xTF32 forward (only when that kernel can take the shape)
+    fa::LaunchArgs probe = a;
+    probe.o = probe.workspace = nullptr;
+    probe.workspace_bytes = ~size_t(0);
+    if (fa::g_path_override != 1 && fa::sm100_f32_forward_supports(probe)) s = fa::sm100_f32_forward_workspace_bytes(a);
+  }
   return g > s ? g : s;
 }
 
@@ -155,6 +162,9 @@ int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* 
   if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_forward_supports(a)) {
     fa::g_last_path = 2;
     e = fa::sm100_f16_forward(a, st);
+  } else if (fa::g_path_override != 1 && p->dtype == FA_F32 && fa::sm100_f32_forward_supports(a)) {
+    fa::g_last_path = 3;
+    e = fa::sm100_f32_forward(a, st);
   } else {
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;

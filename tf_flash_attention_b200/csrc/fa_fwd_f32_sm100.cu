@@ -1,0 +1,493 @@
+// fa_fwd_f32_sm100.cu — fp32 forward on the Blackwell tensor cores with a 3xTF32 split.
+//
+// x = hi + lo with hi = x truncated to TF32 (low 13 mantissa bits cleared) and lo = x - hi (exact).
+// Every product A.B is evaluated as  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with tcgen05.mma kind::tf32
+// and fp32 accumulation in TMEM; the dropped lo.lo term is ~2^-22 relative, which keeps O within the
+// 1e-5 bar of BASELINE.json (tests/test_gpu_sm100.py::test_fp32_3xtf32_*). The hi / lo copies of Q, K, V
+// are produced once per call by a bandwidth-bound pre-pass into the caller's workspace; P is split in
+// registers by the softmax warps and written to TMEM as two A operands.
+//
+// Same channel-first layout tricks as the fp16 kernel (fa_fwd_f16_sm100.cu): Q and K tiles are
+// MN-major operands straight from TMA (box = 32 floats of sequence x all channels, 128-byte swizzle),
+// V is K-major. One 128-row Q tile per CTA, 64-key tiles, K/V ring of 4 stages (each stage = hi + lo).
+// Replaces the reference's float instantiation of ForwardImpl (flash_attention/kernel/flash_attention.cu:
+// 425-1077, FFMA). The fp32 backward and fp64 run on the FFMA / DFMA kernels of fa_generic.cu.
+#include "fa_common.cuh"
+#include "fa_launch.h"
+#include "sm100_ptx.cuh"
+#include "sm100_tiles.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace fa {
+namespace sm100 {
+
+using namespace ptx;
+
+constexpr int kF32BlockM = 128;
+constexpr int kF32BlockN = 64;
+constexpr int kF32Stages = 4;
+constexpr int kF32Threads = 256;  // 4 softmax warps + producer + mma + alloc + spare
+constexpr float kF32Log2e = 1.4426950408889634f;
+constexpr float kF32Ln2 = 0.6931471805599453f;
+constexpr float kF32Rescale = 8.0f;
+
+struct alignas(64) F32FwdParams {
+  CUtensorMap map_q_hi, map_q_lo, map_k_hi, map_k_lo, map_v_hi, map_v_lo, map_o;
+  FaRule rule;
+  float* l;
+  float* m;
+  int32_t nq, nk, n_qtiles, batch;
+  float scale_log2;
+};
+
+// hi = x with the low 13 mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact)
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                  int64_t n) {
+  for (int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += int64_t(gridDim.x) * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+      *reinterpret_cast<float4*>(hi + i) = h;
+      *reinterpret_cast<float4*>(lo + i) = l;
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        const float h = __uint_as_float(__float_as_uint(x[j]) & 0xffffe000u);
+        hi[j] = h;
+        lo[j] = x[j] - h;
+      }
+    }
+  }
+}
+
+template <int D, int VD>
+struct F32Cfg {
+  static constexpr int kCh = D > VD ? D : VD;
+  static constexpr int kQBytes = kF32BlockM * D * 4;        // one of hi / lo; hi doubles as O staging
+  static constexpr int kQRegion = 2 * (kF32BlockM * kCh * 4);
+  static constexpr int kHalfStage = kF32BlockN * kCh * 4;   // hi or lo of a K or V tile
+  static constexpr int kStageBytes = 2 * kHalfStage;
+  static constexpr int kBarOffset = kQRegion + kF32Stages * kStageBytes;
+  static constexpr int kNumBars = 1 + 2 * kF32Stages + 1 + 1 + 1;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kF32Threads, 1) fwd_f32_kernel(const __grid_constant__ F32FwdParams p) {
+  using Cfg = F32Cfg<D, VD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_hi = smem_base, q_lo = smem_base + Cfg::kQRegion / 2;
+  const uint32_t ring = smem_base + Cfg::kQRegion;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_q_full = bars;
+  const uint32_t bar_kv_full = bars + 8;
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * kF32Stages;
+  const uint32_t bar_s_full = bar_kv_empty + 8 * kF32Stages;
+  const uint32_t bar_p_ready = bar_s_full + 8;
+  const uint32_t bar_o_final = bar_p_ready + 8;
+  const uint32_t tmem_slot = bar_o_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_qtiles);
+  const int qt = p.n_qtiles - 1 - int(blockIdx.x % p.n_qtiles);
+  const int q0 = qt * kF32BlockM;
+  const int q_hi_row = min(q0 + kF32BlockM, p.nq) - 1;
+  int kt_first, kt_last;
+  fa_k_tile_range(rule, q0, q_hi_row, kF32BlockN, &kt_first, &kt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {q0};
+    const int hi[1] = {q_hi_row};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, true, lo, hi, valid, 1, kt_first, kt_last, kF32BlockN, p.nk, kF32Threads / 32);
+  }
+
+  if (warp == 4) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q_hi);
+      prefetch_tensormap(&p.map_q_lo);
+      prefetch_tensormap(&p.map_k_hi);
+      prefetch_tensormap(&p.map_k_lo);
+      prefetch_tensormap(&p.map_v_hi);
+      prefetch_tensormap(&p.map_v_lo);
+      prefetch_tensormap(&p.map_o);
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      mbar_init(bar_q_full, 1);
+      mbar_init(bar_s_full, 1);
+      mbar_init(bar_p_ready, kF32BlockM);
+      mbar_init(bar_o_final, 1);
+      for (int s = 0; s < kF32Stages; ++s) {
+        mbar_init(bar_kv_full + 8 * s, 1);
+        mbar_init(bar_kv_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 6) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: S_main / P_hi [0,64)  S_corr [64,128)  P_lo [128,192)  O_main [192,256)  O_corr [256,320).
+  // The tensor core adds into its fp32 accumulator with truncation, so every accumulate step costs up to
+  // one ulp of the accumulator. The small cross terms (hi.lo + lo.hi, ~2^-11 of the result) therefore go to
+  // accumulators of their own and are added once in registers with round-to-nearest: the large
+  // accumulators see 8 instead of 24 additions per tile (measured O error at 8192 keys 1.0e-5 -> 3e-6).
+  constexpr uint32_t kColS = 0, kColSc = 64, kColPlo = 128, kColO = 192, kColOc = 256;
+
+  if (warp >= 4) {
+    if (warp == 4) {
+      // ===================== TMA producer =====================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q_full, 2 * Cfg::kQBytes);
+        for (int h = 0; h < 4; ++h) {
+          tma_load_2d(q_hi + h * (D * 128), &p.map_q_hi, bar_q_full, q0 + h * 32, b * D);
+          tma_load_2d(q_lo + h * (D * 128), &p.map_q_lo, bar_q_full, q0 + h * 32, b * D);
+        }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        int kt, tw, tb;
+        while (it.next(&kt, &tw, &tb)) {
+          for (int kv = 0; kv < 2; ++kv) {
+            const int rows = kv == 0 ? D : VD;
+            const void* mh = kv == 0 ? (const void*)&p.map_k_hi : (const void*)&p.map_v_hi;
+            const void* ml = kv == 0 ? (const void*)&p.map_k_lo : (const void*)&p.map_v_lo;
+            const int s = t % kF32Stages, u = t / kF32Stages;
+            mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_kv_full + 8 * s, 2 * kF32BlockN * rows * 4);
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d(ring + s * Cfg::kStageBytes + h * (rows * 128), mh, bar_kv_full + 8 * s,
+                          kt * kF32BlockN + h * 32, b * rows);
+              tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kHalfStage + h * (rows * 128), ml,
+                          bar_kv_full + 8 * s, kt * kF32BlockN + h * 32, b * rows);
+            }
+            ++t;
+          }
+        }
+      }
+    } else if (warp == 5) {
+      // ===================== MMA issuer =====================
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_s = idesc_tf32(kF32BlockM, kF32BlockN, true, true);
+        constexpr uint32_t idesc_o = idesc_tf32(kF32BlockM, VD, false, false);
+        auto issue_s = [&](int stage) {
+          const uint32_t k_hi = ring + stage * Cfg::kStageBytes, k_lo = k_hi + Cfg::kHalfStage;
+          // S = Qhi.Khi + Qhi.Klo + Qlo.Khi ; K = 8 channels per instruction = one 1024-byte swizzle atom
+          const uint32_t a_src[3] = {q_hi, q_hi, q_lo};
+          const uint32_t b_src[3] = {k_hi, k_lo, k_hi};
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+            for (int ks = 0; ks < D / 8; ++ks)
+              // MN-major TF32: 128B swizzle with 32B atoms -> 4-channel atoms of 512 bytes (SBO), 8 channels
+              // per instruction = 1024 bytes; LBO = next 32 sequence positions = next TMA box
+              mma_ss_tf32(tmem_base + (t3 == 0 ? kColS : kColSc),
+                          smem_desc_sw128_base32(a_src[t3] + ks * 1024, D * 128, 512),
+                          smem_desc_sw128_base32(b_src[t3] + ks * 1024, D * 128, 512), idesc_s,
+                          (t3 == 0 ? ks : ((t3 - 1) | ks)) != 0);
+        };
+        auto issue_o = [&](int stage, bool accumulate) {
+          const uint32_t v_hi = ring + stage * Cfg::kStageBytes, v_lo = v_hi + Cfg::kHalfStage;
+          // O += Phi.Vhi + Phi.Vlo + Plo.Vhi ; 8 keys = 32 bytes inside the 128-byte row, 32 keys per box
+          const uint32_t a_col[3] = {kColS, kColS, kColPlo};
+          const uint32_t b_src[3] = {v_hi, v_lo, v_hi};
+#pragma unroll
+          for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+            for (int ks = 0; ks < kF32BlockN / 8; ++ks)
+              mma_ts_tf32(tmem_base + (t3 == 0 ? kColO : kColOc), tmem_base + a_col[t3] + ks * 8,
+                          smem_desc_sw128(b_src[t3] + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024), idesc_o,
+                          (accumulate || (t3 == 0 ? ks : ((t3 - 1) | ks)) != 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_q_full, 0);
+          mbar_wait(bar_kv_full + 0, 0);
+          tc_fence_after();
+          issue_s(0);
+          mma_commit(bar_s_full);
+          mma_commit(bar_kv_empty + 0);
+          for (int j = 0; j < n; ++j) {
+            const int tv = 2 * j + 1, sv = tv % kF32Stages;
+            const int tk = 2 * j + 2, sk = tk % kF32Stages;
+            mbar_wait(bar_kv_full + 8 * sv, (tv / kF32Stages) & 1);
+            mbar_wait(bar_p_ready, j & 1);
+            tc_fence_after();
+            issue_o(sv, j > 0);
+            mma_commit(bar_kv_empty + 8 * sv);
+            if (j + 1 < n) {
+              mbar_wait(bar_kv_full + 8 * sk, (tk / kF32Stages) & 1);
+              tc_fence_after();
+              issue_s(sk);
+              mma_commit(bar_s_full);
+              mma_commit(bar_kv_empty + 8 * sk);
+            } else {
+              mma_commit(bar_o_final);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroup (thread = row) =====================
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + kColS;
+    const uint32_t t_sc = tmem_base + lane_addr + kColSc;
+    const uint32_t t_plo = tmem_base + lane_addr + kColPlo;
+    const uint32_t t_o = tmem_base + lane_addr + kColO;
+    const uint32_t t_oc = tmem_base + lane_addr + kColOc;
+    const int qi = q0 + r;
+    const bool q_valid = qi < p.nq;
+    const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
+    const float scale_log2 = p.scale_log2;
+    const float NEG_INF = __int_as_float(0xff800000);
+    float m_ref = NEG_INF, m_true = NEG_INF, l_sum = 0.f;
+    int j = 0;
+    TileIter it;
+    it.init(sched, 1, kt_first, kt_last);
+    int kt, tw, tb;
+    while (it.next(&kt, &tw, &tb)) {
+      const int k0 = kt * kF32BlockN;
+      const int k_hi = min(k0 + kF32BlockN, p.nk) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool masked = cls != FA_TILE_FULL || (k0 + kF32BlockN > p.nk);
+      uint32_t okm[2] = {0xffffffffu, 0xffffffffu};
+      if (masked) {
+        const int nvalid = k_hi - k0 + 1;
+        okm[0] = tile_mask32(rule, true, qpos, k0, 0, nvalid);
+        okm[1] = tile_mask32(rule, true, qpos, k0, 32, nvalid);
+      }
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      float s[64];
+      {
+        float sc[64];
+        tmem_ld32f(t_s, &s[0]);
+        tmem_ld32f(t_s + 32, &s[32]);
+        tmem_ld32f(t_sc, &sc[0]);
+        tmem_ld32f(t_sc + 32, &sc[32]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] += sc[c];
+      }
+      if (masked) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
+      const float mx2 = mx * scale_log2;
+      m_true = fmaxf(m_true, mx2);
+      if (j == 0) {
+        m_ref = mx2;
+      } else {
+        const bool need = mx2 > m_ref + kF32Rescale;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = fmaxf(m_ref, mx2);
+          const float alpha = (m_new == NEG_INF) ? 1.f : exp2f(m_ref - m_new);
+          m_ref = m_new;
+          l_sum *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < (VD + 31) / 32; ++c) {
+            float o[32];
+            tmem_ld32f(t_o + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] *= alpha;
+            tmem_st32f(t_o + c * 32, o);
+            tmem_ld32f(t_oc + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] *= alpha;
+            tmem_st32f(t_oc + c * 32, o);
+          }
+        }
+      }
+      const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float phi[32], plo[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float pv = exp2f(fmaf(s[c * 32 + e], scale_log2, -m_use));  // accurate exp2 (fp32 contract)
+          sum += pv;
+          phi[e] = __uint_as_float(__float_as_uint(pv) & 0xffffe000u);
+          plo[e] = pv - phi[e];
+        }
+        tmem_st32f(t_s + c * 32, phi);
+        tmem_st32f(t_plo + c * 32, plo);
+      }
+      l_sum += sum;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+      ++j;
+    }
+
+    // ---- epilogue: O = acc / l -> smem [VD][32] x4 -> TMA store; l, m -> global ----
+    float* stage_f = reinterpret_cast<float*>(smem_gen) + (r >> 5) * (VD * 32) + (r & 31);
+    if (j > 0) {
+      mbar_wait(bar_o_final, 0);
+      tc_fence_after();
+      const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+      constexpr int kChunks = (VD + 31) / 32;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        float o[32], oc[32];
+        tmem_ld32f(t_o + c * 32, o);
+        tmem_ld32f(t_oc + c * 32, oc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e < VD) stage_f[(c * 32 + e) * 32] = l_sum > 0.f ? (o[e] + oc[e]) * inv : 0.f;
+      }
+    } else {
+      mbar_wait(bar_q_full, 0);
+      for (int c = 0; c < VD; ++c) stage_f[c * 32] = 0.f;
+    }
+    if (q_valid) {
+      const int64_t idx = int64_t(b) * p.nq + qi;
+      if (l_sum > 0.f) {
+        const float m_nat = m_true * kF32Ln2;
+        p.m[idx] = m_nat;
+        p.l[idx] = l_sum * exp2f(m_ref - m_nat * kF32Log2e);
+      } else {
+        p.m[idx] = sentinel<float>();
+        p.l[idx] = 0.f;
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, kF32BlockM);
+    if (r == 0) {
+      for (int h = 0; h < 4; ++h)
+        if (q0 + h * 32 < p.nq) tma_store_2d(&p.map_o, q_hi + h * (VD * 128), q0 + h * 32, b * VD);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+// swizzle: 0 none, 1 = 128B (K-major operands), 2 = 128B with 32-byte atoms (MN-major TF32 operands)
+static bool make_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int swizzle) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = []() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  }();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(cols) * 4};
+  cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+template <int D, int VD>
+cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
+  using Cfg = F32Cfg<D, VD>;
+  const int nq = a.rule.q.total, nk = a.rule.k.total;
+  const size_t nqe = size_t(a.batch) * D * nq, nke = size_t(a.batch) * D * nk, nve = size_t(a.batch) * VD * nk;
+  char* ws = reinterpret_cast<char*>(a.workspace);
+  float* qh = reinterpret_cast<float*>(ws);
+  float* ql = reinterpret_cast<float*>(ws + align256(nqe * 4));
+  float* kh = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4));
+  float* kl = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + align256(nke * 4));
+  float* vh = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + 2 * align256(nke * 4));
+  float* vl = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + 2 * align256(nke * 4) + align256(nve * 4));
+  const float* src[3] = {(const float*)a.q, (const float*)a.k, (const float*)a.v};
+  float* hi[3] = {qh, kh, vh};
+  float* lo[3] = {ql, kl, vl};
+  const size_t cnt[3] = {nqe, nke, nve};
+  for (int t = 0; t < 3; ++t) {
+    const int blocks = int(std::min<size_t>((cnt[t] / 4 + 255) / 256 + 1, 148 * 16));
+    ScopedKernel timed("split_tf32", stream);
+    split_tf32_kernel<<<blocks, 256, 0, stream>>>(src[t], hi[t], lo[t], int64_t(cnt[t]));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  F32FwdParams p;
+  if (!make_map_f32(&p.map_q_hi, qh, a.batch * D, nq, D, 2) || !make_map_f32(&p.map_q_lo, ql, a.batch * D, nq, D, 2) ||
+      !make_map_f32(&p.map_k_hi, kh, a.batch * D, nk, D, 2) || !make_map_f32(&p.map_k_lo, kl, a.batch * D, nk, D, 2) ||
+      !make_map_f32(&p.map_v_hi, vh, a.batch * VD, nk, VD, 1) ||
+      !make_map_f32(&p.map_v_lo, vl, a.batch * VD, nk, VD, 1) || !make_map_f32(&p.map_o, a.o, a.batch * VD, nq, VD, 0))
+    return cudaErrorInvalidValue;
+  p.rule = a.rule;
+  p.l = (float*)a.l;
+  p.m = (float*)a.m;
+  p.nq = nq;
+  p.nk = nk;
+  p.n_qtiles = (nq + kF32BlockM - 1) / kF32BlockM;
+  p.batch = int32_t(a.batch);
+  p.scale_log2 = kF32Log2e / sqrtf(float(D));
+  auto kern = fwd_f32_kernel<D, VD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  ScopedKernel timed("fwd_f32_3xtf32_sm100", stream);
+  kern<<<unsigned(int64_t(p.n_qtiles) * p.batch), kF32Threads, Cfg::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sm100
+
+size_t sm100_f32_forward_workspace_bytes(const LaunchArgs& a) {
+  const size_t nq = a.rule.q.total, nk = a.rule.k.total;
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  return 2 * al(size_t(a.batch) * a.d * nq * 4) + 2 * al(size_t(a.batch) * a.d * nk * 4) +
+         2 * al(size_t(a.batch) * a.v_d * nk * 4);
+}
+
+bool sm100_f32_forward_supports(const LaunchArgs& a) {
+  if (a.dtype != 1 || a.accumulate) return false;
+  const bool shape_ok = (a.d == 64 && a.v_d == 64) || (a.d == 32 && a.v_d == 32) || (a.d == 32 && a.v_d == 16);
+  if (!shape_ok) return false;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (nq % 4 || nk % 4) return false;  // TMA: row pitch must be a multiple of 16 bytes
+  if (nk > int64_t(sm100::kF32BlockN) * 32 * sm100::kMaxTileWords) return false;
+  if ((reinterpret_cast<uintptr_t>(a.o) & 15) || (reinterpret_cast<uintptr_t>(a.workspace) & 255)) return false;
+  if (a.workspace_bytes < sm100_f32_forward_workspace_bytes(a)) return false;
+  if (((nq + 127) / 128) * a.batch > 0x7fffffffLL) return false;
+  return true;
+}
+
+cudaError_t sm100_f32_forward(const LaunchArgs& a, cudaStream_t stream) {
+  if (a.d == 64) return sm100::launch_fwd_f32<64, 64>(a, stream);
+  if (a.v_d == 32) return sm100::launch_fwd_f32<32, 32>(a, stream);
+  return sm100::launch_fwd_f32<32, 16>(a, stream);
+}
+
+}  // namespace fa

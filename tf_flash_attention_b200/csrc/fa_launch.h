@@ -55,4 +55,9 @@ size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward);
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream);
 cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream);
 
+// tcgen05 kind::tf32 forward for float with a 3xTF32 split (fa_fwd_f32_sm100.cu)
+bool sm100_f32_forward_supports(const LaunchArgs& a);
+size_t sm100_f32_forward_workspace_bytes(const LaunchArgs& a);
+cudaError_t sm100_f32_forward(const LaunchArgs& a, cudaStream_t stream);
+
 }  // namespace fa

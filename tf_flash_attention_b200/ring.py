@@ -71,6 +71,7 @@ class DeviceBackend:
         self.p.q_full_len = self.p.k_full_len = seq_len
         self.v_d = v_d
         self.acc_dtype = torch.float64 if dtype_code == _capi.FA_F64 else torch.float32
+        self._ws = None
 
     def _stream(self):
         return self.torch.cuda.current_stream().cuda_stream
@@ -91,8 +92,12 @@ class DeviceBackend:
     def attend_partial(self, q, k, v, q_base, k_base, out):
         self.p.q_index_base, self.p.k_index_base, self.p.accumulate = q_base, k_base, 0
         o, l, m = out
+        need = _capi.lib.fa_workspace_bytes(C.byref(self.p), 0)
+        if need and (self._ws is None or self._ws.numel() < need):
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=q.device)
         _capi.check(_capi.lib.fa_forward(C.byref(self.p), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
-                                         l.data_ptr(), m.data_ptr(), None, 0, self._stream()), "fa_forward")
+                                         l.data_ptr(), m.data_ptr(), self._ws.data_ptr() if need else None, need,
+                                         self._stream()), "fa_forward")
 
     def merge(self, part, acc, first):
         o, l, m = part
