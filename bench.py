@@ -58,7 +58,7 @@ WORKLOADS = {
 
 # DRAM bytes per launch measured with `ncu --set full` on the GPU (profiles/r1_*_ncu*.md); bench.py cannot
 # run under a profiler, so the captured values are carried here for the workload they were taken on.
-NCU_TRAFFIC = {("C2", "fwd"): 2.153e9, ("C2", "bwd"): 6.98e9}
+NCU_TRAFFIC = {("C2", "fwd"): 2.153e9, ("C2", "bwd"): 5.35e9}  # bwd: the fused dQ/dK/dV kernel alone
 
 
 def measured_peaks():
@@ -370,7 +370,7 @@ def main():
             traffic = NCU_TRAFFIC.get((args.workload, "bwd"))
         peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_ncu.md" if traffic else None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_fused_ncu.md (bwd: fused kernel only)" if traffic else None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
                     "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic": what}
         if "fwd_f16_sm100" in kernels:

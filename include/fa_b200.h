@@ -193,7 +193,8 @@ int64_t fa_launch_count(int reset);
  * returns up to max_entries (name, milliseconds) pairs in launch order and clears the list.   */
 void fa_kernel_timing(int enable);
 int fa_kernel_timings(int max_entries, const char** names, float* ms);
-/* Force a kernel family (testing): 0 auto, 1 generic only.                             */
+/* Force a kernel family (testing): 0 auto, 1 generic only, 4 fp16 backward as the two-kernel
+ * (dQ, then dK/dV) variant instead of the fused kernel.                                   */
 void fa_set_path_override(int path);
 const char* fa_version(void);
 

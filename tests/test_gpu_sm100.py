@@ -139,6 +139,41 @@ def test_full_size_properties_c2():
     assert torch.equal(Oq, Oa[perm])
 
 
+D128_CASES = [c for c in CASES if c[7] == 128]
+
+
+@pytest.mark.parametrize("case", D128_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-w{c[3]}s{c[4]}c{c[5]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_split_backward_variant_matches_oracle(case):
+    """head_dim 128 normally runs the fused dQ/dK/dV kernel; fa_set_path_override(4) selects the two-kernel
+    variant (dQ kernel, then dK/dV kernel) that head_dim 64 always uses. Both must meet the same bar."""
+    _capi.lib.fa_set_path_override(4)
+    try:
+        _run(*case, seed=zlib.crc32(repr(case).encode()) % 1000)
+    finally:
+        _capi.lib.fa_set_path_override(0)
+
+
+def test_fused_backward_agrees_with_split_variant():
+    """Same inputs through both backward variants: dK and dV are computed by identical arithmetic (bit-equal);
+    dQ is accumulated in fp32 across key tiles in a different order (fused: atomic adds) -> within 1 fp16 ulp-ish."""
+    rng = np.random.default_rng(5)
+    Q, K, V, dO = da.random_inputs(rng, np.float16, (3,), 128, 128, (1024,), (1536,))
+    tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+    tdo = torch.from_numpy(dO).cuda()
+    out = {}
+    for variant in (0, 4):
+        _capi.lib.fa_set_path_override(variant)
+        try:
+            O = fa.causal_1d(tq, tk, tv, "scale_end")
+            out[variant] = torch.autograd.grad(O, (tq, tk, tv), tdo)
+            assert _capi.lib.fa_last_path() == 2
+        finally:
+            _capi.lib.fa_set_path_override(0)
+    assert torch.equal(out[0][1], out[4][1]) and torch.equal(out[0][2], out[4][2])
+    dq_a, dq_b = out[0][0].float(), out[4][0].float()
+    assert float(((dq_a - dq_b).abs() / dq_b.abs().clamp(min=1)).max()) <= 1e-3
+
+
 F32_CASES = [
     (1, "full", "none_front", 1, 0, 0, (2,), 64, 64, (256,), (320,)),
     (1, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (512,), (512,)),

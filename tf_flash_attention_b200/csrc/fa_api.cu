@@ -136,6 +136,7 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
   if (fill_args(p, &a)) return 0;
   size_t g = fa::generic_workspace_bytes(p->dtype, p->batch, a.rule.q.total, is_backward != 0);
   size_t s = 0;
+  a.variant = fa::g_path_override;
   if (p->dtype == FA_F16) s = fa::sm100_f16_workspace_bytes(a, is_backward != 0);
   if (p->dtype == FA_F32 && !is_backward) {
     // hi / lo TF32 copies of Q, K, V for the 3xTF32 forward (only when that kernel can take the shape)
@@ -186,6 +187,7 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   a.q = q; a.k = k; a.v = v; a.o = (void*)o; a.l = (void*)l; a.m = (void*)m; a.d_o = d_o;
   a.d_q = d_q; a.d_k = d_k; a.d_v = d_v;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  a.variant = fa::g_path_override;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_backward_supports(a)) {

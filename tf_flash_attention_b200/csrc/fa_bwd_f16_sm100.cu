@@ -12,12 +12,16 @@
 //   bwd_dkdv_kernel : CTA = 128 keys, streams 64-query Q/dO tiles into two ping-pong slots
 //        S^T = K Q^T, dP^T = V dO^T  (SS, MN-major)
 //        dV += P^T dO, dK += dS^T Q  (TS: P^T / dS^T from TMEM; dO / Q tiles re-read K-major)
+//   bwd_fused_kernel (head_dim 128): bwd_dkdv_kernel + dQ^T = K^T dS^T in the same pass, dQ accumulated
+//        across key tiles with TMA reduce-add into an fp32 scratch tensor (see its header comment)
 // Formulas as in the reference: P = exp(s*scale - m)/l (flash_attention.cu:1838-1841),
 // dS = P (dP - D) scale (:1544-1546), D = rowsum(dO o O) (:1882-1891).
 #include "fa_common.cuh"
 #include "fa_launch.h"
 #include "sm100_ptx.cuh"
 #include "sm100_tiles.cuh"
+
+#include <cudaTypedefs.h>
 
 namespace fa {
 namespace sm100 {
@@ -640,6 +644,437 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
   }
 }
 
+// LSE2 + D arrays (padded), rounded up so that the fp32 dQ scratch behind them is 256-byte aligned
+static size_t stats_bytes(int64_t batch, int64_t nq) {
+  return (size_t(2) * (batch * nq + kStatPad) * sizeof(float) + 255) & ~size_t(255);
+}
+
+static bool make_map_f32_sw128(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols,
+                               int box_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = []() {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  }();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(cols) * 4};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// =================================================================================================
+// fused dQ / dK / dV kernel (D == 128)
+// =================================================================================================
+// Same CTA shape as bwd_dkdv_kernel (128 resident keys, 64-query sub-tiles in two ping-pong slots), but
+// dQ is produced here as well, so S and dP are computed once instead of twice (5 GEMMs per tile pair
+// instead of 7):
+//     dQ^T[d, q] = K^T[d, keys] . dS^T[keys, q]
+// A = the resident K tile re-read K-major, B = dS^T written by the softmax warps to shared memory in the
+// MN-major 128B-swizzled layout (one 128-byte row of 64 queries per key), accumulator = the S^T slot of
+// the same ping-pong slot (free once the softmax warpgroup has read it). A fourth warpgroup drains the
+// dQ^T accumulator and adds it into an fp32 [batch*D, nq] scratch tensor with TMA reduce-add
+// (cp.reduce.async.bulk.tensor ... .add); bwd_dq_convert scales and rounds it to fp16 afterwards.
+// (The order of the fp32 additions into the scratch tensor is not fixed, so dQ may differ in the last
+// fp16 bit between runs; dK and dV are deterministic.)
+constexpr int kFusedThreads = 512;
+
+template <int D, int VD>
+struct FusedCfg {
+  static constexpr int kStages = 3;
+  static constexpr int kKBytes = kBM * D * 2;
+  static constexpr int kVBytes = kBM * VD * 2;
+  static constexpr int kQBytes = kBN * D * 2;
+  static constexpr int kDoBytes = kBN * VD * 2;
+  static constexpr int kStatBytes = 2 * kBN * 4;
+  static constexpr int kStageBytes = kQBytes + kDoBytes;
+  static constexpr int kDsBytes = kBM * kBN * 2;       // dS^T tile, fp16, one per slot
+  static constexpr int kRedBytes = D * 32 * 4;         // dQ^T staging: D rows x 32 queries fp32 (two of them)
+  static constexpr int kRingOffset = kKBytes + kVBytes;
+  static constexpr int kDsOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kRedOffset = kDsOffset + 2 * kDsBytes;
+  static constexpr int kStatOffset = kRedOffset + 2 * kRedBytes;
+  static constexpr int kBarOffset = kStatOffset + kStages * kStatBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 2 + 2 + 2 + 2 + 1;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  // no alignment slack: the dynamic shared window is declared 1024-byte aligned (checked at run time)
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule));
+  static_assert(kSmemBytes <= 232448, "fused backward exceeds the 227 KB shared memory of an SM");
+};
+
+__device__ __forceinline__ void tma_reduce_add_2d(const void* map, uint32_t smem_src, int32_t x, int32_t y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct alignas(64) FusedParams {
+  BwdParams base;
+  CUtensorMap map_dq_acc;   // fp32 [batch*D, nq], box 32 x D, 128B swizzle
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __grid_constant__ FusedParams fp) {
+  using Cfg = FusedCfg<D, VD>;
+  constexpr int kStages = Cfg::kStages;
+  const BwdParams& p = fp.base;
+  extern __shared__ __align__(1024) uint8_t smem_fused[];
+  const uint32_t smem_base = smem_u32(smem_fused);
+  if (smem_base & 1023u) __trap();   // swizzled tiles need 1024-byte alignment
+  uint8_t* smem_gen = smem_fused;
+  const uint32_t k_smem = smem_base;
+  const uint32_t v_smem = smem_base + Cfg::kKBytes;
+  const uint32_t ring = smem_base + Cfg::kRingOffset;
+  const uint32_t ds_smem = smem_base + Cfg::kDsOffset;     // [2][kDsBytes]
+  const uint32_t red_smem = smem_base + Cfg::kRedOffset;   // [2][kRedBytes]
+  const uint32_t stat_smem = smem_base + Cfg::kStatOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_kv_res = bars;
+  const uint32_t bar_full = bars + 8;                        // [kStages]
+  const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
+  const uint32_t bar_s_full = bar_empty + 8 * kStages;       // [2]
+  const uint32_t bar_p_ready = bar_s_full + 16;              // [2]
+  const uint32_t bar_dq_full = bar_p_ready + 16;             // [2]
+  const uint32_t bar_dq_free = bar_dq_full + 16;             // [2]
+  const uint32_t bar_final = bar_dq_free + 16;               // [1]
+  const uint32_t tmem_slot = bar_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+  const float* stat_gen = reinterpret_cast<const float*>(smem_gen + Cfg::kStatOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_blocks);
+  const int kblk = int(blockIdx.x % p.n_blocks);
+  const int k0 = kblk * kBM;
+  const int k_hi = min(k0 + kBM, p.nk) - 1;
+  int qt_first, qt_last;
+  fa_q_tile_range(rule, k0, k_hi, kBN, &qt_first, &qt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {k0};
+    const int hi[1] = {k_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, false, lo, hi, valid, 1, qt_first, qt_last, kBN, p.nq, kFusedThreads / 32);
+  }
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_do);
+      prefetch_tensormap(&p.map_dk);
+      prefetch_tensormap(&p.map_dv);
+      prefetch_tensormap(&fp.map_dq_acc);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      mbar_init(bar_kv_res, 1);
+      mbar_init(bar_final, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, kBM);
+        mbar_init(bar_dq_full + 8 * i, 1);
+        mbar_init(bar_dq_free + 8 * i, 128);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: slot x: S^T_x, later dQ^T_x [x*64, +64);  dP^T_x [128+x*64, +64), later packed fp16
+  // P^T_x [128+x*64, +32) and dS^T_x [128+x*64+32, +32);  dV [256, +VD);  dK [384, +D)
+
+  if (warp >= 8) {
+    setmaxnreg_dec<64>();
+    if (warp == 8) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
+          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+        }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        int qt, tw, tb;
+        while (it.next(&qt, &tw, &tb)) {
+          const int s = t % kStages, u = t / kStages;
+          mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
+          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
+          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
+          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
+          ++t;
+        }
+      }
+    } else if (warp == 9) {
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
+        constexpr uint32_t idesc_dq = idesc_f16(D, kBN, false, true);
+        auto issue_st_dpt = [&](int x, int stage) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
+                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < VD / 16; ++ks)
+            mma_ss(tmem_base + 128 + x * kBN, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
+                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+        };
+        auto issue_dq = [&](int x) {
+#pragma unroll
+          for (int ks = 0; ks < kBM / 16; ++ks)
+            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + (ks >> 2) * (D * 128) + (ks & 3) * 32, 16, 1024),
+                   smem_desc_sw128(ds_smem + x * Cfg::kDsBytes + ks * 2048, 16, 1024), idesc_dq, ks > 0);
+        };
+        auto issue_dv_dk = [&](int x, int stage, bool accumulate) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 256, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+                   idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + 32 + ks * 8,
+                   smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_res, 0);
+          for (int t = 0; t < 2 && t < n; ++t) {
+            mbar_wait(bar_full + 8 * (t % kStages), (t / kStages) & 1);
+            tc_fence_after();
+            issue_st_dpt(t & 1, t % kStages);
+            mma_commit(bar_s_full + 8 * (t & 1));
+          }
+          for (int t = 0; t < n; ++t) {
+            const int x = t & 1, st = t % kStages;
+            mbar_wait(bar_p_ready + 8 * x, (t >> 1) & 1);
+            tc_fence_after();
+#ifndef FA_FUSED_NO_DQ
+            issue_dq(x);                       // first: its drain overlaps the dV / dK products
+            mma_commit(bar_dq_full + 8 * x);
+#endif
+            issue_dv_dk(x, st, t > 0);
+            mma_commit(bar_empty + 8 * st);
+            if (t + 2 < n) {
+              const int t2 = t + 2, s2 = t2 % kStages;
+              mbar_wait(bar_full + 8 * s2, (t2 / kStages) & 1);
+#ifndef FA_FUSED_NO_DQ
+              mbar_wait(bar_dq_free + 8 * x, (t >> 1) & 1);   // dQ^T_x read out: S^T_x may be overwritten
+#endif
+              tc_fence_after();
+              issue_st_dpt(x, s2);
+              mma_commit(bar_s_full + 8 * x);
+            }
+          }
+          mma_commit(bar_final);
+        }
+      }
+    } else if (warp >= 12) {
+      // ---- dQ^T drain: TMEM -> registers -> swizzled staging tile -> TMA reduce-add into fp32 scratch
+      const int rr = threadIdx.x - 384;   // channel row d
+      const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+      int t = 0;
+      TileIter it;
+      it.init(sched, 1, qt_first, qt_last);
+#ifdef FA_FUSED_NO_DQ
+      it.init(sched, 1, 1, 0);
+#endif
+      int qt, tw, tb;
+      while (it.next(&qt, &tw, &tb)) {
+        const int x = t & 1;
+        mbar_wait(bar_dq_full + 8 * x, (t >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t stage = red_smem + h * Cfg::kRedBytes;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_addr + x * kBN + h * 32, v);
+          tmem_wait_ld();
+          if (h == 1) {
+            tc_fence_before();
+            mbar_arrive(bar_dq_free + 8 * x);
+          }
+          if (rr == 0) bulk_wait_read_1();   // the reduce issued two groups ago has finished reading `stage`
+          named_bar_sync(3, 128);
+          const uint32_t row_smem = stage + rr * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(row_smem + ((c ^ (rr & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (rr == 0) {
+#ifndef FA_FUSED_NO_RED
+            tma_reduce_add_2d(&fp.map_dq_acc, stage, qt * kBN + h * 32, b * D);
+#endif
+            tma_store_commit();
+          }
+        }
+        ++t;
+      }
+      if (rr == 0) tma_store_wait_all();
+    }
+  } else {
+    setmaxnreg_inc<192>();
+    const int x = warp >> 2;                 // ping-pong slot this warpgroup serves
+    const int r = threadIdx.x & 127;         // key row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + x * kBN;
+    const uint32_t t_dp = tmem_base + lane_addr + 128 + x * kBN;
+    const uint32_t ds_row = ds_smem + x * Cfg::kDsBytes + r * 128;
+    const int ki = k0 + r;
+    const bool k_valid = ki < p.nk;
+    const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
+    const float scale_log2 = p.scale_log2;
+    int t = 0;
+    TileIter it;
+    it.init(sched, 1, qt_first, qt_last);
+    int qt, tw, tb;
+    while (it.next(&qt, &tw, &tb)) {
+      if ((t & 1) != x) {
+        ++t;
+        continue;
+      }
+      const int st = t % kStages;
+      const int q0 = qt * kBN;
+      const int q_hi = min(q0 + kBN, p.nq) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool ragged = (q0 + kBN > p.nq) || (k0 + kBM > p.nk);
+      mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
+      mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
+      tc_fence_after();
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
+      uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        okmask_lo = okmask_hi = 0u;
+        if (k_valid) {
+          const int nvalid = q_hi - q0 + 1;
+          if (rule.dims == 1 && rule.rule != 2) {
+            int lo, hi;
+            interval_1d(rule, false, kpos, q0, nvalid, &lo, &hi);
+            okmask_lo = interval_bits32(lo, hi, 0);
+            okmask_hi = interval_bits32(lo, hi, 32);
+          } else {
+            okmask_lo = tile_mask32(rule, false, kpos, q0, 0, nvalid);
+            okmask_hi = tile_mask32(rule, false, kpos, q0, 32, nvalid);
+          }
+        }
+      }
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_dp, &dp[0]);
+      tmem_ld32f(t_dp + 32, &dp[32]);
+      tmem_wait_ld();
+      const float* lse_s = stat_gen + st * (2 * kBN);
+      const float* dsum_s = lse_s + kBN;
+      uint32_t pk[32], dk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
+        float p0 = ex2(fmaf(s[c], scale_log2, -lse_s[c]));
+        float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse_s[c + 1]));
+        p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
+        p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
+        pk[c >> 1] = pack_half2(p0, p1);
+        dk[c >> 1] = pack_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]));
+      }
+      tmem_st32(t_dp, pk);          // P^T  -> columns [0, 32) of the dP^T slot (fp16 pairs)
+      tmem_st32(t_dp + 32, dk);     // dS^T -> columns [32, 64)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        st_shared_v4(ds_row + ((c ^ (r & 7)) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+      fence_proxy_async_smem();
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready + 8 * x);
+      ++t;
+    }
+    // epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK (staged over the resident V / K tiles)
+    const int CH = x == 0 ? VD : D;
+    const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 256 : 384);
+    const float out_scale = x == 0 ? 1.f : p.scale;
+    uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
+    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
+    if (t > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+      for (int c = 0; c < CH / 32; ++c) {
+        float o[32];
+        tmem_ld32f(t_acc + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+      }
+    } else {
+      mbar_wait(bar_kv_res, 0);
+      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + x, kBM);
+    if (r == 0) {
+      for (int h = 0; h < 2; ++h)
+        if (k0 + h * 64 < p.nk) {
+          if (x == 0)
+            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+          else
+            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+        }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dQ = fp16(scale * dQ_acc); 8 elements per thread
+__global__ void bwd_dq_convert(const float4* __restrict__ acc, uint4* __restrict__ dq, int64_t n8, float scale) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 a = acc[2 * i], c = acc[2 * i + 1];
+    uint4 o;
+    o.x = pack_half2(a.x * scale, a.y * scale);
+    o.y = pack_half2(a.z * scale, a.w * scale);
+    o.z = pack_half2(c.x * scale, c.y * scale);
+    o.w = pack_half2(c.z * scale, c.w * scale);
+    dq[i] = o;
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 template <int D, int VD>
 cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
@@ -672,6 +1107,40 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  if constexpr (D == 128) {
+    if (a.variant != 4) {
+      // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics
+      float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + stats_bytes(a.batch, nq));
+      const size_t acc_bytes = size_t(a.batch) * D * nq * sizeof(float);
+      FusedParams fp;
+      fp.base = p;
+      if (!make_map_f32_sw128(&fp.map_dq_acc, acc, a.batch * D, nq, 32, D)) return cudaErrorInvalidValue;
+      {
+        ScopedKernel timed("bwd_dq_zero", stream);
+        cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, stream);
+        if (e != cudaSuccess) return e;
+      }
+      {
+        auto kern = bwd_fused_kernel<D, VD>;
+        cudaError_t e =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<D, VD>::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        fp.base.n_blocks = (nk + kBM - 1) / kBM;
+        ScopedKernel timed("bwd_fused_f16_sm100", stream);
+        kern<<<unsigned(int64_t(fp.base.n_blocks) * p.batch), kFusedThreads, FusedCfg<D, VD>::kSmemBytes, stream>>>(fp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+      }
+      {
+        const int64_t n8 = a.batch * int64_t(D) * nq / 8;
+        const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 148 * 16));
+        ScopedKernel timed("bwd_dq_convert", stream);
+        bwd_dq_convert<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(acc),
+                                                   reinterpret_cast<uint4*>(a.d_q), n8, p.scale);
+        return cudaGetLastError();
+      }
+    }
+  }
   {
     auto kern = bwd_dq_kernel<D, VD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D, VD>::kSmemBytes);
@@ -694,7 +1163,11 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   }
 }
 
-size_t bwd_workspace_bytes(int64_t batch, int64_t nq) { return size_t(2) * (batch * nq + kStatPad) * sizeof(float); }
+size_t bwd_workspace_bytes(int64_t batch, int64_t nq, int d, int variant) {
+  size_t s = stats_bytes(batch, nq);
+  if (d == 128 && variant != 4) s += size_t(batch) * d * nq * sizeof(float);
+  return s;
+}
 
 }  // namespace sm100
 
@@ -710,12 +1183,12 @@ bool sm100_f16_backward_supports(const LaunchArgs& a) {
     return false;
   if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
   if (((nq + 255) / 256) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
-  if (a.workspace_bytes < sm100::bwd_workspace_bytes(a.batch, nq)) return false;
+  if (a.workspace_bytes < sm100::bwd_workspace_bytes(a.batch, nq, a.d, a.variant)) return false;
   return true;
 }
 
 size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) {
-  return sm100::bwd_workspace_bytes(a.batch, a.rule.q.total);
+  return sm100::bwd_workspace_bytes(a.batch, a.rule.q.total, a.d, a.variant);
 }
 
 cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream) {
