@@ -130,6 +130,14 @@ int fa_partial_merge(const fa_problem_t* p, const void* o_part, const void* l_pa
 int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_acc, const void* m_acc,
                         void* o, void* l, void* m, void* stream);
 
+/* Ring backward: a gradient shard (dQ of the local queries, or the dK / dV that travel with their K/V
+ * shard) is the sum of the fa_backward results of every (query chunk, key chunk) block; each call is
+ * made with the FINAL l, m, O of the whole sequence, so the blocks simply add.
+ *   fa_grad_accumulate: acc[i] = (first ? 0 : acc[i]) + part[i]    acc float (double for FA_F64)
+ *   fa_grad_finalize  : out[i] = (dtype) acc[i]                                                  */
+int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream);
+int fa_grad_finalize(int32_t dtype, const void* acc, void* out, int64_t n, void* stream);
+
 /* ---- host-side helpers shared with the kernels (same code, fa_rules.h) ---------- */
 
 /* Number of attended (q,k) pairs per batch element under the bit-exact rule; the unit

@@ -64,6 +64,34 @@ class OracleBackend:
         out[0].copy_(oa / torch.where(la > 0, la, torch.ones_like(la))[:, None, :])
         out[1].copy_(la); out[2].copy_(ma)
 
+    # ---- backward stand-in: one block with the FINAL statistics (kernel/internal_test.cu:413-511 algebra)
+    def new_grad_acc(self, like):
+        return torch.zeros_like(like, dtype=torch.float64)
+
+    def new_grad_part(self, q, k, v):
+        return (torch.empty_like(q), torch.empty_like(k), torch.empty_like(v))
+
+    def grad_partial(self, q, k, v, o, l, m, d_o, q_base, k_base, part):
+        qi = q_base + np.arange(self.chunk)
+        kj = k_base + np.arange(self.chunk)
+        mask = qi[:, None] >= kj[None, :]
+        qn, kn, vn, on, ln, mn, don = (x.numpy() for x in (q, k, v, o, l, m, d_o))
+        scale = 1.0 / np.sqrt(self.d)
+        logit = np.einsum("bcq,bck->bqk", qn, kn) * scale
+        P = np.where(mask[None], np.exp(logit - mn[..., None]) / ln[..., None], 0.0)
+        D = np.einsum("bcq,bcq->bq", don, on)
+        dP = np.einsum("bcq,bck->bqk", don, vn)
+        dS = P * (dP - D[..., None]) * scale
+        part[0].copy_(torch.from_numpy(np.einsum("bqk,bck->bcq", dS, kn)))
+        part[1].copy_(torch.from_numpy(np.einsum("bqk,bcq->bck", dS, qn)))
+        part[2].copy_(torch.from_numpy(np.einsum("bqk,bcq->bck", P, don)))
+
+    def grad_add(self, part, acc):
+        acc += part
+
+    def grad_finalize(self, acc, like):
+        return acc.clone()
+
 
 def _worker(rank, world, port, seq, d, v_d, batch, result_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -80,6 +108,39 @@ def _worker(rank, world, port, seq, d, v_d, batch, result_dir):
     ref = da.forward(Q, K, V, pattern.tests_mask((seq,), (seq,), "none_front", "causal"))[0][:, :, idx]
     np.save(os.path.join(result_dir, f"err_{rank}.npy"), np.array([np.abs(O - ref).max()]))
     dist.destroy_process_group()
+
+
+def _worker_bwd(rank, world, port, seq, d, v_d, batch, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(12)
+    Q, K, V, dO = da.random_inputs(rng, np.float64, (batch,), d, v_d, (seq,), (seq,))
+    mask = pattern.tests_mask((seq,), (seq,), "none_front", "causal")
+    O, l, m = da.forward(Q, K, V, mask)
+    ref = dict(zip(("dQ", "dK", "dV"), da.backward(Q, K, V, mask, dO)))
+    layout = ring.ZigZag(seq, world)
+    idx = layout.gather_index(rank)
+    c = layout.chunk
+
+    def halves(X):
+        return [torch.from_numpy(np.ascontiguousarray(X[..., idx[:c]])), torch.from_numpy(np.ascontiguousarray(X[..., idx[c:]]))]
+    d_q, d_kv = ring.ring_backward(OracleBackend(batch, d, v_d, c), layout, rank, halves(Q), halves(K) + halves(V),
+                                   halves(O), halves(l), halves(m), halves(dO), dist, None, "causal")
+    got = {"dQ": np.concatenate([x.numpy() for x in d_q], axis=-1),
+           "dK": np.concatenate([x.numpy() for x in d_kv[:2]], axis=-1),
+           "dV": np.concatenate([x.numpy() for x in d_kv[2:]], axis=-1)}
+    errs = [np.abs(got[n] - ref[n][:, :, idx]).max() for n in ("dQ", "dK", "dV")]
+    np.save(os.path.join(result_dir, f"berr_{rank}.npy"), np.array(errs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ring_backward_driver_matches_dense_oracle(world, tmp_path):
+    """dQ stays local, the dK / dV accumulators travel with their shard and come home after `world` hops."""
+    seq = 16 * world
+    mp.spawn(_worker_bwd, args=(world, _free_port(), seq, 8, 6, 2, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert float(np.load(tmp_path / f"berr_{r}.npy").max()) < 1e-12
 
 
 @pytest.mark.parametrize("world", [2, 4])

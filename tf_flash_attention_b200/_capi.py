@@ -85,6 +85,8 @@ def _load():
         "fa_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_partial_merge": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
         "fa_partial_finalize": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp]),
+        "fa_grad_accumulate": (C.c_int, [C.c_int32, vp, vp, i64, C.c_int, vp]),
+        "fa_grad_finalize": (C.c_int, [C.c_int32, vp, vp, i64, vp]),
         "fa_strerror": (C.c_char_p, [C.c_int]),
         "fa_last_cuda_error": (C.c_int, []),
         "fa_last_path": (C.c_int, []),

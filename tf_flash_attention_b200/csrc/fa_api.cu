@@ -201,6 +201,24 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   return e == cudaSuccess ? FA_OK : cuda_fail(e);
 }
 
+// ---- gradient shards (ring backward) ---------------------------------------------------------
+int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream) {
+  if (dtype < FA_F16 || dtype > FA_F64) return FA_EINVAL_DTYPE;
+  if (n < 0) return FA_EINVAL_SHAPE;
+  if (n == 0) return FA_OK;
+  if (!part || !acc) return FA_EINVAL_NULL;
+  cudaError_t e = fa::grad_accumulate(dtype, part, acc, n, first, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+int fa_grad_finalize(int32_t dtype, const void* acc, void* out, int64_t n, void* stream) {
+  if (dtype < FA_F16 || dtype > FA_F64) return FA_EINVAL_DTYPE;
+  if (n < 0) return FA_EINVAL_SHAPE;
+  if (n == 0) return FA_OK;
+  if (!acc || !out) return FA_EINVAL_NULL;
+  cudaError_t e = fa::grad_finalize(dtype, acc, out, n, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
 // ---- partial results over key shards (K/V ring) -------------------------------------------------
 int fa_partial_merge(const fa_problem_t* p, const void* o_part, const void* l_part, const void* m_part,
                      void* o_acc, void* l_acc, void* m_acc, int first, void* stream) {

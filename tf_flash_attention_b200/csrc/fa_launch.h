@@ -49,6 +49,10 @@ cudaError_t partial_merge(const LaunchArgs& a, const void* o_part, const void* l
 cudaError_t partial_finalize(const LaunchArgs& a, const void* o_acc, const void* l_acc, const void* m_acc, void* o,
                              void* l, void* m, cudaStream_t stream);
 
+// gradient shards of the ring backward: acc (float; double for f64) (+)= part, and the final cast
+cudaError_t grad_accumulate(int dtype, const void* part, void* acc, int64_t n, int first, cudaStream_t stream);
+cudaError_t grad_finalize(int dtype, const void* acc, void* out, int64_t n, cudaStream_t stream);
+
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);
 bool sm100_f16_backward_supports(const LaunchArgs& a);

@@ -108,4 +108,48 @@ cudaError_t partial_finalize(const LaunchArgs& a, const void* o_acc, const void*
   }
 }
 
+// ---- gradient shards (ring backward): acc (+)= part, and the final cast ----------------------
+template <typename T, typename A>
+__global__ void grad_accumulate_kernel(const T* __restrict__ part, A* __restrict__ acc, int64_t n, int first) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    acc[i] = (first ? A(0) : acc[i]) + to_acc<A>(part[i]);
+}
+template <typename T, typename A>
+__global__ void grad_finalize_kernel(const A* __restrict__ acc, T* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    out[i] = from_acc<T>(acc[i]);
+}
+
+template <typename T, typename A>
+static cudaError_t grad_acc_t(const void* part, void* acc, int64_t n, int first, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 16));
+  ScopedKernel timed("grad_accumulate", stream);
+  grad_accumulate_kernel<T, A><<<blocks, 256, 0, stream>>>((const T*)part, (A*)acc, n, first);
+  return cudaGetLastError();
+}
+template <typename T, typename A>
+static cudaError_t grad_fin_t(const void* acc, void* out, int64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int blocks = int(std::min<int64_t>((n + 255) / 256, 148 * 16));
+  ScopedKernel timed("grad_finalize", stream);
+  grad_finalize_kernel<T, A><<<blocks, 256, 0, stream>>>((const A*)acc, (T*)out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t grad_accumulate(int dtype, const void* part, void* acc, int64_t n, int first, cudaStream_t stream) {
+  switch (dtype) {
+    case 0: return grad_acc_t<__half, float>(part, acc, n, first, stream);
+    case 1: return grad_acc_t<float, float>(part, acc, n, first, stream);
+    default: return grad_acc_t<double, double>(part, acc, n, first, stream);
+  }
+}
+cudaError_t grad_finalize(int dtype, const void* acc, void* out, int64_t n, cudaStream_t stream) {
+  switch (dtype) {
+    case 0: return grad_fin_t<__half, float>(acc, out, n, stream);
+    case 1: return grad_fin_t<float, float>(acc, out, n, stream);
+    default: return grad_fin_t<double, double>(acc, out, n, stream);
+  }
+}
+
 }  // namespace fa

@@ -12,6 +12,11 @@ The driver is written against a tiny backend interface so that the host logic (c
 schedule, index bases, skip rule) can be exercised on CPU with the gloo backend and the NumPy oracle
 as the compute stand-in (tests/test_ring_gloo.py); the product backend is `DeviceBackend` below, which
 calls the C ABI (fa_forward / fa_partial_merge / fa_partial_finalize).
+
+Backward (`ring_backward`): every block (local query chunk x visiting key chunk) is one fa_backward call
+made with the FINAL O, l, m of the whole sequence, so block results simply add. dQ accumulates locally in
+fp32; the fp32 dK / dV accumulators travel around the ring together with their K/V shard (one extra hop
+at the end brings them home), K/V one step ahead of the compute, the accumulators right behind it.
 """
 import ctypes as C
 
@@ -116,6 +121,34 @@ class DeviceBackend:
     def empty_like_kv(self, kv):
         return [self.torch.empty_like(x) for x in kv]
 
+    # ---- backward ---------------------------------------------------------------------------
+    def new_grad_acc(self, like):
+        return self.torch.zeros(like.shape, dtype=self.acc_dtype, device=like.device)
+
+    def new_grad_part(self, q, k, v):
+        return (self.torch.empty_like(q), self.torch.empty_like(k), self.torch.empty_like(v))
+
+    def grad_partial(self, q, k, v, o, l, m, d_o, q_base, k_base, part):
+        self.p.q_index_base, self.p.k_index_base, self.p.accumulate = q_base, k_base, 0
+        need = _capi.lib.fa_workspace_bytes(C.byref(self.p), 1)
+        if need and (self._ws is None or self._ws.numel() < need):
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=q.device)
+        dq, dk, dv = part
+        _capi.check(_capi.lib.fa_backward(C.byref(self.p), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                          l.data_ptr(), m.data_ptr(), d_o.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                          dv.data_ptr(), self._ws.data_ptr() if need else None, need, self._stream()),
+                    "fa_backward")
+
+    def grad_add(self, part, acc):
+        _capi.check(_capi.lib.fa_grad_accumulate(self.p.dtype, part.data_ptr(), acc.data_ptr(), part.numel(), 0,
+                                                 self._stream()), "fa_grad_accumulate")
+
+    def grad_finalize(self, acc, like):
+        out = self.torch.empty_like(like)
+        _capi.check(_capi.lib.fa_grad_finalize(self.p.dtype, acc.data_ptr(), out.data_ptr(), acc.numel(),
+                                               self._stream()), "fa_grad_finalize")
+        return out
+
 
 def ring_forward(backend, layout, rank, q_chunks, kv_chunks, dist=None, group=None, rule="causal", is_causal=False):
     """q_chunks: [Q_a, Q_b] local query chunks, each [batch..., d, c] contiguous.
@@ -153,6 +186,71 @@ def ring_forward(backend, layout, rank, q_chunks, kv_chunks, dist=None, group=No
         backend.finalize(acc[qa], out)
         outs.append(out)
     return outs
+
+
+def ring_backward(backend, layout, rank, q_chunks, kv_chunks, o_chunks, l_chunks, m_chunks, do_chunks, dist=None,
+                  group=None, rule="causal", is_causal=False):
+    """Gradients of ring_forward. q/o/l/m/do_chunks: the two local query chunks (O, l, m as ring_forward
+    returned them, i.e. final over the whole sequence); kv_chunks: [K_a, K_b, V_a, V_b].
+    Returns ([dQ_a, dQ_b], [dK_a, dK_b, dV_a, dV_b]) for the local chunks."""
+    world = layout.world
+    cur = list(kv_chunks)
+    nxt = backend.empty_like_kv(cur) if world > 1 else None
+    dq_acc = [backend.new_grad_acc(q) for q in q_chunks]
+    dkv_acc = [backend.new_grad_acc(x) for x in cur]          # travels with `cur`
+    dkv_nxt = [backend.new_grad_acc(x) for x in cur] if world > 1 else None
+    part = backend.new_grad_part(q_chunks[0], cur[0], cur[2])
+    for step in range(world):
+        reqs = []
+        if world > 1 and step + 1 < world:                     # K/V shard for the next step, overlapped
+            ops = []
+            for t_send, t_recv in zip(cur, nxt):
+                ops.append(dist.P2POp(dist.isend, t_send, (rank + 1) % world, group))
+                ops.append(dist.P2POp(dist.irecv, t_recv, (rank - 1) % world, group))
+            reqs = dist.batch_isend_irecv(ops)
+        _, plan = step_plan(layout, rank, step, rule, is_causal)
+        for qa, kb, q_base, k_base in plan:
+            backend.grad_partial(q_chunks[qa], cur[kb], cur[2 + kb], o_chunks[qa], l_chunks[qa], m_chunks[qa],
+                                 do_chunks[qa], q_base, k_base, part)
+            backend.grad_add(part[0], dq_acc[qa])
+            backend.grad_add(part[1], dkv_acc[kb])
+            backend.grad_add(part[2], dkv_acc[2 + kb])
+        for r in reqs:
+            r.wait()
+        if world > 1:
+            # the accumulators follow their shard (after the last step this hop returns them to the owner)
+            ops = []
+            for t_send, t_recv in zip(dkv_acc, dkv_nxt):
+                ops.append(dist.P2POp(dist.isend, t_send, (rank + 1) % world, group))
+                ops.append(dist.P2POp(dist.irecv, t_recv, (rank - 1) % world, group))
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            dkv_acc, dkv_nxt = dkv_nxt, dkv_acc
+            if step + 1 < world:
+                cur, nxt = nxt, cur
+    d_q = [backend.grad_finalize(dq_acc[i], q_chunks[i]) for i in range(2)]
+    d_kv = [backend.grad_finalize(dkv_acc[i], kv_chunks[i]) for i in range(4)]
+    return d_q, d_kv
+
+
+def ring_causal_1d_backward(Q, K, V, O, l, m, dO, sync_mode="none_front", group=None):
+    """Gradients of ring_causal_1d: all tensors are this rank's zig-zag shards (chunk r then chunk 2G-1-r);
+    O, l, m as returned by ring_causal_1d(..., returning_l_m=True). Returns (dQ, dK, dV) shards."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    layout = ZigZag(Q.shape[-1] * world, world)
+    c = layout.chunk
+    codes = {torch.float16: _capi.FA_F16, torch.float32: _capi.FA_F32, torch.float64: _capi.FA_F64}
+    backend = DeviceBackend(codes[Q.dtype], "causal", sync_mode, 1, 0, False, Q.shape[:-2], Q.shape[-2], V.shape[-2], c,
+                            layout.seq_len)
+
+    def halves(x):
+        return [x[..., :c].contiguous(), x[..., c:].contiguous()]
+    d_q, d_kv = ring_backward(backend, layout, rank, halves(Q), halves(K) + halves(V), halves(O), halves(l), halves(m),
+                              halves(dO), dist if world > 1 else None, group, "causal")
+    return (torch.cat(d_q, dim=-1), torch.cat(d_kv[:2], dim=-1), torch.cat(d_kv[2:], dim=-1))
 
 
 def ring_causal_1d(Q, K, V, sync_mode="none_front", group=None, returning_l_m=False):
