@@ -154,7 +154,7 @@ def cpu_reference_leg(w, nnz, steps, warmup, heads):
 
 def ring_bench(args, w, nnz, config, rank, world, local_rank):
     """C5: one causal sequence of 131072 sharded zig-zag over the ranks; STRONG scaling (total work fixed).
-    Forward only (the ring backward is a later row of SURVEY.md section 8f)."""
+    Forward by default; `--ring-bwd` times forward + ring backward."""
     import torch
     import torch.distributed as dist
     from tf_flash_attention_b200 import _capi, ring
@@ -169,10 +169,18 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
     def u(ch):
         return (torch.rand(w["batch"] + (ch, shard), generator=g, device=dev) * 4 - 2).half()
     Q, K, V = u(w["d"]), u(w["d"]), u(w["v_d"])
+    dO = u(w["v_d"])
+
+    def ring_step():
+        if not args.ring_bwd:
+            ring.ring_causal_1d(Q, K, V)
+            return
+        O, l, m = ring.ring_causal_1d(Q, K, V, returning_l_m=True)
+        ring.ring_causal_1d_backward(Q, K, V, O, l, m, dO)
     sampler = ClockSampler(local_rank)
     sampler.launch()
     for _ in range(max(3, args.warmup)):
-        ring.ring_causal_1d(Q, K, V)
+        ring_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -182,7 +190,7 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        ring.ring_causal_1d(Q, K, V)
+        ring_step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -194,16 +202,18 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     fwd_flops = 2.0 * nnz * (w["d"] + w["v_d"]) * int(np.prod(w["batch"]))
+    if args.ring_bwd:
+        fwd_flops += 2.0 * nnz * (3 * w["d"] + 2 * w["v_d"]) * int(np.prod(w["batch"]))
     value = fwd_flops / (ms * 1e-3) / 1e12
     peaks = measured_peaks()
     peak = (peaks["tensor_sustained"] or peaks["tensor_burst"]) * world
     config = dict(config, flops_per_step=fwd_flops, parallelism=f"K/V ring, zig-zag chunks, {world} rank(s), NCCL send/recv")
-    config["pass"] = "fwd"
-    line = {"metric": "attention fwd TFLOPS (unmasked FLOPs), single sequence K/V ring", "value": value, "unit": "TFLOPS",
+    config["pass"] = "fwd+bwd" if args.ring_bwd else "fwd"
+    line = {"metric": f"attention {config['pass']} TFLOPS (unmasked FLOPs), single sequence K/V ring", "value": value, "unit": "TFLOPS",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
             "data": "synthetic U(-2,2)", "config": config, "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "fwd_f16_sm100 (per-block partials) + partial_merge",
+            "roofline": {"bound": "tensor", "kernel": "fwd_f16_sm100 (per-block partials) + partial_merge" + (" + backward blocks + grad_accumulate" if args.ring_bwd else ""),
                          "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak, "traffic": None,
                          "peak_source": peaks["source"] + f", sustained bf16 GEMM x {world} GPUs"}}
     if rank == 0:
@@ -225,6 +235,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-refkernel", action="store_true")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--ring-bwd", action="store_true", help="C5: time forward + ring backward")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
