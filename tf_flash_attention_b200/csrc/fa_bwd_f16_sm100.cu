@@ -675,12 +675,22 @@ static bool make_map_f32_sw128(CUtensorMap* map, const void* base, int64_t rows,
 // instead of 7):
 //     dQ^T[d, q] = K^T[d, keys] . dS^T[keys, q]
 // A = the resident K tile re-read K-major, B = dS^T written by the softmax warps to shared memory in the
-// MN-major 128B-swizzled layout (one 128-byte row of 64 queries per key), accumulator = the S^T slot of
-// the same ping-pong slot (free once the softmax warpgroup has read it). A fourth warpgroup drains the
+// MN-major 128B-swizzled layout (one 128-byte row of 64 queries per key), accumulator = the dP^T slot of
+// the same ping-pong slot (the dP^T columns, free once the softmax warpgroup has read them). A fourth warpgroup drains the
 // dQ^T accumulator and adds it into an fp32 [batch*D, nq] scratch tensor with TMA reduce-add
 // (cp.reduce.async.bulk.tensor ... .add); bwd_dq_convert scales and rounds it to fp16 afterwards.
 // (The order of the fp32 additions into the scratch tensor is not fixed, so dQ may differ in the last
 // fp16 bit between runs; dK and dV are deterministic.)
+#ifdef FA_DBG_TIMELINE
+// developer-only (tools/timeline_bwd.py): clock64 stamps of CTA 0 -> g_dbg_bwd[role][t][event]
+__device__ long long* g_dbg_bwd = nullptr;
+#define FB_STAMP(role, j, ev)                                                                           \
+  do {                                                                                                  \
+    if (g_dbg_bwd && blockIdx.x == 0 && (j) < 128) g_dbg_bwd[((role) * 128 + (j)) * 4 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define FB_STAMP(role, j, ev)
+#endif
 constexpr int kFusedThreads = 512;
 
 template <int D, int VD>
@@ -803,11 +813,62 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
-  // TMEM columns: slot x: S^T_x, later dQ^T_x [x*64, +64);  dP^T_x [128+x*64, +64), later packed fp16
-  // P^T_x [128+x*64, +32) and dS^T_x [128+x*64+32, +32);  dV [256, +VD);  dK [384, +D)
+  // TMEM columns: slot x: S^T_x [x*64, +64), later packed fp16 P^T_x [x*64, +32) and dS^T_x [x*64+32, +32);
+  // dP^T_x [128+x*64, +64), later dQ^T_x (free once the softmax warpgroup has read dP^T);  dV [256, +VD);
+  // dK [384, +D). S^T of the next sub-tile only has to wait for dV / dK of this one (in order on the
+  // tensor pipe); dP^T of the next sub-tile waits for the dQ^T drain, one S^T product later.
 
-  if (warp >= 8) {
-    setmaxnreg_dec<64>();
+  // register budget (512 threads x 128 at launch): softmax 8 warps x 184, drain 4 warps x 88, others 4 x 56
+  if (warp >= 12) {
+    setmaxnreg_dec<88>();
+    // ---- dQ^T drain: TMEM -> registers -> swizzled staging tile -> TMA reduce-add into fp32 scratch
+    const int rr = threadIdx.x - 384;   // channel row d
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    int t = 0;
+    TileIter it;
+    it.init(sched, 1, qt_first, qt_last);
+#ifdef FA_FUSED_NO_DQ
+    it.init(sched, 1, 1, 0);
+#endif
+    int qt, tw, tb;
+    while (it.next(&qt, &tw, &tb)) {
+      const int x = t & 1;
+      mbar_wait(bar_dq_full + 8 * x, (t >> 1) & 1);
+      tc_fence_after();
+      if (rr == 0) FB_STAMP(2, t, 0);
+      // whole accumulator to registers first, so that the TMEM columns go back to the MMA warp at once
+      uint32_t va[32], vb[32];
+      tmem_ld32(tmem_base + lane_addr + 128 + x * kBN, va);
+      tmem_ld32(tmem_base + lane_addr + 128 + x * kBN + 32, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_dq_free + 8 * x);
+      if (rr == 0) FB_STAMP(2, t, 1);
+      const uint32_t row_off = rr * 128;
+      auto stage_half = [&](const uint32_t (&v)[32], int h) {
+        const uint32_t stage = red_smem + h * Cfg::kRedBytes;
+        if (rr == 0) bulk_wait_read_1();   // the reduce issued two groups ago has finished reading `stage`
+        named_bar_sync(3, 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(stage + row_off + ((c ^ (rr & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (rr == 0) {
+#ifndef FA_FUSED_NO_RED
+          tma_reduce_add_2d(&fp.map_dq_acc, stage, qt * kBN + h * 32, b * D);
+#endif
+          tma_store_commit();
+        }
+      };
+      stage_half(va, 0);
+      stage_half(vb, 1);
+      if (rr == 0) FB_STAMP(2, t, 2);
+      ++t;
+    }
+    if (rr == 0) tma_store_wait_all();
+  } else if (warp >= 8) {
+    setmaxnreg_dec<56>();
     if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
@@ -828,6 +889,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
           const int64_t off = int64_t(b) * p.nq + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
+          FB_STAMP(3, t, 3);
           ++t;
         }
       }
@@ -840,12 +902,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
         constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
         constexpr uint32_t idesc_dq = idesc_f16(D, kBN, false, true);
-        auto issue_st_dpt = [&](int x, int stage) {
-          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+        auto issue_st = [&](int x, int stage) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
             mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
                    smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+        };
+        auto issue_dpt = [&](int x, int stage) {
+          const uint32_t do_s = ring + stage * Cfg::kStageBytes + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
             mma_ss(tmem_base + 128 + x * kBN, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
@@ -854,18 +919,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         auto issue_dq = [&](int x) {
 #pragma unroll
           for (int ks = 0; ks < kBM / 16; ++ks)
-            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + (ks >> 2) * (D * 128) + (ks & 3) * 32, 16, 1024),
+            mma_ss(tmem_base + 128 + x * kBN,
+                   smem_desc_sw128(k_smem + (ks >> 2) * (D * 128) + (ks & 3) * 32, 16, 1024),
                    smem_desc_sw128(ds_smem + x * Cfg::kDsBytes + ks * 2048, 16, 1024), idesc_dq, ks > 0);
         };
         auto issue_dv_dk = [&](int x, int stage, bool accumulate) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 256, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+            mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
                    idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + 32 + ks * 8,
+            mma_ts(tmem_base + 384, tmem_base + x * kBN + 32 + ks * 8,
                    smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
         };
         if (n > 0) {
@@ -873,79 +939,46 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
           for (int t = 0; t < 2 && t < n; ++t) {
             mbar_wait(bar_full + 8 * (t % kStages), (t / kStages) & 1);
             tc_fence_after();
-            issue_st_dpt(t & 1, t % kStages);
+            issue_st(t & 1, t % kStages);
+            issue_dpt(t & 1, t % kStages);
             mma_commit(bar_s_full + 8 * (t & 1));
           }
           for (int t = 0; t < n; ++t) {
             const int x = t & 1, st = t % kStages;
             mbar_wait(bar_p_ready + 8 * x, (t >> 1) & 1);
             tc_fence_after();
+            FB_STAMP(1, t, 0);
 #ifndef FA_FUSED_NO_DQ
             issue_dq(x);                       // first: its drain overlaps the dV / dK products
             mma_commit(bar_dq_full + 8 * x);
 #endif
+            FB_STAMP(3, t, 0);
             issue_dv_dk(x, st, t > 0);
             mma_commit(bar_empty + 8 * st);
+            FB_STAMP(3, t, 1);
             if (t + 2 < n) {
               const int t2 = t + 2, s2 = t2 % kStages;
               mbar_wait(bar_full + 8 * s2, (t2 / kStages) & 1);
-#ifndef FA_FUSED_NO_DQ
-              mbar_wait(bar_dq_free + 8 * x, (t >> 1) & 1);   // dQ^T_x read out: S^T_x may be overwritten
-#endif
               tc_fence_after();
-              issue_st_dpt(x, s2);
+              FB_STAMP(3, t, 2);
+              issue_st(x, s2);
+              FB_STAMP(1, t, 1);
+#ifndef FA_FUSED_NO_DQ
+              mbar_wait(bar_dq_free + 8 * x, (t >> 1) & 1);   // dQ^T_x read out: dP^T_x may be overwritten
+              tc_fence_after();
+#endif
+              FB_STAMP(1, t, 2);
+              issue_dpt(x, s2);
               mma_commit(bar_s_full + 8 * x);
+              FB_STAMP(1, t, 3);
             }
           }
           mma_commit(bar_final);
         }
       }
-    } else if (warp >= 12) {
-      // ---- dQ^T drain: TMEM -> registers -> swizzled staging tile -> TMA reduce-add into fp32 scratch
-      const int rr = threadIdx.x - 384;   // channel row d
-      const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
-      int t = 0;
-      TileIter it;
-      it.init(sched, 1, qt_first, qt_last);
-#ifdef FA_FUSED_NO_DQ
-      it.init(sched, 1, 1, 0);
-#endif
-      int qt, tw, tb;
-      while (it.next(&qt, &tw, &tb)) {
-        const int x = t & 1;
-        mbar_wait(bar_dq_full + 8 * x, (t >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t stage = red_smem + h * Cfg::kRedBytes;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_addr + x * kBN + h * 32, v);
-          tmem_wait_ld();
-          if (h == 1) {
-            tc_fence_before();
-            mbar_arrive(bar_dq_free + 8 * x);
-          }
-          if (rr == 0) bulk_wait_read_1();   // the reduce issued two groups ago has finished reading `stage`
-          named_bar_sync(3, 128);
-          const uint32_t row_smem = stage + rr * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            st_shared_v4(row_smem + ((c ^ (rr & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          fence_proxy_async_smem();
-          named_bar_sync(3, 128);
-          if (rr == 0) {
-#ifndef FA_FUSED_NO_RED
-            tma_reduce_add_2d(&fp.map_dq_acc, stage, qt * kBN + h * 32, b * D);
-#endif
-            tma_store_commit();
-          }
-        }
-        ++t;
-      }
-      if (rr == 0) tma_store_wait_all();
     }
   } else {
-    setmaxnreg_inc<192>();
+    setmaxnreg_inc<184>();
     const int x = warp >> 2;                 // ping-pong slot this warpgroup serves
     const int r = threadIdx.x & 127;         // key row
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
@@ -973,6 +1006,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
       mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
       tc_fence_after();
+      if (r == 0) FB_STAMP(0, t, 0);
       // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
       uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
       if (cls == FA_TILE_PARTIAL || ragged) {
@@ -996,21 +1030,49 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       tmem_ld32f(t_dp, &dp[0]);
       tmem_ld32f(t_dp + 32, &dp[32]);
       tmem_wait_ld();
-      const float* lse_s = stat_gen + st * (2 * kBN);
-      const float* dsum_s = lse_s + kBN;
+      if (r == 0) FB_STAMP(0, t, 1);
+      // per-column statistics as warp-uniform 16-byte shared loads; the loop is issue-bound (two softmax warps
+      // and a drain warp share each scheduler), so unmasked sub-tiles take a variant without the selects
+      const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN));
+      const float4* dsum4 = lse4 + kBN / 4;
       uint32_t pk[32], dk[32];
+      if (okmask_lo == 0xffffffffu && okmask_hi == 0xffffffffu) {
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
-        float p0 = ex2(fmaf(s[c], scale_log2, -lse_s[c]));
-        float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse_s[c + 1]));
-        p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
-        p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
-        pk[c >> 1] = pack_half2(p0, p1);
-        dk[c >> 1] = pack_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]));
+        for (int c = 0; c < 64; c += 4) {
+          const float4 ls = lse4[c >> 2];
+          const float4 dd = dsum4[c >> 2];
+          const float p0 = ex2(fmaf(s[c], scale_log2, -ls.x));
+          const float p1 = ex2(fmaf(s[c + 1], scale_log2, -ls.y));
+          const float p2 = ex2(fmaf(s[c + 2], scale_log2, -ls.z));
+          const float p3 = ex2(fmaf(s[c + 3], scale_log2, -ls.w));
+          pk[c >> 1] = pack_half2(p0, p1);
+          pk[(c >> 1) + 1] = pack_half2(p2, p3);
+          dk[c >> 1] = pack_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y));
+          dk[(c >> 1) + 1] = pack_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const uint32_t mword = (c < 32 ? okmask_lo : okmask_hi) >> (c & 31);
+          const float4 ls = lse4[c >> 2];
+          const float4 dd = dsum4[c >> 2];
+          float p0 = ex2(fmaf(s[c], scale_log2, -ls.x));
+          float p1 = ex2(fmaf(s[c + 1], scale_log2, -ls.y));
+          float p2 = ex2(fmaf(s[c + 2], scale_log2, -ls.z));
+          float p3 = ex2(fmaf(s[c + 3], scale_log2, -ls.w));
+          p0 = mword & 1u ? p0 : 0.f;
+          p1 = mword & 2u ? p1 : 0.f;
+          p2 = mword & 4u ? p2 : 0.f;
+          p3 = mword & 8u ? p3 : 0.f;
+          pk[c >> 1] = pack_half2(p0, p1);
+          pk[(c >> 1) + 1] = pack_half2(p2, p3);
+          dk[c >> 1] = pack_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y));
+          dk[(c >> 1) + 1] = pack_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w));
+        }
       }
-      tmem_st32(t_dp, pk);          // P^T  -> columns [0, 32) of the dP^T slot (fp16 pairs)
-      tmem_st32(t_dp + 32, dk);     // dS^T -> columns [32, 64)
+      if (r == 0) FB_STAMP(0, t, 2);
+      tmem_st32(t_s, pk);           // P^T  -> columns [0, 32) of the S^T slot (fp16 pairs)
+      tmem_st32(t_s + 32, dk);      // dS^T -> columns [32, 64)
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         st_shared_v4(ds_row + ((c ^ (r & 7)) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
@@ -1018,6 +1080,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * x);
+      if (r == 0) FB_STAMP(0, t, 3);
       ++t;
     }
     // epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK (staged over the resident V / K tiles)
@@ -1162,6 +1225,10 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
   }
 }
+
+#ifdef FA_DBG_TIMELINE
+extern "C" void fa_debug_set_buffer_bwd(void* buf) { cudaMemcpyToSymbol(g_dbg_bwd, &buf, sizeof(buf)); }
+#endif
 
 size_t bwd_workspace_bytes(int64_t batch, int64_t nq, int d, int variant) {
   size_t s = stats_bytes(batch, nq);
