@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       mbar_init(bar_final, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_s_full + 8 * i, 1);
-        mbar_init(bar_p_ready + 8 * i, kBM);
+        mbar_init(bar_p_ready + 8 * i, 2 * kBM);
         mbar_init(bar_dq_full + 8 * i, 1);
         mbar_init(bar_dq_free + 8 * i, 128);
       }
@@ -927,11 +927,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
-                   idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+            mma_ts(tmem_base + 256, tmem_base + x * kBN + (ks >> 1) * 32 + (ks & 1) * 8,
+                   smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 384, tmem_base + x * kBN + 32 + ks * 8,
+            mma_ts(tmem_base + 384, tmem_base + x * kBN + (ks >> 1) * 32 + 16 + (ks & 1) * 8,
                    smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
         };
         if (n > 0) {
@@ -979,12 +979,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
     }
   } else {
     setmaxnreg_inc<184>();
-    const int x = warp >> 2;                 // ping-pong slot this warpgroup serves
+    // Both warpgroups work on EVERY sub-tile (no row reduction in the backward pass): warpgroup x takes the
+    // query columns [32x, 32x+32) -> half the softmax latency on the S^T -> P^T/dS^T -> dV/dK/dQ chain.
+    const int x = warp >> 2;                 // column half in the main loop; dV / dK role in the epilogue
     const int r = threadIdx.x & 127;         // key row
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_addr + x * kBN;
-    const uint32_t t_dp = tmem_base + lane_addr + 128 + x * kBN;
-    const uint32_t ds_row = ds_smem + x * Cfg::kDsBytes + r * 128;
     const int ki = k0 + r;
     const bool k_valid = ki < p.nk;
     const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
@@ -994,51 +993,43 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
     it.init(sched, 1, qt_first, qt_last);
     int qt, tw, tb;
     while (it.next(&qt, &tw, &tb)) {
-      if ((t & 1) != x) {
-        ++t;
-        continue;
-      }
+      const int slot = t & 1;
       const int st = t % kStages;
       const int q0 = qt * kBN;
       const int q_hi = min(q0 + kBN, p.nq) - 1;
       const int cls = it.cls(0, tw, tb);
       const bool ragged = (q0 + kBN > p.nq) || (k0 + kBM > p.nk);
+      const uint32_t t_s = tmem_base + lane_addr + slot * kBN + x * 32;   // own 32 columns of S^T (dP^T at +128)
       mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
-      mbar_wait(bar_s_full + 8 * x, (t >> 1) & 1);
+      mbar_wait(bar_s_full + 8 * slot, (t >> 1) & 1);
       tc_fence_after();
       if (r == 0) FB_STAMP(0, t, 0);
       // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
-      uint32_t okmask_lo = 0xffffffffu, okmask_hi = 0xffffffffu;
+      uint32_t okmask = 0xffffffffu;
       if (cls == FA_TILE_PARTIAL || ragged) {
-        okmask_lo = okmask_hi = 0u;
+        okmask = 0u;
         if (k_valid) {
           const int nvalid = q_hi - q0 + 1;
           if (rule.dims == 1 && rule.rule != 2) {
             int lo, hi;
             interval_1d(rule, false, kpos, q0, nvalid, &lo, &hi);
-            okmask_lo = interval_bits32(lo, hi, 0);
-            okmask_hi = interval_bits32(lo, hi, 32);
+            okmask = interval_bits32(lo, hi, x * 32);
           } else {
-            okmask_lo = tile_mask32(rule, false, kpos, q0, 0, nvalid);
-            okmask_hi = tile_mask32(rule, false, kpos, q0, 32, nvalid);
+            okmask = tile_mask32(rule, false, kpos, q0, x * 32, nvalid);
           }
         }
       }
-      float s[64], dp[64];
-      tmem_ld32f(t_s, &s[0]);
-      tmem_ld32f(t_s + 32, &s[32]);
-      tmem_ld32f(t_dp, &dp[0]);
-      tmem_ld32f(t_dp + 32, &dp[32]);
+      float s[32], dp[32];
+      tmem_ld32f(t_s, s);
+      tmem_ld32f(t_s + 128, dp);
       tmem_wait_ld();
       if (r == 0) FB_STAMP(0, t, 1);
-      // per-column statistics as warp-uniform 16-byte shared loads; the loop is issue-bound (two softmax warps
-      // and a drain warp share each scheduler), so unmasked sub-tiles take a variant without the selects
-      const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN));
+      const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN) + x * 32);
       const float4* dsum4 = lse4 + kBN / 4;
-      uint32_t pk[32], dk[32];
-      if (okmask_lo == 0xffffffffu && okmask_hi == 0xffffffffu) {
+      uint32_t pk[16], dk[16];
+      if (okmask == 0xffffffffu) {
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
+        for (int c = 0; c < 32; c += 4) {
           const float4 ls = lse4[c >> 2];
           const float4 dd = dsum4[c >> 2];
           const float p0 = ex2(fmaf(s[c], scale_log2, -ls.x));
@@ -1052,8 +1043,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          const uint32_t mword = (c < 32 ? okmask_lo : okmask_hi) >> (c & 31);
+        for (int c = 0; c < 32; c += 4) {
+          const uint32_t mword = okmask >> c;
           const float4 ls = lse4[c >> 2];
           const float4 dd = dsum4[c >> 2];
           float p0 = ex2(fmaf(s[c], scale_log2, -ls.x));
@@ -1071,15 +1062,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         }
       }
       if (r == 0) FB_STAMP(0, t, 2);
-      tmem_st32(t_s, pk);           // P^T  -> columns [0, 32) of the S^T slot (fp16 pairs)
-      tmem_st32(t_s + 32, dk);      // dS^T -> columns [32, 64)
+      tmem_st16(t_s, pk);           // P^T (fp16 pairs) over the first 16 of this half's S^T columns
+      tmem_st16(t_s + 16, dk);      // dS^T over the other 16
+      const uint32_t ds_row = ds_smem + slot * Cfg::kDsBytes + r * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        st_shared_v4(ds_row + ((c ^ (r & 7)) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        st_shared_v4(ds_row + (((x * 4 + c) ^ (r & 7)) << 4), dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
       fence_proxy_async_smem();
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(bar_p_ready + 8 * x);
+      mbar_arrive(bar_p_ready + 8 * slot);
       if (r == 0) FB_STAMP(0, t, 3);
       ++t;
     }
