@@ -50,6 +50,13 @@ WORKLOADS = {
     "C4f64": dict(desc="full_1d cross-attention Lq=1024 Lk=8192 scale_end fp64 (DFMA) head_dim 64, 16 heads",
                   seq_dims=1, dtype="float64", batch=(4, 4), d=64, v_d=64, q=(1024,), k=(8192,), rule="full",
                   sync="scale_end", w=1, s=0, c=0),
+    # bandwidth-bound short-sequence cases (north_star: "achieved HBM GB/s for the bandwidth-bound short-sequence cases")
+    "S1": dict(desc="causal_1d fp16 short sequences: 16384 heads x seq 256, head_dim 64 (HBM-bound)", seq_dims=1,
+               dtype="float16", batch=(64, 256), d=64, v_d=64, q=(256,), k=(256,), rule="causal",
+               sync="none_front", w=1, s=0, c=0),
+    "S2": dict(desc="local_1d fp16 window 32, 2048 heads x seq 4096, head_dim 64 (HBM-bound)", seq_dims=1,
+               dtype="float16", batch=(8, 256), d=64, v_d=64, q=(4096,), k=(4096,), rule="local",
+               sync="none_front", w=32, s=0, c=0),
     "C5": dict(desc="causal_1d fp16 single sequence 131072, head_dim 128, 16 heads, K/V ring over NCCL (fwd)",
                seq_dims=1, dtype="float16", batch=(1, 16), d=128, v_d=128, q=(131072,), k=(131072,), rule="causal",
                sync="none_front", w=1, s=0, c=0, ring=True),
@@ -235,6 +242,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-refkernel", action="store_true")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--override", type=int, default=0, help="fa_set_path_override value (developer A/B)")
     ap.add_argument("--ring-bwd", action="store_true", help="C5: time forward + ring backward")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -315,6 +323,8 @@ def main():
         if not args.fwd_only:
             bwd()
 
+    if args.override:
+        _capi.lib.fa_set_path_override(args.override)
     sampler = ClockSampler(local_rank)
     sampler.launch()
     for _ in range(max(3, args.warmup)):
@@ -368,7 +378,7 @@ def main():
     if kernels:
         dom = max(kernels, key=lambda n: kernels[n]["share"])
         bwd_names = [n for n in kernels if "bwd" in n]
-        if dom in ("fwd_f16_sm100", "generic_fwd", "fwd_f32_3xtf32_sm100"):
+        if dom.startswith("fwd_") or dom == "generic_fwd":
             ach = fwd_flops / (kernels[dom]["avg_ms"] * 1e-3) / 1e12
             what = f"{dom}: 2*nnz*(d+v_d)*batch FLOPs per launch"
             traffic = NCU_TRAFFIC.get((args.workload, "fwd"))
@@ -384,6 +394,27 @@ def main():
                     "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_fused_ncu.md (bwd: fused kernel only)" if traffic else None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
                     "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic": what}
+        # HBM side of the roofline: algorithmic bytes of the same kernel(s) over their duration.
+        # Workloads whose arithmetic intensity is below the ridge (short sequences, narrow windows) are HBM-bound
+        # and report that as the primary bound.
+        esz = {"float16": 2, "float32": 4, "float64": 8}[w["dtype"]]
+        lsz = 4 if w["dtype"] == "float16" else esz
+        nb, nq_, nk_ = int(np.prod(w["batch"])), int(np.prod(w["q"])), int(np.prod(w["k"]))
+        fwd_bytes = esz * nb * (nq_ * w["d"] + nk_ * w["d"] + nk_ * w["v_d"] + nq_ * w["v_d"]) + nb * nq_ * (lsz + esz)
+        bwd_bytes = esz * nb * (2 * nq_ * w["d"] + 2 * nk_ * w["d"] + 2 * nk_ * w["v_d"] + 2 * nq_ * w["v_d"]) + nb * nq_ * (lsz + esz)
+        is_fwd = roofline["kernel"].startswith("fwd_") or roofline["kernel"] == "generic_fwd"
+        k_bytes = fwd_bytes if is_fwd else bwd_bytes
+        k_ms = kernels[roofline["kernel"]]["avg_ms"] if is_fwd else sum(kernels[n]["avg_ms"] for n in bwd_names)
+        k_flops = fwd_flops if is_fwd else bwd_flops
+        gbs = k_bytes / (k_ms * 1e-3) / 1e9
+        ridge = peak * 1e12 / (peaks["hbm"] * 1e9)
+        roofline["hbm"] = {"algorithmic_bytes": k_bytes, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": gbs / peaks["hbm"], "intensity_flop_per_byte": k_flops / k_bytes,
+                           "ridge_flop_per_byte": ridge}
+        if k_flops / k_bytes < ridge:
+            roofline.update({"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                             "frac": gbs / peaks["hbm"], "tensor": {"achieved": ach, "peak": peak, "frac": ach / peak},
+                             "algorithmic": what + f"; {k_bytes} algorithmic bytes (inputs and outputs once)"})
         if "fwd_f16_sm100" in kernels:
             fa_ = fwd_flops / (kernels["fwd_f16_sm100"]["avg_ms"] * 1e-3) / 1e12
             roofline["fwd_kernel"] = {"achieved": fa_, "frac": fa_ / peak, "frac_of_burst": fa_ / (peaks["tensor_burst"] or peak),

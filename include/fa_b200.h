@@ -202,7 +202,8 @@ int64_t fa_launch_count(int reset);
 void fa_kernel_timing(int enable);
 int fa_kernel_timings(int max_entries, const char** names, float* ms);
 /* Force a kernel family (testing): 0 auto, 1 generic only, 4 fp16 backward as the two-kernel
- * (dQ, then dK/dV) variant instead of the fused kernel.                                   */
+ * (dQ, then dK/dV) variant instead of the fused kernel, 5 fp16 head_dim-64 forward with 128-key
+ * tiles and one CTA per SM instead of 64-key tiles and two CTAs per SM.                    */
 void fa_set_path_override(int path);
 const char* fa_version(void);
 

@@ -158,6 +158,7 @@ int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* 
   if (workspace_bytes < fa_workspace_bytes(p, 0)) return FA_EINVAL_WORKSPACE;
   a.q = q; a.k = k; a.v = v; a.o = o; a.l = l; a.m = m;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  a.variant = fa::g_path_override;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_forward_supports(a)) {

@@ -25,7 +25,6 @@ namespace sm100 {
 using namespace ptx;
 
 constexpr int kBlockM = 128;     // query rows per tile == TMEM lanes
-constexpr int kBlockN = 128;     // keys per tile
 constexpr int kQTiles = 2;       // Q tiles per CTA (ping-pong)
 constexpr int kStages = 4;       // K/V ring depth (each stage holds one K or one V tile)
 constexpr int kThreads = 384;    // 8 softmax warps + producer + mma + alloc + spare
@@ -54,20 +53,28 @@ __device__ long long* g_dbg = nullptr;
 #define FA_STAMP(role, j, ev)
 #endif
 
-template <int D, int VD>
+// BN = keys per streamed tile. 128 is the compute-bound configuration (one CTA per SM, 512 TMEM columns).
+// BN = 64 with head_dim 64 needs 256 TMEM columns and ~66 KB of shared memory, so two CTAs share an SM
+// (MINB = 2): short sequences and narrow windows are latency chains per CTA (prologue, 2-3 tiles, epilogue)
+// and HBM-bound overall, and only a second resident CTA hides those chains.
+template <int D, int VD, int BN>
 struct FwdCfg {
   static constexpr int kCh = D > VD ? D : VD;
   static constexpr int kQTileBytes = kBlockM * kCh * 2;   // doubles as the O staging tile
-  static constexpr int kStageBytes = kBlockN * kCh * 2;
+  static constexpr int kStageBytes = BN * kCh * 2;
+  static constexpr int kColO = kQTiles * BN;               // TMEM: S_i at i*BN (P aliased), O_i at kColO + i*VD
+  static constexpr int kColsUsed = kColO + kQTiles * VD;
+  static constexpr int kTmemCols = kColsUsed <= 256 ? 256 : 512;
   static constexpr int kBarOffset = kQTiles * kQTileBytes + kStages * kStageBytes;
   static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
   static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;  // + alignment slack
 };
 
-template <int D, int VD>
-__global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant__ FwdParams p) {
-  using Cfg = FwdCfg<D, VD>;
+template <int D, int VD, int BN, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_constant__ FwdParams p) {
+  using Cfg = FwdCfg<D, VD, BN>;
+  constexpr int kBlockN = BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
       fence_barrier_init();
     }
   } else if (warp == 10) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -133,7 +140,10 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp >= 8) {
-    setmaxnreg_dec<56>();
+    if constexpr (MINB == 1)
+      setmaxnreg_dec<56>();
+    else
+      setmaxnreg_dec<32>();
     if (warp == 8) {
       // ===================== TMA producer =====================
       if (elect_one()) {
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
             const int s = t % kStages, u = t / kStages;
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * D * 2);
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < kBlockN / 64; ++h)
               tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
                           kt * kBlockN + h * 64, b * D);
             ++t;
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
             const int s = t % kStages, u = t / kStages;
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * VD * 2);
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < kBlockN / 64; ++h)
               tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
                           kt * kBlockN + h * 64, b * VD);
             ++t;
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
           for (int ks = 0; ks < kBlockN / 16; ++ks) {
             // K-major SW128: 16 keys = 32 bytes inside the 128-byte row; second box after 64 keys
             const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
-            mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
+            mma_ts(tmem_base + Cfg::kColO + i * VD, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
                    (accumulate || ks > 0) ? 1u : 0u);
           }
         };
@@ -235,12 +245,15 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
     }
   } else {
     // ===================== softmax warpgroups =====================
-    setmaxnreg_inc<224>();
+    if constexpr (MINB == 1)
+      setmaxnreg_inc<224>();
+    else
+      setmaxnreg_inc<104>();
     const int i = warp >> 2;                    // which Q tile
     const int r = threadIdx.x & 127;            // row inside the tile
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + i * kBlockN;
-    const uint32_t t_o = tmem_base + lane_addr + 256 + i * 128;
+    const uint32_t t_o = tmem_base + lane_addr + Cfg::kColO + i * VD;
     const int tq0 = q0 + i * kBlockM;
     const int tq_hi = min(tq0 + kBlockM, p.nq) - 1;
     const bool tile_valid = tq0 < p.nq;
@@ -269,32 +282,32 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
       // destination registers (e.g. the out-of-line mask builder) may sit between tcgen05.ld and
       // tcgen05.wait::ld.
       const bool masked = cls != FA_TILE_FULL || ragged;
-      uint32_t okm[4] = {0u, 0u, 0u, 0u};
+      uint32_t okm[kBlockN / 32] = {};
       if (masked && cls != FA_TILE_SKIP) {
         const int nvalid = k_hi - k0 + 1;
         if (rule.dims == 1 && rule.rule != 2) {
           int lo, hi;
           interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
+          for (int c = 0; c < kBlockN / 32; ++c) okm[c] = interval_bits32(lo, hi, 32 * c);
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) okm[c] = tile_mask32(rule, true, qpos, k0, 32 * c, nvalid);
+          for (int c = 0; c < kBlockN / 32; ++c) okm[c] = tile_mask32(rule, true, qpos, k0, 32 * c, nvalid);
         }
       }
       // S row -> registers (one row per thread)
-      float s[128];
+      float s[kBlockN];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
+      for (int c = 0; c < kBlockN / 32; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
       tmem_wait_ld();
       if (masked) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
+        for (int c = 0; c < kBlockN; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
       }
       if (r == 0) FA_STAMP(i, j, 1);
       float mx = s[0];
 #pragma unroll
-      for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
+      for (int c = 1; c < kBlockN; ++c) mx = fmaxf(mx, s[c]);
       const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
       // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_kernel(const __grid_constant_
   __syncthreads();
   if (warp == 10) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -420,9 +433,9 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
-template <int D, int VD>
+template <int D, int VD, int BN, int MINB>
 cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
-  using Cfg = FwdCfg<D, VD>;
+  using Cfg = FwdCfg<D, VD, BN>;
   FwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
   if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
@@ -438,10 +451,10 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
   p.batch = int32_t(a.batch);
   p.scale_log2 = kLog2e / sqrtf(float(D));
-  auto kern = fwd_kernel<D, VD>;
+  auto kern = fwd_kernel<D, VD, BN, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  ScopedKernel timed("fwd_f16_sm100", stream);
+  ScopedKernel timed(BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64", stream);
   kern<<<unsigned(int64_t(p.n_qpairs) * p.batch), kThreads, Cfg::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
@@ -470,11 +483,17 @@ size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
   return backward ? sm100_f16_bwd_workspace_bytes(a) : 0;
 }
 
+// head_dim 64: the 64-key / two-CTAs-per-SM configuration is faster on every workload measured (S1 1.01 -> 0.67 ms,
+// S2 3.95 -> 2.01 ms, C3 0.84 -> 0.51 ms, C4 0.86 -> 0.73 ms; profiles/r1_short_sequences.md); override 5 keeps the
+// 128-key / one-CTA configuration reachable for A/B runs.
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 128 && a.v_d == 128) return sm100::launch_fwd<128, 128>(a, stream);
-  if (a.d == 64 && a.v_d == 64) return sm100::launch_fwd<64, 64>(a, stream);
-  if (a.d == 128 && a.v_d == 64) return sm100::launch_fwd<128, 64>(a, stream);
-  return sm100::launch_fwd<64, 128>(a, stream);
+  if (a.d == 128 && a.v_d == 128) return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
+  if (a.d == 64 && a.v_d == 64) {
+    if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
+    return sm100::launch_fwd<64, 64, 128, 1>(a, stream);
+  }
+  if (a.d == 128 && a.v_d == 64) return sm100::launch_fwd<128, 64, 128, 1>(a, stream);
+  return sm100::launch_fwd<64, 128, 128, 1>(a, stream);
 }
 
 }  // namespace fa
