@@ -644,6 +644,295 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
   }
 }
 
+// =================================================================================================
+// dK / dV kernel, small configuration (head_dim 64): one S^T / dP^T slot, both softmax warpgroups split
+// the 64 query columns of every sub-tile, 256 TMEM columns and ~100 KB of shared memory -> two CTAs per SM
+// =================================================================================================
+template <int D, int VD>
+struct DkvSmallCfg {
+  static constexpr int kStages = 4;
+  static constexpr int kKBytes = kBM * D * 2;     // resident K tile, also dK staging
+  static constexpr int kVBytes = kBM * VD * 2;    // resident V tile, also dV staging
+  static constexpr int kQBytes = kBN * D * 2;     // streamed Q sub-tile
+  static constexpr int kDoBytes = kBN * VD * 2;
+  static constexpr int kStatBytes = 2 * kBN * 4;  // LSE2[64] + D[64]
+  static constexpr int kStageBytes = kQBytes + kDoBytes;
+  static constexpr int kRingOffset = kKBytes + kVBytes;
+  static constexpr int kStatOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kBarOffset = kStatOffset + kStages * kStatBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 2 + 2 + 1;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __grid_constant__ BwdParams p) {
+  using Cfg = DkvSmallCfg<D, VD>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t k_smem = smem_base;
+  const uint32_t v_smem = smem_base + Cfg::kKBytes;
+  const uint32_t ring = smem_base + Cfg::kRingOffset;
+  const uint32_t stat_smem = smem_base + Cfg::kStatOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_kv_res = bars;                          // resident K/V landed
+  const uint32_t bar_full = bars + 8;                        // [kStages]
+  const uint32_t bar_empty = bar_full + 8 * kStages;         // [kStages]
+  const uint32_t bar_s_full = bar_empty + 8 * kStages;       // [2] (only [0] used)
+  const uint32_t bar_p_ready = bar_s_full + 16;              // [2]
+  const uint32_t bar_final = bar_p_ready + 16;               // [1]
+  const uint32_t tmem_slot = bar_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+  const float* stat_gen = reinterpret_cast<const float*>(smem_gen + Cfg::kStatOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_blocks);     // head-major: Q/dO stay in L2
+  const int kblk = int(blockIdx.x % p.n_blocks);  // early key tiles are the heavy ones under causal
+  const int k0 = kblk * kBM;
+  const int k_hi = min(k0 + kBM, p.nk) - 1;
+  int qt_first, qt_last;
+  fa_q_tile_range(rule, k0, k_hi, kBN, &qt_first, &qt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {k0};
+    const int hi[1] = {k_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, false, lo, hi, valid, 1, qt_first, qt_last, kBN, p.nq, kBwdThreads / 32);
+  }
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_do);
+      prefetch_tensormap(&p.map_dk);
+      prefetch_tensormap(&p.map_dv);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      mbar_init(bar_kv_res, 1);
+      mbar_init(bar_final, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, 2 * kBM);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns (256 allocated, so that two CTAs share an SM): S^T [0, 64)  dP^T [64, 128)  dV [128, +VD)
+  // dK [192, +D); one slot only: the second resident CTA provides the overlap that ping-pong slots give
+  // the big configuration.
+
+  if (warp >= 8) {
+    setmaxnreg_dec<32>();
+    if (warp == 8) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
+          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+        }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        int qt, tw, tb;
+        while (it.next(&qt, &tw, &tb)) {
+          const int s = t % kStages, u = t / kStages;
+          mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
+          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
+          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
+          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
+          bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
+          ++t;
+        }
+      }
+    } else if (warp == 9) {
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
+        auto issue_st_dpt = [&](int stage) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
+                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < VD / 16; ++ks)
+            mma_ss(tmem_base + 64, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
+                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+        };
+        auto issue_dv_dk = [&](int stage, bool accumulate) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
+          // P^T / dS^T: warpgroup h wrote its 32 query columns as 16 packed columns at [32h, 32h+16)
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
+                   smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
+                   smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_res, 0);
+          mbar_wait(bar_full + 0, 0);
+          tc_fence_after();
+          issue_st_dpt(0);
+          mma_commit(bar_s_full);
+          for (int t = 0; t < n; ++t) {
+            const int st = t % kStages;
+            mbar_wait(bar_p_ready, t & 1);
+            tc_fence_after();
+            issue_dv_dk(st, t > 0);
+            mma_commit(bar_empty + 8 * st);
+            if (t + 1 < n) {
+              const int t2 = t + 1, s2 = t2 % kStages;
+              mbar_wait(bar_full + 8 * s2, (t2 / kStages) & 1);
+              tc_fence_after();
+              issue_st_dpt(s2);
+              mma_commit(bar_s_full);
+            }
+          }
+          mma_commit(bar_final);
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<104>();
+    const int x = warp >> 2;                 // column half in the main loop, dV / dK role in the epilogue
+    const int r = threadIdx.x & 127;         // key row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + x * 32;   // own 32 columns of S^T; dP^T at +64
+    const int ki = k0 + r;
+    const bool k_valid = ki < p.nk;
+    const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
+    const float scale_log2 = p.scale_log2;
+    int t = 0;
+    TileIter it;
+    it.init(sched, 1, qt_first, qt_last);
+    int qt, tw, tb;
+    while (it.next(&qt, &tw, &tb)) {
+      const int st = t % kStages;
+      const int q0 = qt * kBN;
+      const int q_hi = min(q0 + kBN, p.nq) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool ragged = (q0 + kBN > p.nq) || (k0 + kBM > p.nk);
+      mbar_wait(bar_full + 8 * st, (t / kStages) & 1);   // stats visible to this thread
+      mbar_wait(bar_s_full, t & 1);
+      tc_fence_after();
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
+      uint32_t okmask = 0xffffffffu;
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        okmask = 0u;
+        if (k_valid) {
+          const int nvalid = q_hi - q0 + 1;
+          if (rule.dims == 1 && rule.rule != 2) {
+            int lo, hi;
+            interval_1d(rule, false, kpos, q0, nvalid, &lo, &hi);
+            okmask = interval_bits32(lo, hi, x * 32);
+          } else {
+            okmask = tile_mask32(rule, false, kpos, q0, x * 32, nvalid);
+          }
+        }
+      }
+      float s[32], dp[32];
+      tmem_ld32f(t_s, s);
+      tmem_ld32f(t_s + 64, dp);
+      tmem_wait_ld();
+      const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN) + x * 32);
+      const float4* dsum4 = lse4 + kBN / 4;
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const uint32_t mword = okmask >> c;
+        const float4 ls = lse4[c >> 2];
+        const float4 dd = dsum4[c >> 2];
+        float p0 = ex2(fmaf(s[c], scale_log2, -ls.x));
+        float p1 = ex2(fmaf(s[c + 1], scale_log2, -ls.y));
+        float p2 = ex2(fmaf(s[c + 2], scale_log2, -ls.z));
+        float p3 = ex2(fmaf(s[c + 3], scale_log2, -ls.w));
+        p0 = mword & 1u ? p0 : 0.f;
+        p1 = mword & 2u ? p1 : 0.f;
+        p2 = mword & 4u ? p2 : 0.f;
+        p3 = mword & 8u ? p3 : 0.f;
+        pk[c >> 1] = pack_half2(p0, p1);
+        pk[(c >> 1) + 1] = pack_half2(p2, p3);
+        dk[c >> 1] = pack_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y));
+        dk[(c >> 1) + 1] = pack_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w));
+      }
+      tmem_st16(t_s, pk);          // P^T  over the first 16 columns of this half of S^T
+      tmem_st16(t_s + 64, dk);     // dS^T over the first 16 columns of this half of dP^T
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+      ++t;
+    }
+    // how many live sub-tiles exist in total (t counted them all)
+    // epilogue: warpgroup 0 stores dV, warpgroup 1 stores dK
+    const int CH = x == 0 ? VD : D;
+    const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 128 : 192);
+    const float out_scale = x == 0 ? 1.f : p.scale;
+    uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
+    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
+    if (t > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+      for (int c = 0; c < CH / 32; ++c) {
+        float o[32];
+        tmem_ld32f(t_acc + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+      }
+    } else {
+      mbar_wait(bar_kv_res, 0);
+      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1 + x, kBM);
+    if (r == 0) {
+      for (int h = 0; h < 2; ++h)
+        if (k0 + h * 64 < p.nk) {
+          if (x == 0)
+            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+          else
+            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+        }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
 // LSE2 + D arrays (padded), rounded up so that the fp32 dQ scratch behind them is 256-byte aligned
 static size_t stats_bytes(int64_t batch, int64_t nq) {
   return (size_t(2) * (batch * nq + kStatPad) * sizeof(float) + 255) & ~size_t(255);
@@ -1205,6 +1494,18 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DqCfg<D, VD>::kSmemBytes, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+  }
+  if constexpr (D == 64 && VD == 64) {
+    if (a.variant != 4) {
+      auto kern = bwd_dkdv_small_kernel<D, VD>;
+      cudaError_t e =
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmallCfg<D, VD>::kSmemBytes);
+      if (e != cudaSuccess) return e;
+      p.n_blocks = (nk + kBM - 1) / kBM;
+      ScopedKernel timed("bwd_dkdv_f16_sm100_2cta", stream);
+      kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DkvSmallCfg<D, VD>::kSmemBytes, stream>>>(p);
+      return cudaGetLastError();
+    }
   }
   {
     auto kern = bwd_dkdv_kernel<D, VD>;
