@@ -174,6 +174,22 @@ def test_fused_backward_agrees_with_split_variant():
     assert float(((dq_a - dq_b).abs() / dq_b.abs().clamp(min=1)).max()) <= 1e-3
 
 
+D64_CASES = [c for c in CASES if c[7] == 64 and c[8] == 64][:6]
+
+
+@pytest.mark.parametrize("override", [4, 5])
+@pytest.mark.parametrize("case", D64_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-w{c[3]}s{c[4]}c{c[5]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_head_dim64_one_cta_per_sm_variants_match_oracle(case, override):
+    """head_dim 64 normally runs the 256-TMEM-column configurations (two CTAs per SM: 64-key forward tiles, one-slot dQ
+    and dK/dV kernels). Override 5 selects the 128-key forward, override 4 the two-slot backward kernels; both stay
+    in the library for A/B runs and must meet the same bar."""
+    _capi.lib.fa_set_path_override(override)
+    try:
+        _run(*case, seed=zlib.crc32(repr(case).encode()) % 1000)
+    finally:
+        _capi.lib.fa_set_path_override(0)
+
+
 F32_CASES = [
     (1, "full", "none_front", 1, 0, 0, (2,), 64, 64, (256,), (320,)),
     (1, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (512,), (512,)),

@@ -351,6 +351,258 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
 }
 
 // =================================================================================================
+// dQ kernel, small configuration (head_dim 64): one 128-row Q tile per CTA, one S / dP slot, both softmax
+// warpgroups split the 64 key columns, 256 TMEM columns and ~82 KB of shared memory -> two CTAs per SM
+// =================================================================================================
+template <int D, int VD>
+struct DqSmallCfg {
+  static constexpr int kStages = 3;
+  static constexpr int kQBytes = kBM * D * 2;       // also the dQ staging tile
+  static constexpr int kDoBytes = kBM * VD * 2;
+  static constexpr int kKBytes = kBN * D * 2;
+  static constexpr int kVBytes = kBN * VD * 2;
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kRingOffset = kQBytes + kDoBytes;
+  static constexpr int kBarOffset = kRingOffset + kStages * kStageBytes;
+  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
+};
+
+template <int D, int VD>
+__global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __grid_constant__ BwdParams p) {
+  using Cfg = DqSmallCfg<D, VD>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base;
+  const uint32_t do_smem = smem_base + Cfg::kQBytes;
+  const uint32_t ring = smem_base + Cfg::kRingOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_q_full = bars;
+  const uint32_t bar_kv_full = bars + 16;
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * kStages;
+  const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;
+  const uint32_t bar_p_ready = bar_s_full + 16;
+  const uint32_t bar_final = bar_p_ready + 16;
+  const uint32_t tmem_slot = bar_final + 16;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_blocks);                     // head-major: K/V stay in L2
+  const int pair = p.n_blocks - 1 - int(blockIdx.x % p.n_blocks);  // heavy (late) rows first
+  const int q0 = pair * kBM;
+  const int q_hi = min(q0 + kBM, p.nq) - 1;
+  int kt_first, kt_last;
+  fa_k_tile_range(rule, q0, q_hi, kBN, &kt_first, &kt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {q0};
+    const int hi[1] = {q_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, true, lo, hi, valid, 1, kt_first, kt_last, kBN, p.nk, kBwdThreads / 32);
+  }
+
+  if (warp == 8) {
+    if (elect_one()) {
+      prefetch_tensormap(&p.map_q);
+      prefetch_tensormap(&p.map_k);
+      prefetch_tensormap(&p.map_v);
+      prefetch_tensormap(&p.map_do);
+      prefetch_tensormap(&p.map_dq);
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_q_full + 8 * i, 1);
+        mbar_init(bar_s_full + 8 * i, 1);
+        mbar_init(bar_p_ready + 8 * i, 2 * kBM);
+        mbar_init(bar_final + 8 * i, 1);
+      }
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(bar_kv_full + 8 * s, 1);
+        mbar_init(bar_kv_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 10) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns (256 allocated -> two CTAs per SM): S [0, 64)  dP [64, 128)  dQ [128, +D); one 128-row Q tile,
+  // both softmax warpgroups split the 64 key columns of every tile
+
+  if (warp >= 8) {
+    setmaxnreg_dec<32>();
+    if (warp == 8) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q_full, Cfg::kQBytes + Cfg::kDoBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_2d(q_smem + h * (D * 128), &p.map_q, bar_q_full, q0 + h * 64, b * D);
+          tma_load_2d(do_smem + h * (VD * 128), &p.map_do, bar_q_full, q0 + h * 64, b * VD);
+        }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        int kt, tw, tb;
+        while (it.next(&kt, &tw, &tb)) {
+          const int s = t % kStages, u = t / kStages;
+          mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
+          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b * D);
+          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b * VD);
+          ++t;
+        }
+      }
+    } else if (warp == 9) {
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, true, true);
+        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, false);
+        auto issue_s_dp = [&](int stage) {
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + Cfg::kKBytes;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks)
+            mma_ss(tmem_base, smem_desc_sw128(q_smem + ks * 2048, D * 128, 1024),
+                   smem_desc_sw128(k_s + ks * 2048, D * 128, 1024), idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < VD / 16; ++ks)
+            mma_ss(tmem_base + 64, smem_desc_sw128(do_smem + ks * 2048, VD * 128, 1024),
+                   smem_desc_sw128(v_s + ks * 2048, VD * 128, 1024), idesc_s, ks > 0);
+        };
+        auto issue_dq = [&](int stage, bool accumulate) {
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes;
+          // dS: warpgroup h wrote its 32 key columns as 16 packed columns at [32h, 32h+16)
+#pragma unroll
+          for (int ks = 0; ks < kBN / 16; ++ks)
+            mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
+                   smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_full + 0, 0);
+          mbar_wait(bar_q_full, 0);
+          tc_fence_after();
+          issue_s_dp(0);
+          mma_commit(bar_s_full);
+          for (int j = 0; j < n; ++j) {
+            const int sj = j % kStages, sn = (j + 1) % kStages;
+            mbar_wait(bar_p_ready, j & 1);
+            tc_fence_after();
+            issue_dq(sj, j > 0);
+            mma_commit(bar_kv_empty + 8 * sj);
+            if (j + 1 < n) {
+              mbar_wait(bar_kv_full + 8 * sn, ((j + 1) / kStages) & 1);
+              tc_fence_after();
+              issue_s_dp(sn);
+              mma_commit(bar_s_full);
+            } else {
+              mma_commit(bar_final);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<104>();
+    const int x = warp >> 2;                 // key-column half in the main loop, channel half in the epilogue
+    const int r = threadIdx.x & 127;         // query row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + x * 32;   // own 32 columns of S; dP at +64
+    const uint32_t t_dq = tmem_base + lane_addr + 128;
+    const int qi = q0 + r;
+    const bool q_valid = qi < p.nq;
+    const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float scale_log2 = p.scale_log2;
+    int j = 0;
+    TileIter it;
+    it.init(sched, 1, kt_first, kt_last);
+    int kt, tw, tb;
+    while (it.next(&kt, &tw, &tb)) {
+      const int k0 = kt * kBN;
+      const int k_hi = min(k0 + kBN, p.nk) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool ragged = k0 + kBN > p.nk;
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
+      uint32_t okmask = 0xffffffffu;
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        const int nvalid = k_hi - k0 + 1;
+        if (rule.dims == 1 && rule.rule != 2) {
+          int lo, hi;
+          interval_1d(rule, true, qpos, k0, nvalid, &lo, &hi);
+          okmask = interval_bits32(lo, hi, x * 32);
+        } else {
+          okmask = tile_mask32(rule, true, qpos, k0, x * 32, nvalid);
+        }
+      }
+      float s[32], dp[32];
+      tmem_ld32f(t_s, s);
+      tmem_ld32f(t_s + 64, dp);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float p0 = ex2(fmaf(s[c], scale_log2, -lse2));
+        float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
+        p0 = (okmask >> c) & 1u ? p0 : 0.f;
+        p1 = (okmask >> (c + 1)) & 1u ? p1 : 0.f;
+        pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
+      }
+      tmem_st16(t_s, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+      ++j;
+    }
+    // epilogue: dQ = scale * acc -> fp16 -> smem [D][64] x2 -> TMA store; warpgroup x handles channels [32x, 32x+32)
+    __half* stage_h = reinterpret_cast<__half*>(smem_gen) + (r >> 6) * (D * 64) + (r & 63);
+    if (j > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+      for (int c = x; c < D / 32; c += 2) {
+        float o[32];
+        tmem_ld32f(t_dq + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
+      }
+    } else {
+      mbar_wait(bar_q_full, 0);
+      for (int c = x * 32; c < D; c += 64)
+#pragma unroll 8
+        for (int e = 0; e < 32; ++e) stage_h[(c + e) * 64] = __float2half_rn(0.f);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 2 * kBM);
+    if (threadIdx.x == 0) {
+      for (int h = 0; h < 2; ++h)
+        if (q0 + h * 64 < p.nq) tma_store_2d(&p.map_dq, q_smem + h * (D * 128), q0 + h * 64, b * D);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+// =================================================================================================
 // dK / dV kernel
 // =================================================================================================
 template <int D, int VD>
@@ -1485,7 +1737,22 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       }
     }
   }
-  {
+  bool dq_done = false;
+  if constexpr (D == 64 && VD == 64) {
+    if (a.variant != 4) {
+      auto kern = bwd_dq_small_kernel<D, VD>;
+      cudaError_t e =
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmallCfg<D, VD>::kSmemBytes);
+      if (e != cudaSuccess) return e;
+      p.n_blocks = (nq + kBM - 1) / kBM;
+      ScopedKernel timed("bwd_dq_f16_sm100_2cta", stream);
+      kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DqSmallCfg<D, VD>::kSmemBytes, stream>>>(p);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      dq_done = true;
+    }
+  }
+  if (!dq_done) {
     auto kern = bwd_dq_kernel<D, VD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
