@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--no-refkernel", action="store_true")
     ap.add_argument("--fwd-only", action="store_true")
     ap.add_argument("--override", type=int, default=0, help="fa_set_path_override value (developer A/B)")
+    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (launch-bound workloads)")
     ap.add_argument("--ring-bwd", action="store_true", help="C5: time forward + ring backward")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -325,6 +326,23 @@ def main():
 
     if args.override:
         _capi.lib.fa_set_path_override(args.override)
+    if args.graph:
+        # capture one step (all launches are stream-ordered) and replay it; per-kernel event timing is not
+        # available inside a graph, so the kernel table of this run comes from one eager step
+        eager_step = step
+        eager_step()
+        torch.cuda.synchronize()
+        cuda_graph = torch.cuda.CUDAGraph()
+        _capi.lib.fa_launch_count(1)
+        with torch.cuda.graph(cuda_graph):
+            sp_saved = sp
+            sp = torch.cuda.current_stream(dev).cuda_stream
+            eager_step()
+            sp = sp_saved
+        graph_launches = int(_capi.lib.fa_launch_count(0))   # kernels captured per step
+
+        def step():  # noqa: F811
+            cuda_graph.replay()
     sampler = ClockSampler(local_rank)
     sampler.launch()
     for _ in range(max(3, args.warmup)):
@@ -356,9 +374,18 @@ def main():
         dist.barrier()
     _capi.lib.fa_kernel_timing(0)
     launches = int(_capi.lib.fa_launch_count(0))
+    if args.graph:
+        launches = graph_launches * args.steps   # replayed from the captured graph, not re-issued by the library
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     kt = _capi.kernel_timings()
+    if args.graph:
+        # per-kernel durations of one eager step outside the timed region (events cannot be recorded into the replay)
+        _capi.lib.fa_kernel_timing(1)
+        eager_step()
+        torch.cuda.synchronize()
+        _capi.lib.fa_kernel_timing(0)
+        kt = _capi.kernel_timings()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -370,7 +397,7 @@ def main():
     per = {}
     for name, ms in kt:
         per.setdefault(name, []).append(ms)
-    kernels = {n: {"launches": len(v), "avg_ms": float(np.mean(v)), "share": float(np.sum(v)) / ms_total}
+    kernels = {n: {"launches": len(v), "avg_ms": float(np.mean(v)), "share": float(np.sum(v)) * (args.steps if args.graph else 1) / ms_total}
                for n, v in per.items()}
     peaks = measured_peaks()
     roofline = None
@@ -424,7 +451,8 @@ def main():
             "value": value, "unit": "TFLOPS", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 (fp32 accumulate)" if w["dtype"] == "float16" else w["dtype"], "data": "synthetic U(-2,2), seed 1234",
-            "config": config, "sequences_per_s": float(np.prod(w["batch"])) * world / (ms_per_step * 1e-3),
+            "config": dict(config, launch="CUDA graph replay" if args.graph else "eager launches"),
+            "sequences_per_s": float(np.prod(w["batch"])) * world / (ms_per_step * 1e-3),
             "paths": {"fwd": fwd_path, "bwd": bwd_path}, "kernels": kernels, "roofline": roofline,
             "clocks": clocks, "gpu_launches": launches, "pct_of_nominal_fp16_peak": 100.0 * value / world / 2250.0}
 
