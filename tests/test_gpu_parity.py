@@ -257,3 +257,55 @@ def test_forward_and_backward_are_cuda_graph_capturable():
                 assert float((got.float() - ref.float()).abs().max()) <= 2e-3 * max(1.0, float(ref.float().abs().max()))
             else:
                 assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("dtype,d,vd,nq,nk,rule", [
+    (np.float16, 128, 128, 520, 328, "causal"),   # fused backward, ragged tiles on both sides
+    (np.float16, 64, 64, 200, 328, "full"),       # two-CTAs-per-SM kernels, ragged
+    (np.float16, 128, 64, 136, 1000, "causal"),
+    (np.float32, 64, 64, 260, 132, "full"),       # 3xTF32 forward, generic backward
+    (np.float32, 40, 24, 100, 70, "causal"),      # generic kernels
+    (np.float64, 16, 16, 96, 50, "full"),
+])
+def test_kernels_write_only_inside_their_outputs(dtype, d, vd, nq, nk, rule):
+    """Guard bands: every output (O, l, m, dQ, dK, dV) and the workspace sit inside larger buffers pre-filled with a
+    byte pattern; after forward + backward the bands must be untouched (compute-sanitizer is not available on
+    the GPU pool, so this is the out-of-bounds check for ragged tiles, TMA stores and the reduce-add scratch)."""
+    import ctypes as C
+    B, PAD = 3, 512   # bytes; keeps the 16-byte alignment the TMA paths need
+    rng = np.random.default_rng(21)
+    Q, K, V, dO = da.random_inputs(rng, dtype, (B,), d, vd, (nq,), (nk,))
+    tq, tk, tv, tdo = (torch.from_numpy(x).cuda() for x in (Q, K, V, dO))
+    code = {np.float16: _capi.FA_F16, np.float32: _capi.FA_F32, np.float64: _capi.FA_F64}[dtype]
+    prob = _capi.make_problem(code, 1, rule, "scale_end", tq.shape, tk.shape, tv.shape)
+    tdt = tq.dtype
+    ldt = torch.float32 if dtype == np.float16 else tdt
+
+    def guarded(shape, dt):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        raw = torch.full((n + 2 * PAD,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[PAD:PAD + n].view(dt).view(shape)
+    bufs = {name: guarded(shape, dt) for name, shape, dt in (
+        ("O", (B, vd, nq), tdt), ("l", (B, nq), ldt), ("m", (B, nq), tdt),
+        ("dQ", (B, d, nq), tdt), ("dK", (B, d, nk), tdt), ("dV", (B, vd, nk), tdt))}
+    nws = max(_capi.lib.fa_workspace_bytes(C.byref(prob), 0), _capi.lib.fa_workspace_bytes(C.byref(prob), 1), 16)
+    nws = (nws + 255) // 256 * 256
+    ws_raw = torch.full((nws + 2 * PAD,), 0xA5, dtype=torch.uint8, device="cuda")
+    ws = ws_raw[PAD:PAD + nws]
+    st = torch.cuda.current_stream().cuda_stream
+    g = {k: v[1] for k, v in bufs.items()}
+    _capi.check(_capi.lib.fa_forward(C.byref(prob), tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), g["O"].data_ptr(),
+                                     g["l"].data_ptr(), g["m"].data_ptr(), ws.data_ptr(), nws, st), "fa_forward")
+    _capi.check(_capi.lib.fa_backward(C.byref(prob), tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), g["O"].data_ptr(),
+                                      g["l"].data_ptr(), g["m"].data_ptr(), tdo.data_ptr(), g["dQ"].data_ptr(),
+                                      g["dK"].data_ptr(), g["dV"].data_ptr(), ws.data_ptr(), nws, st), "fa_backward")
+    torch.cuda.synchronize()
+    for name, (raw, view) in list(bufs.items()) + [("workspace", (ws_raw, ws))]:
+        assert bool((raw[:PAD] == 0xA5).all()) and bool((raw[-PAD:] == 0xA5).all()), f"{name}: guard band overwritten"
+    # and the results are the right ones
+    ref = da.attention(Q, K, V, 1, rule, "scale_end", dO=dO)
+    tol = {np.float16: 2e-3, np.float32: 1e-5, np.float64: 1e-12}[dtype]
+    assert max_abs_err(g["O"].cpu().numpy(), ref["O"]) <= tol
+    for name in ("dQ", "dK", "dV"):
+        gtol = tol * (4 if dtype == np.float16 else 10)
+        assert scaled_err(g[name].cpu().numpy(), ref[name]) <= gtol, name
