@@ -1,0 +1,2 @@
+// test stub: see tests/tf_stub/tf_stub.h
+#include "../../../tf_stub.h"
