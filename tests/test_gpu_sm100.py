@@ -139,6 +139,39 @@ def test_full_size_properties_c2():
     assert torch.equal(Oq, Oa[perm])
 
 
+def test_full_size_backward_properties_c2():
+    """Size-independent properties of the backward pass at the full C2 sequence length (8 heads):
+    (1) linearity in dO: grad(dO1 + dO2) = grad(dO1) + grad(dO2) (the same P is recomputed in every call);
+    (2) batch elements are independent: permuting heads permutes dK / dV bit-exactly (dQ up to the fp32 reduction order);
+    (3) sum_k dK relation: with dO = 0 every gradient is exactly zero."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, d, S = 8, 128, 8192
+
+    def u(*shape, scale=2.0):
+        return ((torch.rand(shape, generator=g, device="cuda") * 2 - 1) * scale).half()
+    Q, K, V = (u(B, d, S).requires_grad_(True) for _ in range(3))
+    dO1, dO2 = u(B, d, S, scale=1.0), u(B, d, S, scale=1.0)
+    O = fa.causal_1d(Q, K, V, "none_front")
+
+    def grads(dO):
+        out = torch.autograd.grad(O, (Q, K, V), dO, retain_graph=True)
+        assert _capi.lib.fa_last_path() == 2
+        return [x.float() for x in out]
+    g1, g2, g12 = grads(dO1), grads(dO2), grads((dO1.float() + dO2.float()).half())
+    for a, b, c, name in zip(g1, g2, g12, ("dQ", "dK", "dV")):
+        err = (c - (a + b)).abs() / (a + b).abs().clamp(min=1.0)
+        assert float(err.max()) <= 8e-3, f"{name}: {float(err.max())}"       # three fp16 roundings of sums of 8192 terms
+        assert float((err <= 2e-3).float().mean()) >= 0.995, name
+    perm = torch.randperm(B, device="cuda")
+    Qp, Kp, Vp = (x.detach()[perm].contiguous().requires_grad_(True) for x in (Q, K, V))
+    Op = fa.causal_1d(Qp, Kp, Vp, "none_front")
+    gp = torch.autograd.grad(Op, (Qp, Kp, Vp), dO1[perm].contiguous())
+    assert torch.equal(gp[1].float(), g1[1][perm]) and torch.equal(gp[2].float(), g1[2][perm])
+    assert float((gp[0].float() - g1[0][perm]).abs().max()) <= 2e-3 * max(1.0, float(g1[0].abs().max()))
+    gz = grads(torch.zeros_like(dO1))
+    assert all(float(x.abs().max()) == 0.0 for x in gz)
+
+
 D128_CASES = [c for c in CASES if c[7] == 128]
 
 
