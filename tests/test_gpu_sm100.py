@@ -232,13 +232,17 @@ F32_CASES = [
     (1, "local", "none_front", 2, 0, 0, (2,), 32, 32, (640,), (128,)),          # rows with no keys
     (2, "local", "none_front", 4, 0, 1, (2,), 64, 64, (24, 32), (24, 32)),
     (2, "causal", "scale_end", 1, 0, 0, (1,), 32, 32, (8, 40), (24, 40)),
+    (1, "causal", "none_front", 1, 0, 0, (2, 2), 64, 64, (1024,), (1024,)),    # fp32 backward on the tensor cores
+    (1, "local", "none_front", 5, 1, 1, (2,), 64, 64, (520,), (520,)),          # ragged, strided window
+    (1, "causal", "scale_end", 1, 0, 0, (2,), 64, 64, (1000,), (88,)),          # more queries than keys
+    (2, "causal", "scale_front", 1, 0, 0, (1,), 64, 64, (16, 24), (32, 24)),
 ]
 
 
 @pytest.mark.parametrize("case", F32_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
 def test_fp32_3xtf32_forward_matches_oracle(case):
     """fp32 forward on the tensor cores (tcgen05 kind::tf32, 3xTF32 split): BASELINE.json bar 1e-5 max-abs on O;
-    the (generic fp32) backward then consumes its l, m."""
+    the backward (tensor-core kernels for head_dim 64, FFMA kernels otherwise) then consumes its l, m."""
     dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
     rng = np.random.default_rng(zlib.crc32(repr(case).encode()) % 1000)
     Q, K, V, dO = da.random_inputs(rng, np.float32, batch, d, vd, qs, ks)
@@ -263,5 +267,11 @@ def test_fp32_3xtf32_forward_matches_oracle(case):
     lse = mn.astype(np.float64)[live] + np.log(ln[live])
     assert np.max(np.abs(lse - (ref["m"][live] + np.log(ref["l"][live])))) <= 1e-5
     dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+    nq, nk = int(np.prod(qs)), int(np.prod(ks))
+    if d == 64 and vd == 64 and nq % 8 == 0 and nk % 8 == 0:
+        # head_dim 64: split-precision tcgen05 backward (three bf16 pieces per operand, fa_bwd_f32_sm100.cu)
+        assert _capi.lib.fa_last_path() == 3, "fp32 backward did not take the tensor-core path"
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
-        assert scaled_err(g.cpu().numpy(), ref[name]) <= 1e-5, name
+        err = scaled_err(g.cpu().numpy(), ref[name])
+        print(name, err)
+        assert err <= 1e-5, name

@@ -138,6 +138,12 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
   size_t s = 0;
   a.variant = fa::g_path_override;
   if (p->dtype == FA_F16) s = fa::sm100_f16_workspace_bytes(a, is_backward != 0);
+  if (p->dtype == FA_F32 && is_backward && fa::g_path_override != 1) {
+    fa::LaunchArgs probe = a;
+    probe.workspace = nullptr;
+    probe.workspace_bytes = ~size_t(0);
+    if (fa::sm100_f32_backward_supports(probe)) s = fa::sm100_f32_backward_workspace_bytes(a);
+  }
   if (p->dtype == FA_F32 && !is_backward) {
     // hi / lo TF32 copies of Q, K, V for the 3xTF32 forward (only when that kernel can take the shape)
     fa::LaunchArgs probe = a;
@@ -194,6 +200,9 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   if (fa::g_path_override != 1 && p->dtype == FA_F16 && fa::sm100_f16_backward_supports(a)) {
     fa::g_last_path = 2;
     e = fa::sm100_f16_backward(a, st);
+  } else if (fa::g_path_override != 1 && p->dtype == FA_F32 && fa::sm100_f32_backward_supports(a)) {
+    fa::g_last_path = 3;
+    e = fa::sm100_f32_backward(a, st);
   } else {
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;

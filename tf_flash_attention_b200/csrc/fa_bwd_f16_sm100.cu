@@ -77,6 +77,12 @@ __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restr
                                                              : __int_as_float(0x7f800000);
     }
   }
+  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
+  // (a NaN there would turn the masked 0 * (dP - D) into NaN)
+  if (blockIdx.x == 0 && threadIdx.x < kStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
 }
 
 // =================================================================================================

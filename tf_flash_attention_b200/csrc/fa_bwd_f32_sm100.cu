@@ -1,0 +1,729 @@
+// fa_bwd_f32_sm100.cu — fp32 backward on the tensor cores (head_dim 64): split-precision tcgen05 kernels.
+//
+// The forward runs fp32 as 3xTF32 (fa_fwd_f32_sm100.cu). The backward needs every streamed tile in BOTH operand
+// orientations (K as the MN-major B operand of S = Q K^T and as the K-major B operand of dQ = dS K, Q likewise in the
+// dK/dV kernel). For kind::tf32 that costs two shared-memory copies per tile: MN-major TF32 operands only work in the
+// "128B swizzle, 32-byte atom" layout and a K-major descriptor over such a tile faults (measured), and
+// with hi/lo copies of everything that does not fit. The same split idea with 16-bit pieces does fit:
+//     x = x0 + x1 + x2,  x_i = bf16 pieces (8 + 8 + 8 mantissa bits, fp32 exponent range),
+//     a*b ~= a0b0 + (a0b1 + a1b0) + (a0b2 + a1b1 + a2b0)          (dropped terms <= 2^-24 |ab|)
+// = 6 kind::f16 (bf16) MMAs per product at full rate, which is the cost of 3 half-rate TF32 MMAs, 6 bytes per
+// element instead of 8, and one 128B-swizzled tile per piece that is readable MN-major and K-major exactly like the
+// fp16 kernels' tiles. Accumulation is fp32 in TMEM; softmax statistics, exp2f and dS are fp32 in registers; P and dS
+// are re-split into three bf16 pieces for the second product of each chain.
+//
+//   split_bf16x3_kernel : Q, K, V, dO -> three bf16 tensors each (workspace)
+//   bwd_prep_f32        : LSE2 = (m + log l) log2 e, D = rowsum(dO o O)
+//   bwd_dq_f32_kernel   : CTA = 128 query rows, streams 64-key tiles:  S, dP (SS) -> dS pieces (TMEM) -> dQ += dS K (TS)
+//   bwd_dkdv_f32_kernel : CTA = 128 keys, streams 64-query tiles: S^T, dP^T (SS) -> P^T, dS^T pieces -> dV, dK (TS)
+// Formulas as in the reference (flash_attention.cu:1838-1841, 1544-1546, 1882-1891).
+#include <cuda_bf16.h>
+
+#include "fa_common.cuh"
+#include "fa_launch.h"
+#include "sm100_ptx.cuh"
+#include "sm100_tiles.cuh"
+
+namespace fa {
+namespace sm100 {
+
+using namespace ptx;
+
+bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                 bool swizzle128);  // fa_fwd_f16_sm100.cu (2-byte elements; the copy does not interpret them)
+
+constexpr int kXM = 128;        // resident rows of a CTA (TMEM lanes)
+constexpr int kXN = 64;         // streamed tile width
+constexpr int kXD = 64;         // head dim (d == v_d == 64)
+constexpr int kXThreads = 256;  // 4 softmax warps, TMA warp, MMA warp, TMEM warp, spare
+constexpr int kXStages = 2;
+constexpr int kXStatPad = 64;
+constexpr float kXLog2e = 1.4426950408889634f;
+
+// kind::f16 instruction descriptor with BF16 inputs (a/b format 1) and F32 accumulation
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
+         (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// piece pairs of a 3-piece product, smallest terms first (the tensor core truncates when it adds into fp32)
+__device__ constexpr int kPairA[6] = {0, 1, 2, 0, 1, 0};
+__device__ constexpr int kPairB[6] = {2, 1, 0, 1, 0, 0};
+
+struct alignas(64) BwdF32Params {
+  CUtensorMap map_q[3], map_k[3], map_v[3], map_do[3];   // bf16 pieces, 128B swizzle, box 64 x 64 channels
+  FaRule rule;
+  const float* lse2;    // from the forward's l, m
+  const float* dsum;
+  float* lse2_refined;  // written by the dQ kernel, read by the dK/dV kernel (see bwd_dq_f32_kernel)
+  float *d_q, *d_k, *d_v;
+  int32_t nq, nk, n_blocks, batch;
+  float scale, scale_log2;
+};
+
+// ---- operand split and row statistics --------------------------------------------------------------------
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
+                                    __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a);
+    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b);
+    p0[i] = a;
+    p1[i] = b;
+    p2[i] = __float2bfloat16_rn(r2);
+  }
+}
+
+__global__ void bwd_prep_f32(const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ l,
+                             const float* __restrict__ m, float* __restrict__ lse2, float* __restrict__ dsum,
+                             float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
+  const int64_t total = batch * nq;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = i / nq, r = i - b * nq;
+    const float* op = o + b * v_d * int64_t(nq) + r;
+    const float* dp = d_o + b * v_d * int64_t(nq) + r;
+    float acc = 0.f;
+    for (int c = 0; c < v_d; ++c) acc = fmaf(op[int64_t(c) * nq], dp[int64_t(c) * nq], acc);
+    dsum[i] = acc;
+    const float lv = l[i], mv = m[i];
+    lse2[i] = (lv > 0.f && !is_sentinel<float>(mv)) ? (mv + logf(lv)) * kXLog2e : __int_as_float(0x7f800000);
+  }
+  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile
+  if (blockIdx.x == 0 && threadIdx.x < kXStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    lse2_refined[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
+}
+
+// three bf16 pieces of two fp32 values, packed pairwise: out[j] = {piece_j(x), piece_j(y)}
+__device__ __forceinline__ void split3_pack(float x, float y, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(x, y);
+  const float rx = x - __bfloat162float(a.x), ry = y - __bfloat162float(a.y);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(rx, ry);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(rx - __bfloat162float(b.x), ry - __bfloat162float(b.y));
+  o0 = *reinterpret_cast<const uint32_t*>(&a);
+  o1 = *reinterpret_cast<const uint32_t*>(&b);
+  o2 = *reinterpret_cast<const uint32_t*>(&c);
+}
+
+__device__ __forceinline__ void bulk_load_1d_x(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct XCfg {
+  static constexpr int kResTile = kXM * kXD * 2;            // one bf16 piece of a resident 128-row tile: 16 KB
+  static constexpr int kStrTile = kXN * kXD * 2;            // one piece of a streamed 64-wide tile: 8 KB
+  static constexpr int kResBytes = 6 * kResTile;            // two resident tensors x three pieces
+  static constexpr int kStageBytes = 6 * kStrTile;          // two streamed tensors x three pieces
+  static constexpr int kStatBytes = 2 * kXN * 4;            // LSE2[64] + D[64] per stage (dK/dV kernel)
+  static constexpr int kRingOffset = kResBytes;
+  static constexpr int kStatOffset = kRingOffset + kXStages * kStageBytes;
+  static constexpr int kBarOffset = kStatOffset + kXStages * kStatBytes;
+  static constexpr int kNumBars = 1 + 2 * kXStages + 1 + 1 + 1;
+  static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
+};
+
+// issues the 6 piece products of one 128 x 64 x 64 SS GEMM (both operands MN-major), small terms first
+__device__ __forceinline__ void issue_ss6(uint32_t d_tmem, uint32_t a_pieces, uint32_t a_stride, uint32_t b_pieces,
+                                          uint32_t b_stride, uint32_t idesc) {
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+#pragma unroll
+    for (int ks = 0; ks < kXD / 16; ++ks)
+      mma_ss(d_tmem, smem_desc_sw128(a_pieces + kPairA[t] * a_stride + ks * 2048, kXD * 128, 1024),
+             smem_desc_sw128(b_pieces + kPairB[t] * b_stride + ks * 2048, kXD * 128, 1024), idesc, (t | ks) != 0);
+}
+// 6 piece products of a TS GEMM: A pieces in TMEM (32 columns each), B pieces K-major in shared memory.
+// d_corr == d_main: everything into one accumulator. Otherwise the leading product a0*b0 goes to d_main and the five
+// small ones to d_corr: an accumulator that lives across many tiles then takes 6x fewer truncating additions.
+__device__ __forceinline__ void issue_ts6(uint32_t d_main, uint32_t d_corr, uint32_t a_tmem, uint32_t b_pieces,
+                                          uint32_t b_stride, uint32_t idesc, bool accumulate) {
+  const bool split = d_main != d_corr;
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+#pragma unroll
+    for (int ks = 0; ks < kXN / 16; ++ks) {
+      const bool lead = t == 5;
+      const bool first = split ? (lead ? ks == 0 : (t | ks) == 0) : (t | ks) == 0;
+      mma_ts(lead ? d_main : d_corr, a_tmem + kPairA[t] * 32 + ks * 8,
+             smem_desc_sw128(b_pieces + kPairB[t] * b_stride + ks * 32, 16, 1024), idesc,
+             (accumulate || !first) ? 1u : 0u);
+    }
+}
+
+// =================================================================================================
+// dQ kernel
+// =================================================================================================
+__global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_constant__ BwdF32Params p) {
+  using Cfg = XCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base;                           // [3][kResTile]
+  const uint32_t do_smem = smem_base + 3 * Cfg::kResTile;      // [3][kResTile]
+  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: K pieces [3][kStrTile], V pieces [3][kStrTile]
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_q_full = bars;
+  const uint32_t bar_kv_full = bars + 8;
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * kXStages;
+  const uint32_t bar_s_full = bar_kv_empty + 8 * kXStages;
+  const uint32_t bar_p_ready = bar_s_full + 8;
+  const uint32_t bar_final = bar_p_ready + 8;
+  const uint32_t tmem_slot = bar_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_blocks);
+  const int blk = p.n_blocks - 1 - int(blockIdx.x % p.n_blocks);
+  const int q0 = blk * kXM;
+  const int q_hi = min(q0 + kXM, p.nq) - 1;
+  int kt_first, kt_last;
+  fa_k_tile_range(rule, q0, q_hi, kXN, &kt_first, &kt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {q0};
+    const int hi[1] = {q_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, true, lo, hi, valid, 1, kt_first, kt_last, kXN, p.nk, kXThreads / 32);
+  }
+  if (warp == 4) {
+    if (elect_one())
+      for (int j = 0; j < 3; ++j) {
+        prefetch_tensormap(&p.map_q[j]);
+        prefetch_tensormap(&p.map_k[j]);
+        prefetch_tensormap(&p.map_v[j]);
+        prefetch_tensormap(&p.map_do[j]);
+      }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      mbar_init(bar_q_full, 1);
+      mbar_init(bar_s_full, 1);
+      mbar_init(bar_p_ready, kXM);
+      mbar_init(bar_final, 1);
+      for (int s = 0; s < kXStages; ++s) {
+        mbar_init(bar_kv_full + 8 * s, 1);
+        mbar_init(bar_kv_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 6) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: S [0, 64)  dP [64, 128)  dQ [128, 192)  dQ small terms [192, 256)  dS pieces [256 + 32 j, +32)
+  constexpr uint32_t kColDp = 64, kColDq = 128, kColDqc = 192, kColDs = 256;
+
+  if (warp >= 4) {
+    if (warp == 4) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_q_full, Cfg::kResBytes);
+        for (int j = 0; j < 3; ++j)
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(q_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_q[j], bar_q_full, q0 + h * 64, b * kXD);
+            tma_load_2d(do_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_do[j], bar_q_full, q0 + h * 64, b * kXD);
+          }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        int kt, tw, tb;
+        while (it.next(&kt, &tw, &tb)) {
+          const int s = t % kXStages, u = t / kXStages;
+          mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
+          for (int j = 0; j < 3; ++j) {
+            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrTile, &p.map_k[j], bar_kv_full + 8 * s, kt * kXN,
+                        b * kXD);
+            tma_load_2d(ring + s * Cfg::kStageBytes + (3 + j) * Cfg::kStrTile, &p.map_v[j], bar_kv_full + 8 * s,
+                        kt * kXN, b * kXD);
+          }
+          ++t;
+        }
+      }
+    } else if (warp == 5) {
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, kt_first, kt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_s = idesc_bf16(kXM, kXN, true, true);
+        constexpr uint32_t idesc_dq = idesc_bf16(kXM, kXD, false, false);
+        auto issue_s_dp = [&](int stage) {
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + 3 * Cfg::kStrTile;
+          issue_ss6(tmem_base, q_smem, Cfg::kResTile, k_s, Cfg::kStrTile, idesc_s);
+          issue_ss6(tmem_base + kColDp, do_smem, Cfg::kResTile, v_s, Cfg::kStrTile, idesc_s);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_full + 0, 0);
+          mbar_wait(bar_q_full, 0);
+          tc_fence_after();
+          issue_s_dp(0);
+          mma_commit(bar_s_full);
+          for (int j = 0; j < n; ++j) {
+            const int sj = j % kXStages, sn = (j + 1) % kXStages;
+            mbar_wait(bar_p_ready, j & 1);
+            tc_fence_after();
+            issue_ts6(tmem_base + kColDq, tmem_base + kColDqc, tmem_base + kColDs, ring + sj * Cfg::kStageBytes,
+                      Cfg::kStrTile, idesc_dq, j > 0);
+            mma_commit(bar_kv_empty + 8 * sj);
+            if (j + 1 < n) {
+              mbar_wait(bar_kv_full + 8 * sn, ((j + 1) / kXStages) & 1);
+              tc_fence_after();
+              issue_s_dp(sn);
+              mma_commit(bar_s_full);
+            } else {
+              mma_commit(bar_final);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;                // query row
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr;
+    const int qi = q0 + r;
+    const bool q_valid = qi < p.nq;
+    const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float scale_log2 = p.scale_log2;
+    // The forward's l, m come from a 3xTF32 S (about 2^-21 relative), this kernel's S from three bf16 pieces (2^-24):
+    // P = exp2(S c - LSE2) then misses sum_k P = 1 by a common factor per row of a few 1e-6, which is the whole error
+    // budget of the gradients. The row sum of P is free here (one thread owns the row over all key tiles), so the row
+    // is renormalised: dQ is divided by it and LSE2 + log2(rowsum) is handed to the dK/dV kernel.
+    float row_sum = 0.f;
+    int j = 0;
+    TileIter it;
+    it.init(sched, 1, kt_first, kt_last);
+    int kt, tw, tb;
+    while (it.next(&kt, &tw, &tb)) {
+      const int k0 = kt * kXN;
+      const int k_hi = min(k0 + kXN, p.nk) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool ragged = k0 + kXN > p.nk;
+      mbar_wait(bar_s_full, j & 1);
+      tc_fence_after();
+      // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
+      uint32_t okm[2] = {0xffffffffu, 0xffffffffu};
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        const int nvalid = k_hi - k0 + 1;
+        okm[0] = tile_mask32(rule, true, qpos, k0, 0, nvalid);
+        okm[1] = tile_mask32(rule, true, qpos, k0, 32, nvalid);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float s[32], dp[32];
+        tmem_ld32f(t_s + h * 32, s);
+        tmem_ld32f(t_s + kColDp + h * 32, dp);
+        tmem_wait_ld();
+        uint32_t c0[16], c1[16], c2[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = exp2f(fmaf(s[c], scale_log2, -lse2));
+          float p1 = exp2f(fmaf(s[c + 1], scale_log2, -lse2));
+          p0 = (okm[h] >> c) & 1u ? p0 : 0.f;
+          p1 = (okm[h] >> (c + 1)) & 1u ? p1 : 0.f;
+          row_sum += p0 + p1;
+          split3_pack(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), c0[c >> 1], c1[c >> 1], c2[c >> 1]);
+        }
+        tmem_st16(t_s + kColDs + h * 16, c0);
+        tmem_st16(t_s + kColDs + 32 + h * 16, c1);
+        tmem_st16(t_s + kColDs + 64 + h * 16, c2);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+      ++j;
+    }
+    // epilogue: dQ = scale * acc, fp32, straight to global (lanes = consecutive queries -> coalesced per channel)
+    float* out = p.d_q + int64_t(b) * kXD * p.nq + qi;
+    const float out_scale = row_sum > 0.f ? p.scale / row_sum : 0.f;
+    if (q_valid)
+      p.lse2_refined[int64_t(b) * p.nq + qi] = row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000);
+    if (j > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kXD / 32; ++c) {
+        float o[32], oc[32];
+        tmem_ld32f(t_s + kColDq + c * 32, o);
+        tmem_ld32f(t_s + kColDqc + c * 32, oc);
+        tmem_wait_ld();
+        if (q_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
+        }
+      }
+    } else if (q_valid) {
+      for (int c = 0; c < kXD; ++c) out[int64_t(c) * p.nq] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================
+// dK / dV kernel
+// =================================================================================================
+__global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid_constant__ BwdF32Params p) {
+  using Cfg = XCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t k_smem = smem_base;                           // [3][kResTile]
+  const uint32_t v_smem = smem_base + 3 * Cfg::kResTile;       // [3][kResTile]
+  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: Q pieces [3][kStrTile], dO pieces [3][kStrTile]
+  const uint32_t stat_smem = smem_base + Cfg::kStatOffset;
+  const uint32_t bars = smem_base + Cfg::kBarOffset;
+  const uint32_t bar_kv_res = bars;
+  const uint32_t bar_full = bars + 8;
+  const uint32_t bar_empty = bar_full + 8 * kXStages;
+  const uint32_t bar_s_full = bar_empty + 8 * kXStages;
+  const uint32_t bar_p_ready = bar_s_full + 8;
+  const uint32_t bar_final = bar_p_ready + 8;
+  const uint32_t tmem_slot = bar_final + 8;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
+  const float* stat_gen = reinterpret_cast<const float*>(smem_gen + Cfg::kStatOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const FaRule& rule = p.rule;
+  const int b = int(blockIdx.x / p.n_blocks);
+  const int kblk = int(blockIdx.x % p.n_blocks);
+  const int k0 = kblk * kXM;
+  const int k_hi = min(k0 + kXM, p.nk) - 1;
+  int qt_first, qt_last;
+  fa_q_tile_range(rule, k0, k_hi, kXN, &qt_first, &qt_last);
+  TileSchedule* sched = reinterpret_cast<TileSchedule*>(smem_gen + Cfg::kSchedOffset);
+  {
+    const int lo[1] = {k0};
+    const int hi[1] = {k_hi};
+    const bool valid[1] = {true};
+    build_schedule(sched, rule, false, lo, hi, valid, 1, qt_first, qt_last, kXN, p.nq, kXThreads / 32);
+  }
+  if (warp == 4) {
+    if (elect_one())
+      for (int j = 0; j < 3; ++j) {
+        prefetch_tensormap(&p.map_q[j]);
+        prefetch_tensormap(&p.map_k[j]);
+        prefetch_tensormap(&p.map_v[j]);
+        prefetch_tensormap(&p.map_do[j]);
+      }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      mbar_init(bar_kv_res, 1);
+      mbar_init(bar_s_full, 1);
+      mbar_init(bar_p_ready, kXM);
+      mbar_init(bar_final, 1);
+      for (int s = 0; s < kXStages; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      fence_barrier_init();
+    }
+  } else if (warp == 6) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  // TMEM columns: S^T [0, 64) and dP^T [64, 128) are read completely into registers by the row's thread, which then
+  // writes the P^T pieces over them at [32 j, +32) and the dS^T pieces at [96 + 32 j, +32) (a thread only ever touches
+  // its own lane, and the next S^T / dP^T products are issued behind the dV / dK products that consume the pieces).
+  // dV [192, 256)  dK [256, 320)  and their small-term accumulators dVc [320, 384)  dKc [384, 448): dV and dK live
+  // across all query tiles, and the tensor core truncates on every accumulation - with everything in one accumulator
+  // the bias reached 2.7e-5 after 16 tiles; the leading products alone add 6x less often.
+  constexpr uint32_t kColDp = 64, kColP = 0, kColDs = 96, kColDv = 192, kColDk = 256, kColDvc = 320, kColDkc = 384;
+
+  if (warp >= 4) {
+    if (warp == 4) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_kv_res, Cfg::kResBytes);
+        for (int j = 0; j < 3; ++j)
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(k_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_k[j], bar_kv_res, k0 + h * 64, b * kXD);
+            tma_load_2d(v_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_v[j], bar_kv_res, k0 + h * 64, b * kXD);
+          }
+        int t = 0;
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        int qt, tw, tb;
+        while (it.next(&qt, &tw, &tb)) {
+          const int s = t % kXStages, u = t / kXStages;
+          mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
+          for (int j = 0; j < 3; ++j) {
+            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrTile, &p.map_q[j], bar_full + 8 * s, qt * kXN,
+                        b * kXD);
+            tma_load_2d(ring + s * Cfg::kStageBytes + (3 + j) * Cfg::kStrTile, &p.map_do[j], bar_full + 8 * s,
+                        qt * kXN, b * kXD);
+          }
+          const int64_t off = int64_t(b) * p.nq + qt * kXN;
+          bulk_load_1d_x(stat_smem + s * Cfg::kStatBytes, p.lse2_refined + off, kXN * 4, bar_full + 8 * s);
+          bulk_load_1d_x(stat_smem + s * Cfg::kStatBytes + kXN * 4, p.dsum + off, kXN * 4, bar_full + 8 * s);
+          ++t;
+        }
+      }
+    } else if (warp == 5) {
+      if (elect_one()) {
+        TileIter it;
+        it.init(sched, 1, qt_first, qt_last);
+        const int n = it.count();
+        constexpr uint32_t idesc_st = idesc_bf16(kXM, kXN, true, true);
+        constexpr uint32_t idesc_acc = idesc_bf16(kXM, kXD, false, false);
+        auto issue_st_dpt = [&](int stage) {
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrTile;
+          issue_ss6(tmem_base, k_smem, Cfg::kResTile, q_s, Cfg::kStrTile, idesc_st);
+          issue_ss6(tmem_base + kColDp, v_smem, Cfg::kResTile, do_s, Cfg::kStrTile, idesc_st);
+        };
+        if (n > 0) {
+          mbar_wait(bar_kv_res, 0);
+          mbar_wait(bar_full + 0, 0);
+          tc_fence_after();
+          issue_st_dpt(0);
+          mma_commit(bar_s_full);
+          for (int t = 0; t < n; ++t) {
+            const int st = t % kXStages, s2 = (t + 1) % kXStages;
+            mbar_wait(bar_p_ready, t & 1);
+            tc_fence_after();
+            const uint32_t q_s = ring + st * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrTile;
+            issue_ts6(tmem_base + kColDv, tmem_base + kColDvc, tmem_base + kColP, do_s, Cfg::kStrTile, idesc_acc, t > 0);
+            issue_ts6(tmem_base + kColDk, tmem_base + kColDkc, tmem_base + kColDs, q_s, Cfg::kStrTile, idesc_acc, t > 0);
+            mma_commit(bar_empty + 8 * st);
+            if (t + 1 < n) {
+              mbar_wait(bar_full + 8 * s2, ((t + 1) / kXStages) & 1);
+              tc_fence_after();
+              issue_st_dpt(s2);
+              mma_commit(bar_s_full);
+            }
+          }
+          mma_commit(bar_final);
+        }
+      }
+    }
+  } else {
+    const int r = threadIdx.x;                // key row
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr;
+    const int ki = k0 + r;
+    const bool k_valid = ki < p.nk;
+    const FaPos kpos = fa_pos(rule, rule.k, min(ki, p.nk - 1));
+    const float scale_log2 = p.scale_log2;
+    int t = 0;
+    TileIter it;
+    it.init(sched, 1, qt_first, qt_last);
+    int qt, tw, tb;
+    while (it.next(&qt, &tw, &tb)) {
+      const int st = t % kXStages;
+      const int q0 = qt * kXN;
+      const int q_hi = min(q0 + kXN, p.nq) - 1;
+      const int cls = it.cls(0, tw, tb);
+      const bool ragged = (q0 + kXN > p.nq) || (k0 + kXM > p.nk);
+      mbar_wait(bar_full + 8 * st, (t / kXStages) & 1);   // statistics visible to this thread
+      mbar_wait(bar_s_full, t & 1);
+      tc_fence_after();
+      uint32_t okm[2] = {0xffffffffu, 0xffffffffu};
+      if (cls == FA_TILE_PARTIAL || ragged) {
+        okm[0] = okm[1] = 0u;
+        if (k_valid) {
+          const int nvalid = q_hi - q0 + 1;
+          okm[0] = tile_mask32(rule, false, kpos, q0, 0, nvalid);
+          okm[1] = tile_mask32(rule, false, kpos, q0, 32, nvalid);
+        }
+      }
+      const float* lse_s = stat_gen + st * (2 * kXN);
+      const float* dsum_s = lse_s + kXN;
+      float s[64], dp[64];
+      tmem_ld32f(t_s, &s[0]);
+      tmem_ld32f(t_s + 32, &s[32]);
+      tmem_ld32f(t_s + kColDp, &dp[0]);
+      tmem_ld32f(t_s + kColDp + 32, &dp[32]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a0[16], a1[16], a2[16], c0[16], c1[16], c2[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = exp2f(fmaf(s[h * 32 + c], scale_log2, -lse_s[h * 32 + c]));
+          float p1 = exp2f(fmaf(s[h * 32 + c + 1], scale_log2, -lse_s[h * 32 + c + 1]));
+          p0 = (okm[h] >> c) & 1u ? p0 : 0.f;
+          p1 = (okm[h] >> (c + 1)) & 1u ? p1 : 0.f;
+          split3_pack(p0, p1, a0[c >> 1], a1[c >> 1], a2[c >> 1]);
+          split3_pack(p0 * (dp[h * 32 + c] - dsum_s[h * 32 + c]), p1 * (dp[h * 32 + c + 1] - dsum_s[h * 32 + c + 1]),
+                      c0[c >> 1], c1[c >> 1], c2[c >> 1]);
+        }
+        tmem_st16(t_s + kColP + h * 16, a0);
+        tmem_st16(t_s + kColP + 32 + h * 16, a1);
+        tmem_st16(t_s + kColP + 64 + h * 16, a2);
+        tmem_st16(t_s + kColDs + h * 16, c0);
+        tmem_st16(t_s + kColDs + 32 + h * 16, c1);
+        tmem_st16(t_s + kColDs + 64 + h * 16, c2);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+      ++t;
+    }
+    // epilogue: dV, dK = scale * acc in fp32, straight to global (lanes = consecutive keys -> coalesced per channel)
+    float* out_v = p.d_v + int64_t(b) * kXD * p.nk + ki;
+    float* out_k = p.d_k + int64_t(b) * kXD * p.nk + ki;
+    if (t > 0) {
+      mbar_wait(bar_final, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2 * (kXD / 32); ++c) {
+        float o[32], oc[32];
+        tmem_ld32f(t_s + kColDv + c * 32, o);    // dV [192, 256) and dK [256, 320) are adjacent,
+        tmem_ld32f(t_s + kColDvc + c * 32, oc);  // and so are their small-term accumulators
+        tmem_wait_ld();
+        if (k_valid) {
+          float* out = c < kXD / 32 ? out_v : out_k;
+          const float sc = c < kXD / 32 ? 1.f : p.scale;
+          const int cc = (c % (kXD / 32)) * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) out[int64_t(cc + e) * p.nk] = (o[e] + oc[e]) * sc;
+        }
+      }
+    } else if (k_valid) {
+      for (int c = 0; c < kXD; ++c) {
+        out_v[int64_t(c) * p.nk] = 0.f;
+        out_k[int64_t(c) * p.nk] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct F32BwdWorkspace {
+  size_t stats, q, k, total;   // byte sizes: statistics, one piece of Q / dO, one piece of K / V
+};
+static F32BwdWorkspace f32_bwd_layout(int64_t batch, int64_t nq, int64_t nk) {
+  F32BwdWorkspace w;
+  w.stats = align256(size_t(3) * (batch * nq + kXStatPad) * sizeof(float));
+  w.q = align256(size_t(batch) * kXD * nq * 2);
+  w.k = align256(size_t(batch) * kXD * nk * 2);
+  w.total = w.stats + 6 * w.q + 6 * w.k;
+  return w;
+}
+
+cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
+  const int nq = a.rule.q.total, nk = a.rule.k.total;
+  const F32BwdWorkspace w = f32_bwd_layout(a.batch, nq, nk);
+  char* ws = reinterpret_cast<char*>(a.workspace);
+  float* lse2 = reinterpret_cast<float*>(ws);
+  float* dsum = lse2 + (a.batch * int64_t(nq) + kXStatPad);
+  float* lse2_refined = dsum + (a.batch * int64_t(nq) + kXStatPad);
+  char* pieces = ws + w.stats;
+  __nv_bfloat16 *qp[3], *dop[3], *kp[3], *vp[3];
+  for (int j = 0; j < 3; ++j) {
+    qp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + j * w.q);
+    dop[j] = reinterpret_cast<__nv_bfloat16*>(pieces + (3 + j) * w.q);
+    kp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 6 * w.q + j * w.k);
+    vp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 6 * w.q + (3 + j) * w.k);
+  }
+  BwdF32Params p;
+  for (int j = 0; j < 3; ++j)
+    if (!make_map_2d(&p.map_q[j], qp[j], a.batch * kXD, nq, 64, kXD, true) ||
+        !make_map_2d(&p.map_do[j], dop[j], a.batch * kXD, nq, 64, kXD, true) ||
+        !make_map_2d(&p.map_k[j], kp[j], a.batch * kXD, nk, 64, kXD, true) ||
+        !make_map_2d(&p.map_v[j], vp[j], a.batch * kXD, nk, 64, kXD, true))
+      return cudaErrorInvalidValue;
+  p.rule = a.rule;
+  p.lse2 = lse2;
+  p.dsum = dsum;
+  p.lse2_refined = lse2_refined;
+  p.d_q = (float*)a.d_q;
+  p.d_k = (float*)a.d_k;
+  p.d_v = (float*)a.d_v;
+  p.nq = nq;
+  p.nk = nk;
+  p.batch = int32_t(a.batch);
+  p.scale = 1.f / sqrtf(float(kXD));
+  p.scale_log2 = p.scale * kXLog2e;
+  cudaError_t e;
+  {
+    const struct { const void* src; __nv_bfloat16** dst; int64_t n; } jobs[4] = {
+        {a.q, qp, a.batch * int64_t(kXD) * nq}, {a.d_o, dop, a.batch * int64_t(kXD) * nq},
+        {a.k, kp, a.batch * int64_t(kXD) * nk}, {a.v, vp, a.batch * int64_t(kXD) * nk}};
+    for (const auto& jb : jobs) {
+      const int blocks = int(std::min<int64_t>((jb.n + 255) / 256, 148 * 16));
+      ScopedKernel timed("split_bf16x3", stream);
+      split_bf16x3_kernel<<<blocks, 256, 0, stream>>>((const float*)jb.src, jb.dst[0], jb.dst[1], jb.dst[2], jb.n);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+  }
+  {
+    const int64_t total = a.batch * int64_t(nq);
+    const int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 16));
+    ScopedKernel timed("bwd_prep_f32", stream);
+    bwd_prep_f32<<<blocks, 256, 0, stream>>>((const float*)a.o, (const float*)a.d_o, (const float*)a.l,
+                                             (const float*)a.m, lse2, dsum, lse2_refined, a.batch, kXD, nq);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    e = cudaFuncSetAttribute(bwd_dq_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    p.n_blocks = (nq + kXM - 1) / kXM;
+    ScopedKernel timed("bwd_dq_f32_bf16x3_sm100", stream);
+    bwd_dq_f32_kernel<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, XCfg::kSmemBytes, stream>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  {
+    e = cudaFuncSetAttribute(bwd_dkdv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    p.n_blocks = (nk + kXM - 1) / kXM;
+    ScopedKernel timed("bwd_dkdv_f32_bf16x3_sm100", stream);
+    bwd_dkdv_f32_kernel<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, XCfg::kSmemBytes, stream>>>(p);
+    return cudaGetLastError();
+  }
+}
+
+}  // namespace sm100
+
+static bool aligned16x(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a) {
+  return sm100::f32_bwd_layout(a.batch, a.rule.q.total, a.rule.k.total).total;
+}
+
+bool sm100_f32_backward_supports(const LaunchArgs& a) {
+  if (a.dtype != 1 || a.accumulate) return false;
+  if (a.d != sm100::kXD || a.v_d != sm100::kXD) return false;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (nq % 8 || nk % 8) return false;   // TMA row pitch of the bf16 pieces
+  if (a.workspace && !aligned16x(a.workspace)) return false;
+  if (a.batch * sm100::kXD > 0x7fffffffLL) return false;
+  if (((nq + 127) / 128) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
+  if (a.workspace_bytes < sm100_f32_backward_workspace_bytes(a)) return false;
+  return true;
+}
+
+cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream) { return sm100::launch_bwd_f32(a, stream); }
+
+}  // namespace fa

@@ -65,4 +65,9 @@ bool sm100_f32_forward_supports(const LaunchArgs& a);
 size_t sm100_f32_forward_workspace_bytes(const LaunchArgs& a);
 cudaError_t sm100_f32_forward(const LaunchArgs& a, cudaStream_t stream);
 
+// fp32 backward on the tensor cores, three bf16 pieces per operand (fa_bwd_f32_sm100.cu)
+bool sm100_f32_backward_supports(const LaunchArgs& a);
+size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a);
+cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream);
+
 }  // namespace fa
