@@ -26,7 +26,7 @@ FA_EINVAL_BATCH = -12
 FA_EINVAL_SEQ_SHAPE = -13
 FA_ECUDA = -100
 
-PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_3xtf32", 4: "dmma_f64"}
+PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_f32_split", 4: "reserved"}
 
 
 class Problem(C.Structure):
