@@ -52,6 +52,12 @@ __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restr
                              const float* __restrict__ l, const __half* __restrict__ m, float* __restrict__ lse2,
                              float* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq) {
   const int64_t total = batch * nq;
+  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
+  // (a NaN there would turn the masked 0 * (dP - D) into NaN)
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
   // two adjacent query positions per thread -> half2 loads, coalesced along the sequence
   for (int64_t i2 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 2; i2 < total;
        i2 += int64_t(gridDim.x) * blockDim.x * 2) {
@@ -76,12 +82,6 @@ __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restr
       lse2[i2 + e] = (lv > 0.f && !is_sentinel<__half>(mv)) ? (__half2float(mv) + logf(lv)) * kLog2eB
                                                              : __int_as_float(0x7f800000);
     }
-  }
-  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
-  // (a NaN there would turn the masked 0 * (dP - D) into NaN)
-  if (blockIdx.x == 0 && threadIdx.x < kStatPad) {
-    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
-    dsum[total + threadIdx.x] = 0.f;
   }
 }
 
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
         if (tq0 + h * 64 < p.nq)
           tma_store_2d(&p.map_dq, q_smem + i * Cfg::kQBytes + h * (D * 128), tq0 + h * 64, b * D);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
       for (int h = 0; h < 2; ++h)
         if (q0 + h * 64 < p.nq) tma_store_2d(&p.map_dq, q_smem + h * (D * 128), q0 + h * 64, b * D);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
             tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
         }
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -1179,7 +1179,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
             tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
         }
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();
@@ -1653,7 +1653,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
             tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
         }
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
   tc_fence_before();

@@ -80,6 +80,12 @@ __global__ void bwd_prep_f32(const float* __restrict__ o, const float* __restric
                              const float* __restrict__ m, float* __restrict__ lse2, float* __restrict__ dsum,
                              float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
   const int64_t total = batch * nq;
+  // the padding behind the arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kXStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    lse2_refined[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t b = i / nq, r = i - b * nq;
     const float* op = o + b * v_d * int64_t(nq) + r;
@@ -89,12 +95,6 @@ __global__ void bwd_prep_f32(const float* __restrict__ o, const float* __restric
     dsum[i] = acc;
     const float lv = l[i], mv = m[i];
     lse2[i] = (lv > 0.f && !is_sentinel<float>(mv)) ? (mv + logf(lv)) * kXLog2e : __int_as_float(0x7f800000);
-  }
-  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile
-  if (blockIdx.x == 0 && threadIdx.x < kXStatPad) {
-    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
-    lse2_refined[total + threadIdx.x] = __int_as_float(0x7f800000);
-    dsum[total + threadIdx.x] = 0.f;
   }
 }
 

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         if (tq0 + h * 64 < p.nq)
           tma_store_2d(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b * VD);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
 

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kF32Threads, 1) fwd_f32_kernel(const __grid_co
       for (int h = 0; h < 4; ++h)
         if (q0 + h * 32 < p.nq) tma_store_2d(&p.map_o, q_hi + h * (VD * 128), q0 + h * 32, b * VD);
       tma_store_commit();
-      tma_store_wait_all();
+      tma_store_wait_read();
     }
   }
 

@@ -70,6 +70,11 @@ __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t smem_src,
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// shared-memory source of every committed bulk store has been read (enough before the CTA reuses the tile or exits;
+// the global writes complete on their own before the grid does)
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
