@@ -423,8 +423,16 @@ def main():
                 what = f"{dom}: 2*nnz*(3d+2v_d)*batch FLOPs per backward pass"
             traffic = NCU_TRAFFIC.get((args.workload, "bwd"))
         peak = peaks["tensor_sustained"] or peaks["tensor_burst"]
+        peak_note = ", sustained bf16 GEMM"
+        if w["dtype"] == "float32":
+            # split precision: 3 half-rate TF32 MMAs (forward) or 6 full-rate bf16 MMAs (backward) per fp32 product
+            peak = peak / 6.0
+            peak_note = ", sustained bf16 GEMM / 6 (fp32 through split-precision tensor-core products)"
+        elif w["dtype"] == "float64":
+            peak = 40.0
+            peak_note = "; fp64: nominal 40 TFLOP/s (DFMA / DMMA), not measured on this pool"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_fused_ncu.md (bwd: the fused kernel)" if traffic else None, "peak_source": peaks["source"] + ", sustained bf16 GEMM",
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_fused_ncu.md (bwd: the fused kernel)" if traffic else None, "peak_source": peaks["source"] + peak_note,
                     "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic": what}
         # HBM side of the roofline: algorithmic bytes of the same kernel(s) over their duration.
