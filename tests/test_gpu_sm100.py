@@ -268,8 +268,8 @@ def test_fp32_3xtf32_forward_matches_oracle(case):
     assert np.max(np.abs(lse - (ref["m"][live] + np.log(ref["l"][live])))) <= 1e-5
     dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
     nq, nk = int(np.prod(qs)), int(np.prod(ks))
-    if d == 64 and vd == 64 and nq % 8 == 0 and nk % 8 == 0:
-        # head_dim 64: split-precision tcgen05 backward (three bf16 pieces per operand, fa_bwd_f32_sm100.cu)
+    if (d, vd) in ((64, 64), (32, 32), (32, 16)) and nq % 8 == 0 and nk % 8 == 0:
+        # split-precision tcgen05 backward (three bf16 pieces per operand, fa_bwd_f32_sm100.cu)
         assert _capi.lib.fa_last_path() == 3, "fp32 backward did not take the tensor-core path"
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
         err = scaled_err(g.cpu().numpy(), ref[name])

@@ -1,4 +1,4 @@
-// fa_bwd_f32_sm100.cu — fp32 backward on the tensor cores (head_dim 64): split-precision tcgen05 kernels.
+// fa_bwd_f32_sm100.cu — fp32 backward on the tensor cores (head dims 64/64, 32/32, 32/16): split-precision tcgen05 kernels.
 //
 // The forward runs fp32 as 3xTF32 (fa_fwd_f32_sm100.cu). The backward needs every streamed tile in BOTH operand
 // orientations (K as the MN-major B operand of S = Q K^T and as the K-major B operand of dQ = dS K, Q likewise in the
@@ -12,7 +12,7 @@
 // fp16 kernels' tiles. Accumulation is fp32 in TMEM; softmax statistics, exp2f and dS are fp32 in registers; P and dS
 // are re-split into three bf16 pieces for the second product of each chain.
 //
-//   split_bf16x3_kernel : Q, K, V, dO -> three bf16 tensors each (workspace)
+//   split_bf16x3_all    : Q, K, V, dO -> three bf16 tensors each (workspace), one launch
 //   bwd_prep_f32        : LSE2 = (m + log l) log2 e, D = rowsum(dO o O)
 //   bwd_dq_f32_kernel   : CTA = 128 query rows, streams 64-key tiles:  S, dP (SS) -> dS pieces (TMEM) -> dQ += dS K (TS)
 //   bwd_dkdv_f32_kernel : CTA = 128 keys, streams 64-query tiles: S^T, dP^T (SS) -> P^T, dS^T pieces -> dV, dK (TS)
@@ -34,7 +34,6 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 
 constexpr int kXM = 128;        // resident rows of a CTA (TMEM lanes)
 constexpr int kXN = 64;         // streamed tile width
-constexpr int kXD = 64;         // head dim (d == v_d == 64)
 constexpr int kXThreads = 256;  // 4 softmax warps, TMA warp, MMA warp, TMEM warp, spare
 constexpr int kXStages = 2;
 constexpr int kXStatPad = 64;
@@ -62,20 +61,6 @@ struct alignas(64) BwdF32Params {
 };
 
 // ---- operand split and row statistics --------------------------------------------------------------------
-__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p0,
-                                    __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int64_t n) {
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-    const float v = x[i];
-    const __nv_bfloat16 a = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(a);
-    const __nv_bfloat16 b = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(b);
-    p0[i] = a;
-    p1[i] = b;
-    p2[i] = __float2bfloat16_rn(r2);
-  }
-}
-
 __global__ void bwd_prep_f32(const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ l,
                              const float* __restrict__ m, float* __restrict__ lse2, float* __restrict__ dsum,
                              float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
@@ -116,11 +101,16 @@ __device__ __forceinline__ void bulk_load_1d_x(uint32_t smem_dst, const void* gs
                : "memory");
 }
 
+// D = channels of Q / K, VD = channels of V / dO. One bf16 piece of a tile is [channels][64 positions] boxes of
+// 128-byte rows: a resident 128-position tile is two boxes, a streamed tile one.
+template <int D, int VD>
 struct XCfg {
-  static constexpr int kResTile = kXM * kXD * 2;            // one bf16 piece of a resident 128-row tile: 16 KB
-  static constexpr int kStrTile = kXN * kXD * 2;            // one piece of a streamed 64-wide tile: 8 KB
-  static constexpr int kResBytes = 6 * kResTile;            // two resident tensors x three pieces
-  static constexpr int kStageBytes = 6 * kStrTile;          // two streamed tensors x three pieces
+  static constexpr int kResD = kXM * D * 2;                 // resident piece with D channels (Q or K): 16 KB at D = 64
+  static constexpr int kResV = kXM * VD * 2;                // resident piece with VD channels (dO or V)
+  static constexpr int kStrD = kXN * D * 2;                 // streamed piece with D channels (K or Q)
+  static constexpr int kStrV = kXN * VD * 2;                // streamed piece with VD channels (V or dO)
+  static constexpr int kResBytes = 3 * (kResD + kResV);     // two resident tensors x three pieces
+  static constexpr int kStageBytes = 3 * (kStrD + kStrV);   // two streamed tensors x three pieces
   static constexpr int kStatBytes = 2 * kXN * 4;            // LSE2[64] + D[64] per stage (dK/dV kernel)
   static constexpr int kRingOffset = kResBytes;
   static constexpr int kStatOffset = kRingOffset + kXStages * kStageBytes;
@@ -130,15 +120,17 @@ struct XCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-// issues the 6 piece products of one 128 x 64 x 64 SS GEMM (both operands MN-major), small terms first
+// issues the 6 piece products of one 128 x 64 x CH SS GEMM (both operands MN-major, CH = contraction length = channels
+// of the tiles), small terms first
+template <int CH>
 __device__ __forceinline__ void issue_ss6(uint32_t d_tmem, uint32_t a_pieces, uint32_t a_stride, uint32_t b_pieces,
                                           uint32_t b_stride, uint32_t idesc) {
 #pragma unroll
   for (int t = 0; t < 6; ++t)
 #pragma unroll
-    for (int ks = 0; ks < kXD / 16; ++ks)
-      mma_ss(d_tmem, smem_desc_sw128(a_pieces + kPairA[t] * a_stride + ks * 2048, kXD * 128, 1024),
-             smem_desc_sw128(b_pieces + kPairB[t] * b_stride + ks * 2048, kXD * 128, 1024), idesc, (t | ks) != 0);
+    for (int ks = 0; ks < CH / 16; ++ks)
+      mma_ss(d_tmem, smem_desc_sw128(a_pieces + kPairA[t] * a_stride + ks * 2048, CH * 128, 1024),
+             smem_desc_sw128(b_pieces + kPairB[t] * b_stride + ks * 2048, CH * 128, 1024), idesc, (t | ks) != 0);
 }
 // 6 piece products of a TS GEMM: A pieces in TMEM (32 columns each), B pieces K-major in shared memory.
 // d_corr == d_main: everything into one accumulator. Otherwise the leading product a0*b0 goes to d_main and the five
@@ -161,14 +153,15 @@ __device__ __forceinline__ void issue_ts6(uint32_t d_main, uint32_t d_corr, uint
 // =================================================================================================
 // dQ kernel
 // =================================================================================================
+template <int D, int VD>
 __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_constant__ BwdF32Params p) {
-  using Cfg = XCfg;
+  using Cfg = XCfg<D, VD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t q_smem = smem_base;                           // [3][kResTile]
-  const uint32_t do_smem = smem_base + 3 * Cfg::kResTile;      // [3][kResTile]
-  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: K pieces [3][kStrTile], V pieces [3][kStrTile]
+  const uint32_t q_smem = smem_base;                           // [3][kResD]
+  const uint32_t do_smem = smem_base + 3 * Cfg::kResD;         // [3][kResV]
+  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: K pieces [3][kStrD], V pieces [3][kStrV]
   const uint32_t bars = smem_base + Cfg::kBarOffset;
   const uint32_t bar_q_full = bars;
   const uint32_t bar_kv_full = bars + 8;
@@ -232,8 +225,8 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
         mbar_arrive_expect_tx(bar_q_full, Cfg::kResBytes);
         for (int j = 0; j < 3; ++j)
           for (int h = 0; h < 2; ++h) {
-            tma_load_2d(q_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_q[j], bar_q_full, q0 + h * 64, b * kXD);
-            tma_load_2d(do_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_do[j], bar_q_full, q0 + h * 64, b * kXD);
+            tma_load_2d(q_smem + j * Cfg::kResD + h * (D * 128), &p.map_q[j], bar_q_full, q0 + h * 64, b * D);
+            tma_load_2d(do_smem + j * Cfg::kResV + h * (VD * 128), &p.map_do[j], bar_q_full, q0 + h * 64, b * VD);
           }
         int t = 0;
         TileIter it;
@@ -244,10 +237,10 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
           for (int j = 0; j < 3; ++j) {
-            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrTile, &p.map_k[j], bar_kv_full + 8 * s, kt * kXN,
-                        b * kXD);
-            tma_load_2d(ring + s * Cfg::kStageBytes + (3 + j) * Cfg::kStrTile, &p.map_v[j], bar_kv_full + 8 * s,
-                        kt * kXN, b * kXD);
+            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrD, &p.map_k[j], bar_kv_full + 8 * s, kt * kXN,
+                        b * D);
+            tma_load_2d(ring + s * Cfg::kStageBytes + 3 * Cfg::kStrD + j * Cfg::kStrV, &p.map_v[j],
+                        bar_kv_full + 8 * s, kt * kXN, b * VD);
           }
           ++t;
         }
@@ -258,11 +251,11 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
         it.init(sched, 1, kt_first, kt_last);
         const int n = it.count();
         constexpr uint32_t idesc_s = idesc_bf16(kXM, kXN, true, true);
-        constexpr uint32_t idesc_dq = idesc_bf16(kXM, kXD, false, false);
+        constexpr uint32_t idesc_dq = idesc_bf16(kXM, D, false, false);
         auto issue_s_dp = [&](int stage) {
-          const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + 3 * Cfg::kStrTile;
-          issue_ss6(tmem_base, q_smem, Cfg::kResTile, k_s, Cfg::kStrTile, idesc_s);
-          issue_ss6(tmem_base + kColDp, do_smem, Cfg::kResTile, v_s, Cfg::kStrTile, idesc_s);
+          const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + 3 * Cfg::kStrD;
+          issue_ss6<D>(tmem_base, q_smem, Cfg::kResD, k_s, Cfg::kStrD, idesc_s);
+          issue_ss6<VD>(tmem_base + kColDp, do_smem, Cfg::kResV, v_s, Cfg::kStrV, idesc_s);
         };
         if (n > 0) {
           mbar_wait(bar_kv_full + 0, 0);
@@ -275,7 +268,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
             mbar_wait(bar_p_ready, j & 1);
             tc_fence_after();
             issue_ts6(tmem_base + kColDq, tmem_base + kColDqc, tmem_base + kColDs, ring + sj * Cfg::kStageBytes,
-                      Cfg::kStrTile, idesc_dq, j > 0);
+                      Cfg::kStrD, idesc_dq, j > 0);
             mma_commit(bar_kv_empty + 8 * sj);
             if (j + 1 < n) {
               mbar_wait(bar_kv_full + 8 * sn, ((j + 1) / kXStages) & 1);
@@ -348,7 +341,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       ++j;
     }
     // epilogue: dQ = scale * acc, fp32, straight to global (lanes = consecutive queries -> coalesced per channel)
-    float* out = p.d_q + int64_t(b) * kXD * p.nq + qi;
+    float* out = p.d_q + int64_t(b) * D * p.nq + qi;
     const float out_scale = row_sum > 0.f ? p.scale / row_sum : 0.f;
     if (q_valid)
       p.lse2_refined[int64_t(b) * p.nq + qi] = row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000);
@@ -356,18 +349,19 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       mbar_wait(bar_final, 0);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < kXD / 32; ++c) {
+      for (int c = 0; c < (D + 31) / 32; ++c) {
         float o[32], oc[32];
         tmem_ld32f(t_s + kColDq + c * 32, o);
         tmem_ld32f(t_s + kColDqc + c * 32, oc);
         tmem_wait_ld();
         if (q_valid) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < D) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
         }
       }
     } else if (q_valid) {
-      for (int c = 0; c < kXD; ++c) out[int64_t(c) * p.nq] = 0.f;
+      for (int c = 0; c < D; ++c) out[int64_t(c) * p.nq] = 0.f;
     }
   }
   tc_fence_before();
@@ -381,14 +375,15 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
 // =================================================================================================
 // dK / dV kernel
 // =================================================================================================
+template <int D, int VD>
 __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid_constant__ BwdF32Params p) {
-  using Cfg = XCfg;
+  using Cfg = XCfg<D, VD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t k_smem = smem_base;                           // [3][kResTile]
-  const uint32_t v_smem = smem_base + 3 * Cfg::kResTile;       // [3][kResTile]
-  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: Q pieces [3][kStrTile], dO pieces [3][kStrTile]
+  const uint32_t k_smem = smem_base;                           // [3][kResD]
+  const uint32_t v_smem = smem_base + 3 * Cfg::kResD;          // [3][kResV]
+  const uint32_t ring = smem_base + Cfg::kRingOffset;          // stage: Q pieces [3][kStrD], dO pieces [3][kStrV]
   const uint32_t stat_smem = smem_base + Cfg::kStatOffset;
   const uint32_t bars = smem_base + Cfg::kBarOffset;
   const uint32_t bar_kv_res = bars;
@@ -459,8 +454,8 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kResBytes);
         for (int j = 0; j < 3; ++j)
           for (int h = 0; h < 2; ++h) {
-            tma_load_2d(k_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_k[j], bar_kv_res, k0 + h * 64, b * kXD);
-            tma_load_2d(v_smem + j * Cfg::kResTile + h * (kXD * 128), &p.map_v[j], bar_kv_res, k0 + h * 64, b * kXD);
+            tma_load_2d(k_smem + j * Cfg::kResD + h * (D * 128), &p.map_k[j], bar_kv_res, k0 + h * 64, b * D);
+            tma_load_2d(v_smem + j * Cfg::kResV + h * (VD * 128), &p.map_v[j], bar_kv_res, k0 + h * 64, b * VD);
           }
         int t = 0;
         TileIter it;
@@ -471,10 +466,10 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
           for (int j = 0; j < 3; ++j) {
-            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrTile, &p.map_q[j], bar_full + 8 * s, qt * kXN,
-                        b * kXD);
-            tma_load_2d(ring + s * Cfg::kStageBytes + (3 + j) * Cfg::kStrTile, &p.map_do[j], bar_full + 8 * s,
-                        qt * kXN, b * kXD);
+            tma_load_2d(ring + s * Cfg::kStageBytes + j * Cfg::kStrD, &p.map_q[j], bar_full + 8 * s, qt * kXN,
+                        b * D);
+            tma_load_2d(ring + s * Cfg::kStageBytes + 3 * Cfg::kStrD + j * Cfg::kStrV, &p.map_do[j],
+                        bar_full + 8 * s, qt * kXN, b * VD);
           }
           const int64_t off = int64_t(b) * p.nq + qt * kXN;
           bulk_load_1d_x(stat_smem + s * Cfg::kStatBytes, p.lse2_refined + off, kXN * 4, bar_full + 8 * s);
@@ -488,11 +483,12 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         it.init(sched, 1, qt_first, qt_last);
         const int n = it.count();
         constexpr uint32_t idesc_st = idesc_bf16(kXM, kXN, true, true);
-        constexpr uint32_t idesc_acc = idesc_bf16(kXM, kXD, false, false);
+        constexpr uint32_t idesc_dv = idesc_bf16(kXM, VD, false, false);
+        constexpr uint32_t idesc_dk = idesc_bf16(kXM, D, false, false);
         auto issue_st_dpt = [&](int stage) {
-          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrTile;
-          issue_ss6(tmem_base, k_smem, Cfg::kResTile, q_s, Cfg::kStrTile, idesc_st);
-          issue_ss6(tmem_base + kColDp, v_smem, Cfg::kResTile, do_s, Cfg::kStrTile, idesc_st);
+          const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrD;
+          issue_ss6<D>(tmem_base, k_smem, Cfg::kResD, q_s, Cfg::kStrD, idesc_st);
+          issue_ss6<VD>(tmem_base + kColDp, v_smem, Cfg::kResV, do_s, Cfg::kStrV, idesc_st);
         };
         if (n > 0) {
           mbar_wait(bar_kv_res, 0);
@@ -504,9 +500,9 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
             const int st = t % kXStages, s2 = (t + 1) % kXStages;
             mbar_wait(bar_p_ready, t & 1);
             tc_fence_after();
-            const uint32_t q_s = ring + st * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrTile;
-            issue_ts6(tmem_base + kColDv, tmem_base + kColDvc, tmem_base + kColP, do_s, Cfg::kStrTile, idesc_acc, t > 0);
-            issue_ts6(tmem_base + kColDk, tmem_base + kColDkc, tmem_base + kColDs, q_s, Cfg::kStrTile, idesc_acc, t > 0);
+            const uint32_t q_s = ring + st * Cfg::kStageBytes, do_s = q_s + 3 * Cfg::kStrD;
+            issue_ts6(tmem_base + kColDv, tmem_base + kColDvc, tmem_base + kColP, do_s, Cfg::kStrV, idesc_dv, t > 0);
+            issue_ts6(tmem_base + kColDk, tmem_base + kColDkc, tmem_base + kColDs, q_s, Cfg::kStrD, idesc_dk, t > 0);
             mma_commit(bar_empty + 8 * st);
             if (t + 1 < n) {
               mbar_wait(bar_full + 8 * s2, ((t + 1) / kXStages) & 1);
@@ -583,30 +579,38 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
       ++t;
     }
     // epilogue: dV, dK = scale * acc in fp32, straight to global (lanes = consecutive keys -> coalesced per channel)
-    float* out_v = p.d_v + int64_t(b) * kXD * p.nk + ki;
-    float* out_k = p.d_k + int64_t(b) * kXD * p.nk + ki;
+    float* out_v = p.d_v + int64_t(b) * VD * p.nk + ki;
+    float* out_k = p.d_k + int64_t(b) * D * p.nk + ki;
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2 * (kXD / 32); ++c) {
+      for (int c = 0; c < (VD + 31) / 32; ++c) {
         float o[32], oc[32];
-        tmem_ld32f(t_s + kColDv + c * 32, o);    // dV [192, 256) and dK [256, 320) are adjacent,
-        tmem_ld32f(t_s + kColDvc + c * 32, oc);  // and so are their small-term accumulators
+        tmem_ld32f(t_s + kColDv + c * 32, o);
+        tmem_ld32f(t_s + kColDvc + c * 32, oc);
         tmem_wait_ld();
         if (k_valid) {
-          float* out = c < kXD / 32 ? out_v : out_k;
-          const float sc = c < kXD / 32 ? 1.f : p.scale;
-          const int cc = (c % (kXD / 32)) * 32;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) out[int64_t(cc + e) * p.nk] = (o[e] + oc[e]) * sc;
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < VD) out_v[int64_t(c * 32 + e) * p.nk] = o[e] + oc[e];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < (D + 31) / 32; ++c) {
+        float o[32], oc[32];
+        tmem_ld32f(t_s + kColDk + c * 32, o);
+        tmem_ld32f(t_s + kColDkc + c * 32, oc);
+        tmem_wait_ld();
+        if (k_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < D) out_k[int64_t(c * 32 + e) * p.nk] = (o[e] + oc[e]) * p.scale;
         }
       }
     } else if (k_valid) {
-      for (int c = 0; c < kXD; ++c) {
-        out_v[int64_t(c) * p.nk] = 0.f;
-        out_k[int64_t(c) * p.nk] = 0.f;
-      }
+      for (int c = 0; c < VD; ++c) out_v[int64_t(c) * p.nk] = 0.f;
+      for (int c = 0; c < D; ++c) out_k[int64_t(c) * p.nk] = 0.f;
     }
   }
   tc_fence_before();
@@ -621,20 +625,45 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct F32BwdWorkspace {
-  size_t stats, q, k, total;   // byte sizes: statistics, one piece of Q / dO, one piece of K / V
+  size_t stats, q, dout, k, v, total;   // byte sizes: statistics, one bf16 piece of Q, dO, K, V
 };
-static F32BwdWorkspace f32_bwd_layout(int64_t batch, int64_t nq, int64_t nk) {
+static F32BwdWorkspace f32_bwd_layout(int64_t batch, int64_t nq, int64_t nk, int d, int v_d) {
   F32BwdWorkspace w;
   w.stats = align256(size_t(3) * (batch * nq + kXStatPad) * sizeof(float));
-  w.q = align256(size_t(batch) * kXD * nq * 2);
-  w.k = align256(size_t(batch) * kXD * nk * 2);
-  w.total = w.stats + 6 * w.q + 6 * w.k;
+  w.q = align256(size_t(batch) * d * nq * 2);
+  w.dout = align256(size_t(batch) * v_d * nq * 2);
+  w.k = align256(size_t(batch) * d * nk * 2);
+  w.v = align256(size_t(batch) * v_d * nk * 2);
+  w.total = w.stats + 3 * (w.q + w.dout + w.k + w.v);
   return w;
 }
 
+struct SplitJobs {
+  const float* src[4];
+  __nv_bfloat16* dst[4][3];
+  int64_t n[4];
+};
+// one launch for the four operands: blockIdx.y selects the tensor
+__global__ void split_bf16x3_all(const SplitJobs jobs) {
+  const int t = blockIdx.y;
+  const float* __restrict__ x = jobs.src[t];
+  const int64_t n = jobs.n[t];
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+    jobs.dst[t][0][i] = a;
+    jobs.dst[t][1][i] = b2;
+    jobs.dst[t][2][i] = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+  }
+}
+
+template <int D, int VD>
 cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
+  using Cfg = XCfg<D, VD>;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
-  const F32BwdWorkspace w = f32_bwd_layout(a.batch, nq, nk);
+  const F32BwdWorkspace w = f32_bwd_layout(a.batch, nq, nk, D, VD);
   char* ws = reinterpret_cast<char*>(a.workspace);
   float* lse2 = reinterpret_cast<float*>(ws);
   float* dsum = lse2 + (a.batch * int64_t(nq) + kXStatPad);
@@ -643,16 +672,16 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   __nv_bfloat16 *qp[3], *dop[3], *kp[3], *vp[3];
   for (int j = 0; j < 3; ++j) {
     qp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + j * w.q);
-    dop[j] = reinterpret_cast<__nv_bfloat16*>(pieces + (3 + j) * w.q);
-    kp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 6 * w.q + j * w.k);
-    vp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 6 * w.q + (3 + j) * w.k);
+    dop[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 3 * w.q + j * w.dout);
+    kp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 3 * (w.q + w.dout) + j * w.k);
+    vp[j] = reinterpret_cast<__nv_bfloat16*>(pieces + 3 * (w.q + w.dout + w.k) + j * w.v);
   }
   BwdF32Params p;
   for (int j = 0; j < 3; ++j)
-    if (!make_map_2d(&p.map_q[j], qp[j], a.batch * kXD, nq, 64, kXD, true) ||
-        !make_map_2d(&p.map_do[j], dop[j], a.batch * kXD, nq, 64, kXD, true) ||
-        !make_map_2d(&p.map_k[j], kp[j], a.batch * kXD, nk, 64, kXD, true) ||
-        !make_map_2d(&p.map_v[j], vp[j], a.batch * kXD, nk, 64, kXD, true))
+    if (!make_map_2d(&p.map_q[j], qp[j], a.batch * D, nq, 64, D, true) ||
+        !make_map_2d(&p.map_do[j], dop[j], a.batch * VD, nq, 64, VD, true) ||
+        !make_map_2d(&p.map_k[j], kp[j], a.batch * D, nk, 64, D, true) ||
+        !make_map_2d(&p.map_v[j], vp[j], a.batch * VD, nk, 64, VD, true))
       return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.lse2 = lse2;
@@ -664,42 +693,51 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   p.nq = nq;
   p.nk = nk;
   p.batch = int32_t(a.batch);
-  p.scale = 1.f / sqrtf(float(kXD));
+  p.scale = 1.f / sqrtf(float(D));
   p.scale_log2 = p.scale * kXLog2e;
   cudaError_t e;
   {
-    const struct { const void* src; __nv_bfloat16** dst; int64_t n; } jobs[4] = {
-        {a.q, qp, a.batch * int64_t(kXD) * nq}, {a.d_o, dop, a.batch * int64_t(kXD) * nq},
-        {a.k, kp, a.batch * int64_t(kXD) * nk}, {a.v, vp, a.batch * int64_t(kXD) * nk}};
-    for (const auto& jb : jobs) {
-      const int blocks = int(std::min<int64_t>((jb.n + 255) / 256, 148 * 16));
-      ScopedKernel timed("split_bf16x3", stream);
-      split_bf16x3_kernel<<<blocks, 256, 0, stream>>>((const float*)jb.src, jb.dst[0], jb.dst[1], jb.dst[2], jb.n);
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    SplitJobs jobs;
+    const float* src[4] = {(const float*)a.q, (const float*)a.d_o, (const float*)a.k, (const float*)a.v};
+    __nv_bfloat16** dst[4] = {qp, dop, kp, vp};
+    const int64_t n[4] = {a.batch * int64_t(D) * nq, a.batch * int64_t(VD) * nq, a.batch * int64_t(D) * nk,
+                          a.batch * int64_t(VD) * nk};
+    int64_t nmax = 0;
+    for (int t = 0; t < 4; ++t) {
+      jobs.src[t] = src[t];
+      jobs.n[t] = n[t];
+      for (int j = 0; j < 3; ++j) jobs.dst[t][j] = dst[t][j];
+      nmax = std::max(nmax, n[t]);
     }
+    const int blocks = int(std::min<int64_t>((nmax + 255) / 256, 148 * 8));
+    ScopedKernel timed("split_bf16x3", stream);
+    split_bf16x3_all<<<dim3(blocks, 4), 256, 0, stream>>>(jobs);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
     const int64_t total = a.batch * int64_t(nq);
     const int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 16));
     ScopedKernel timed("bwd_prep_f32", stream);
     bwd_prep_f32<<<blocks, 256, 0, stream>>>((const float*)a.o, (const float*)a.d_o, (const float*)a.l,
-                                             (const float*)a.m, lse2, dsum, lse2_refined, a.batch, kXD, nq);
+                                             (const float*)a.m, lse2, dsum, lse2_refined, a.batch, VD, nq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    e = cudaFuncSetAttribute(bwd_dq_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg::kSmemBytes);
+    auto kern = bwd_dq_f32_kernel<D, VD>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nq + kXM - 1) / kXM;
     ScopedKernel timed("bwd_dq_f32_bf16x3_sm100", stream);
-    bwd_dq_f32_kernel<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, XCfg::kSmemBytes, stream>>>(p);
+    kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, Cfg::kSmemBytes, stream>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    e = cudaFuncSetAttribute(bwd_dkdv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg::kSmemBytes);
+    auto kern = bwd_dkdv_f32_kernel<D, VD>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nk + kXM - 1) / kXM;
     ScopedKernel timed("bwd_dkdv_f32_bf16x3_sm100", stream);
-    bwd_dkdv_f32_kernel<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, XCfg::kSmemBytes, stream>>>(p);
+    kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kXThreads, Cfg::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
   }
 }
@@ -708,22 +746,30 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
 
 static bool aligned16x(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static bool f32_bwd_shape(const LaunchArgs& a) {
+  return (a.d == 64 && a.v_d == 64) || (a.d == 32 && a.v_d == 32) || (a.d == 32 && a.v_d == 16);
+}
+
 size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a) {
-  return sm100::f32_bwd_layout(a.batch, a.rule.q.total, a.rule.k.total).total;
+  return sm100::f32_bwd_layout(a.batch, a.rule.q.total, a.rule.k.total, a.d, a.v_d).total;
 }
 
 bool sm100_f32_backward_supports(const LaunchArgs& a) {
   if (a.dtype != 1 || a.accumulate) return false;
-  if (a.d != sm100::kXD || a.v_d != sm100::kXD) return false;
+  if (!f32_bwd_shape(a)) return false;   // the head dims of BASELINE configs C4 (64/64) and C1 (32/16), and 32/32
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   if (nq % 8 || nk % 8) return false;   // TMA row pitch of the bf16 pieces
   if (a.workspace && !aligned16x(a.workspace)) return false;
-  if (a.batch * sm100::kXD > 0x7fffffffLL) return false;
+  if (a.batch * 64 > 0x7fffffffLL) return false;
   if (((nq + 127) / 128) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
   if (a.workspace_bytes < sm100_f32_backward_workspace_bytes(a)) return false;
   return true;
 }
 
-cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream) { return sm100::launch_bwd_f32(a, stream); }
+cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream) {
+  if (a.d == 64) return sm100::launch_bwd_f32<64, 64>(a, stream);
+  if (a.v_d == 32) return sm100::launch_bwd_f32<32, 32>(a, stream);
+  return sm100::launch_bwd_f32<32, 16>(a, stream);
+}
 
 }  // namespace fa
