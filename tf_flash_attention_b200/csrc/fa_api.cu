@@ -71,6 +71,8 @@ int fill_args(const fa_problem_t* p, fa::LaunchArgs* a) {
   a->v_d = p->v_d;
   a->batch = p->batch;
   a->accumulate = p->accumulate;
+  // a key shard of a longer sequence (K/V ring): rows do not see all of their keys in this call
+  a->partial_keys = (p->k_index_base != 0 || (p->k_full_len != 0 && p->k_full_len != a->rule.k.total)) ? 1 : 0;
   return 0;
 }
 

@@ -57,6 +57,7 @@ struct alignas(64) BwdF32Params {
   float* lse2_refined;  // written by the dQ kernel, read by the dK/dV kernel (see bwd_dq_f32_kernel)
   float *d_q, *d_k, *d_v;
   int32_t nq, nk, n_blocks, batch;
+  int32_t renormalise;   // 0 when the call sees only a shard of the keys (ring): sum_k P != 1 by construction there
   float scale, scale_log2;
 };
 
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
     // The forward's l, m come from a 3xTF32 S (about 2^-21 relative), this kernel's S from three bf16 pieces (2^-24):
     // P = exp2(S c - LSE2) then misses sum_k P = 1 by a common factor per row of a few 1e-6, which is the whole error
     // budget of the gradients. The row sum of P is free here (one thread owns the row over all key tiles), so the row
-    // is renormalised: dQ is divided by it and LSE2 + log2(rowsum) is handed to the dK/dV kernel.
+    // is renormalised: dQ is divided by it and LSE2 + log2(rowsum) is handed to the dK/dV kernel. (Not when the call
+    // covers a shard of the keys only - K/V ring - where the row sum over the shard is not 1 by construction.)
     float row_sum = 0.f;
     int j = 0;
     TileIter it;
@@ -342,9 +344,10 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
     }
     // epilogue: dQ = scale * acc, fp32, straight to global (lanes = consecutive queries -> coalesced per channel)
     float* out = p.d_q + int64_t(b) * D * p.nq + qi;
-    const float out_scale = row_sum > 0.f ? p.scale / row_sum : 0.f;
+    const float out_scale = !p.renormalise ? p.scale : (row_sum > 0.f ? p.scale / row_sum : 0.f);
     if (q_valid)
-      p.lse2_refined[int64_t(b) * p.nq + qi] = row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000);
+      p.lse2_refined[int64_t(b) * p.nq + qi] =
+          !p.renormalise ? lse2 : (row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000));
     if (j > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -693,6 +696,7 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   p.nq = nq;
   p.nk = nk;
   p.batch = int32_t(a.batch);
+  p.renormalise = a.partial_keys ? 0 : 1;
   p.scale = 1.f / sqrtf(float(D));
   p.scale_log2 = p.scale * kXLog2e;
   cudaError_t e;

@@ -23,6 +23,7 @@ struct LaunchArgs {
   void *d_q, *d_k, *d_v;
   void* workspace;
   size_t workspace_bytes;
+  int32_t partial_keys;  // the call covers a shard of the keys only (ring): no per-row renormalisation in the backward
   int32_t variant;  // fa_set_path_override value (0 auto; 4 = fp16 backward as two kernels; 5 / 6 = forward tile configuration)
 };
 
