@@ -223,6 +223,34 @@ def test_head_dim64_one_cta_per_sm_variants_match_oracle(case, override):
         _capi.lib.fa_set_path_override(0)
 
 
+TINY_CASES = [
+    (1, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (8,), (8,)),      # a single, mostly empty tile per CTA
+    (1, "full", "scale_end", 1, 0, 0, (3,), 128, 128, (8,), (24,)),
+    (1, "local", "none_front", 2, 0, 1, (1,), 128, 64, (16,), (16,)),
+    (2, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (2, 4), (2, 4)),
+]
+
+
+@pytest.mark.parametrize("case", TINY_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_tiny_sequences_on_the_tcgen05_paths(case):
+    """Sequences far shorter than a tile (TMA boxes reach past the tensor: zero fill on loads, clipping on stores)."""
+    _run(*case, seed=1)
+
+
+def test_tiny_sequences_fp32_split_paths():
+    rng = np.random.default_rng(2)
+    Q, K, V, dO = da.random_inputs(rng, np.float32, (2,), 64, 64, (8,), (16,))
+    ref = da.attention(Q, K, V, 1, "causal", "scale_end", dO=dO)
+    tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+    O = fa.causal_1d(tq, tk, tv, "scale_end")
+    assert _capi.lib.fa_last_path() == 3
+    dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+    assert _capi.lib.fa_last_path() == 3
+    assert max_abs_err(O.detach().cpu().numpy(), ref["O"]) <= 1e-5
+    for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert scaled_err(g.cpu().numpy(), ref[name]) <= 1e-5, name
+
+
 F32_CASES = [
     (1, "full", "none_front", 1, 0, 0, (2,), 64, 64, (256,), (320,)),
     (1, "causal", "none_front", 1, 0, 0, (2,), 64, 64, (512,), (512,)),
