@@ -215,3 +215,37 @@ def test_closed_form_tile_masks_match_reference(tile, resident_is_q):
         p = _capi.make_problem(0, dims, rule, mode, (1, 4) + qs, (1, 4) + ks, (1, 4) + ks, w, 0, cz)
         assert np.array_equal(_capi.pattern_mask_fast(p, tile, resident_is_q),
                               pattern.tests_mask(qs, ks, mode, rule, w, 0, cz)), (dims, qs, ks, rule, mode, w, cz)
+
+
+def test_workspace_sizes_follow_the_dispatch_rules():
+    """fa_workspace_bytes is host-only. What the op author must allocate:
+    fp16 head_dim 128 backward = statistics + fp32 dQ scratch (fused kernel); with override 4 (two-kernel backward) and for
+    head_dim 64 = statistics only; fp32 forward = hi/lo TF32 copies when the tcgen05 forward takes the shape; fp32 backward
+    = three bf16 pieces of Q, K, V, dO for the supported head dims; everything else = the generic kernels' statistics."""
+    import ctypes as C
+
+    def ws(dtype, d, vd, nq, nk, bwd, batch=(2, 3)):
+        p = _capi.make_problem(dtype, 1, "causal", "none_front", batch + (d, nq), batch + (d, nk), batch + (vd, nk))
+        return int(_capi.lib.fa_workspace_bytes(C.byref(p), bwd))
+    B = 6
+    stats16 = lambda nq: (2 * (B * nq + 64) * 4 + 255) // 256 * 256  # noqa: E731
+    try:
+        assert ws(_capi.FA_F16, 128, 128, 512, 512, 0) == 0
+        fused = ws(_capi.FA_F16, 128, 128, 512, 384, 1)
+        assert fused >= stats16(512) + B * 128 * 512 * 4                      # + fp32 dQ scratch
+        assert ws(_capi.FA_F16, 64, 64, 512, 384, 1) < B * 64 * 512 * 4       # head_dim 64: statistics only
+        _capi.lib.fa_set_path_override(4)
+        assert ws(_capi.FA_F16, 128, 128, 512, 384, 1) < B * 128 * 512 * 4    # two-kernel backward: no scratch
+        _capi.lib.fa_set_path_override(0)
+        assert ws(_capi.FA_F32, 64, 64, 512, 384, 0) >= 2 * 4 * B * 64 * (512 + 2 * 384)   # hi + lo of Q, K, V
+        assert ws(_capi.FA_F32, 48, 48, 512, 384, 0) == 0                     # shape not taken by the 3xTF32 forward
+        pieces = 3 * 2 * B * (64 * 512 * 2 + 64 * 384 * 2)                    # 3 bf16 pieces of Q, dO, K, V
+        assert ws(_capi.FA_F32, 64, 64, 512, 384, 1) >= pieces
+        assert ws(_capi.FA_F32, 32, 16, 512, 384, 1) >= 3 * 2 * B * (32 * 512 + 16 * 512 + 32 * 384 + 16 * 384)
+        assert ws(_capi.FA_F32, 48, 48, 512, 384, 1) == 2 * B * 512 * 4       # generic: LSE + D
+        assert ws(_capi.FA_F64, 64, 64, 512, 384, 1) == 2 * B * 512 * 8
+        _capi.lib.fa_set_path_override(1)                                     # generic family only
+        assert ws(_capi.FA_F32, 64, 64, 512, 384, 1) == 2 * B * 512 * 4
+        assert ws(_capi.FA_F32, 64, 64, 512, 384, 0) == 0
+    finally:
+        _capi.lib.fa_set_path_override(0)
