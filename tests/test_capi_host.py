@@ -249,3 +249,17 @@ def test_workspace_sizes_follow_the_dispatch_rules():
         assert ws(_capi.FA_F32, 64, 64, 512, 384, 0) == 0
     finally:
         _capi.lib.fa_set_path_override(0)
+
+
+def test_tensor_core_paths_decline_sequences_beyond_the_tile_schedule():
+    """The per-CTA tile schedule covers 2048 streamed 64-wide tiles (131072 positions); longer sequences must fall back to
+    the generic kernels instead of overrunning it. Observable on the host through the fp32 workspace sizes."""
+    import ctypes as C
+
+    def ws(nq, nk, bwd):
+        p = _capi.make_problem(_capi.FA_F32, 1, "causal", "none_front", (1, 64, nq), (1, 64, nk), (1, 64, nk))
+        return int(_capi.lib.fa_workspace_bytes(C.byref(p), bwd))
+    assert ws(1024, 131072, 0) > 0 and ws(1024, 131072 + 64, 0) == 0
+    assert ws(1024, 131072, 1) > 2 * 1024 * 4 * 10
+    assert ws(1024, 131072 + 64, 1) == 2 * 1024 * 4          # generic: LSE + D only
+    assert ws(131072 + 64, 1024, 1) == 2 * (131072 + 64) * 4

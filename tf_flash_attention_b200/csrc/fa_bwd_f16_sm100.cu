@@ -1817,6 +1817,9 @@ bool sm100_f16_backward_supports(const LaunchArgs& a) {
   if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
   if (((nq + 255) / 256) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
   if (a.workspace_bytes < sm100::bwd_workspace_bytes(a.batch, nq, a.d, a.variant)) return false;
+  // the per-CTA tile schedules hold 32 * kMaxTileWords streamed 64-wide tiles (keys in the dQ kernels, queries in the
+  // dK/dV and fused kernels)
+  if ((nk + 63) / 64 > 32 * sm100::kMaxTileWords || (nq + 63) / 64 > 32 * sm100::kMaxTileWords) return false;
   return true;
 }
 

@@ -767,6 +767,7 @@ bool sm100_f32_backward_supports(const LaunchArgs& a) {
   if (a.batch * 64 > 0x7fffffffLL) return false;
   if (((nq + 127) / 128) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
   if (a.workspace_bytes < sm100_f32_backward_workspace_bytes(a)) return false;
+  if ((nk + 63) / 64 > 32 * sm100::kMaxTileWords || (nq + 63) / 64 > 32 * sm100::kMaxTileWords) return false;
   return true;
 }
 

@@ -475,6 +475,9 @@ bool sm100_f16_forward_supports(const LaunchArgs& a) {
   if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
   const int64_t pairs = (nq + 255) / 256;
   if (pairs * a.batch > 0x7fffffffLL) return false;
+  // the per-CTA tile schedule holds 32 * kMaxTileWords streamed tiles (64-key tiles for head_dim 64, else 128-key)
+  const int64_t tile = (a.d == 64 && a.v_d == 64 && a.variant != 5) ? 64 : 128;
+  if ((nk + tile - 1) / tile > 32 * sm100::kMaxTileWords) return false;
   return true;
 }
 
