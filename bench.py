@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the headline benchmark of BASELINE.json on B200.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C1|C3|C4]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C1|C3|C4|C4f32|C4f64|C5|S1|S2|T1]
 
 Workload (config.workload): BASELINE.json configs[1] — causal_1d fp16 forward + backward,
 batch x heads = 16 x 16, head_dim 128, seq 8192 (GPT-style self-attention), inputs U(-2,2) already
@@ -60,6 +60,10 @@ WORKLOADS = {
     "C5": dict(desc="causal_1d fp16 single sequence 131072, head_dim 128, 16 heads, K/V ring over NCCL (fwd)",
                seq_dims=1, dtype="float16", batch=(1, 16), d=128, v_d=128, q=(131072,), k=(131072,), rule="causal",
                sync="none_front", w=1, s=0, c=0, ring=True),
+    # the step either side of the op: channel-last activations <-> the op's channel-first layout
+    "T1": dict(desc="layout adapter fp16: [16, 8192, 16, 128] channel-last -> channel-first -> channel-last (HBM-bound)",
+               seq_dims=1, dtype="float16", batch=(16, 16), d=128, v_d=128, q=(8192,), k=(8192,), rule="full",
+               sync="none_front", w=1, s=0, c=0, layout=True),
 }
 
 
@@ -229,6 +233,71 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def layout_bench(args, w, rank, world, local_rank):
+    """T1: fa_layout_transpose both ways over one activation tensor larger than L2; bytes = one read + one write per
+    launch. Every rank converts its own tensor (no communication)."""
+    import torch
+    import torch.distributed as dist
+    from tf_flash_attention_b200 import _capi
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, Cc, S = w["batch"][0], w["batch"][1], w["d"], w["q"][0]
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+    x = (torch.rand((B, S, H, Cc), generator=g, device=dev) * 4 - 2).half()
+    y = torch.empty((B, H, Cc, S), dtype=x.dtype, device=dev)
+    x2 = torch.empty_like(x)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    if args.override:
+        _capi.lib.fa_set_path_override(args.override)
+
+    def step():
+        _capi.check(_capi.lib.fa_layout_transpose(0, x.data_ptr(), y.data_ptr(), B, S, H, Cc, 1, sp), "fa_layout_transpose")
+        _capi.check(_capi.lib.fa_layout_transpose(0, y.data_ptr(), x2.data_ptr(), B, S, H, Cc, 0, sp), "fa_layout_transpose")
+    sampler = ClockSampler(local_rank)
+    sampler.launch()
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    assert torch.equal(x, x2) and torch.equal(y, x.permute(0, 2, 3, 1)), "layout adapter round trip differs"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    _capi.lib.fa_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = int(_capi.lib.fa_launch_count(0))
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    nbytes = x.numel() * x.element_size()
+    gbs = 2 * (2 * nbytes) / (ms * 1e-3) / 1e9           # two launches per step, each one read + one write
+    peaks = measured_peaks()
+    line = {"metric": "layout adapter GB/s (algorithmic bytes: one read + one write per launch)", "value": gbs * world,
+            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (byte moves)",
+            "data": "synthetic U(-2,2)", "config": {"workload": f"T1: {w['desc']}", "bytes_per_launch": 2 * nbytes,
+                                                    "l2": "tensor (537 MB) larger than the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "layout_transpose", "achieved": gbs, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+                         "peak_source": peaks["source"]}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -283,6 +352,8 @@ def main():
 
     if w.get("ring"):
         return ring_bench(args, w, nnz, config, rank, world, local_rank)
+    if w.get("layout"):
+        return layout_bench(args, w, rank, world, local_rank)
 
     # ---------------- our arm -------------------------------------------------------------------
     import torch

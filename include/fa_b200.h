@@ -138,6 +138,12 @@ int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_
 int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream);
 int fa_grad_finalize(int32_t dtype, const void* acc, void* out, int64_t n, void* stream);
 
+/* Layout adapter for the step either side of the op (the reference's README wraps it in einsums that build the
+ * channel-first layout): to_channel_first != 0: x [batch, seq, heads, channels] -> y [batch, heads, channels, seq];
+ * otherwise the inverse. Same dtype codes as fa_problem_t. HBM-bound transpose, asynchronous on `stream`.       */
+int fa_layout_transpose(int32_t dtype, const void* x, void* y, int64_t batch, int64_t seq, int32_t heads,
+                        int32_t channels, int to_channel_first, void* stream);
+
 /* ---- host-side helpers shared with the kernels (same code, fa_rules.h) ---------- */
 
 /* Number of attended (q,k) pairs per batch element under the bit-exact rule; the unit

@@ -155,6 +155,52 @@ def test_python_api_surface_matches_reference():
     assert inspect.signature(fa.causal_1d).parameters["sync_mode"].default is inspect.Parameter.empty
 
 
+def test_layout_adapter_argument_checks():
+    """fa_layout_transpose validates before touching the device: dtype code, negative sizes, null pointers; empty
+    tensors are a no-op."""
+    f = _capi.lib.fa_layout_transpose
+    assert f(7, None, None, 1, 1, 1, 1, 1, None) == _capi.FA_EINVAL_DTYPE
+    assert f(0, None, None, -1, 1, 1, 1, 1, None) == _capi.FA_EINVAL_SHAPE
+    assert f(0, None, None, 1, 1, 1, 1, 1, None) == _capi.FA_EINVAL_NULL
+    assert f(1, None, None, 4, 0, 2, 8, 0, None) == _capi.FA_OK
+    with pytest.raises(_capi.InvalidArgumentError):
+        fa.from_channel_last(np.zeros((1, 2, 3, 4), dtype=np.float32))   # host arrays: no CPU fallback
+
+
+def test_layout_fast_path_mapping():
+    """Host emulation of the thread mapping of layout_transpose_f16_kernel (fa_layout.cu): every 8-byte unit of the
+    64 x 64 tile is written once, read once by the thread that stores it to the transposed position, and neither the unit
+    stores nor the unit loads of any half-warp collide on a shared-memory bank (16 banks of 8 bytes)."""
+    smem = {}
+    for tid in range(256):
+        kq, rq = tid % 16, tid // 16
+        for c in range(4):
+            addr = (4 * kq + c) * 16 + (rq ^ kq)
+            assert addr not in smem
+            smem[addr] = (4 * kq + c, rq)            # destination row, group of 4 source rows
+    assert len(smem) == 1024
+    for w in range(8):
+        for c in range(4):
+            for hw in range(2):
+                lanes = [w * 32 + hw * 16 + i for i in range(16)]
+                assert len({((4 * (t % 16) + c) * 16 + ((t // 16) ^ (t % 16))) % 16 for t in lanes}) == 16
+    seen = set()
+    for w in range(8):
+        for i in range(2):
+            for hw in range(2):
+                for which in range(2):
+                    banks = set()
+                    for lane in range(hw * 16, hw * 16 + 16):
+                        u, rsel = lane % 8, lane // 8
+                        rho = 16 * (w >> 1) + 4 * rsel + 2 * (w & 1) + i
+                        addr = rho * 16 + ((2 * u + which) ^ (rho >> 2))
+                        assert smem[addr] == (rho, 2 * u + which)
+                        banks.add(addr % 16)
+                        seen.add((rho, 2 * u + which))
+                    assert len(banks) == 16
+    assert len(seen) == 1024
+
+
 def test_no_cpu_fallback():
     """numpy (host) inputs must fail loudly when no CUDA device is present."""
     try:

@@ -309,3 +309,29 @@ def test_kernels_write_only_inside_their_outputs(dtype, d, vd, nq, nk, rule):
     for name in ("dQ", "dK", "dV"):
         gtol = tol * (4 if dtype == np.float16 else 10)
         assert scaled_err(g[name].cpu().numpy(), ref[name]) <= gtol, name
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(3, 77, 5, 40), (2, 130, 3, 70), (1, 64, 2, 128), (2, 1, 1, 1), (1, 200, 3, 33),
+                                   (2, 200, 3, 72), (1, 1096, 2, 64), (2, 8, 1, 8), (1, 520, 1, 136)])
+def test_channel_last_adapters_round_trip(dtype, shape):
+    """fa_layout_transpose: [b, s, h, c] <-> [b, h, c, s], ragged against its 32 x 32 (odd sizes) and 64 x 64 (even sizes,
+    two elements per thread) tiles and against the fp16 register-transpose kernel (sizes that are multiples of 8, more than
+    one tile and more than one CTA along the sequence); bit-exact vs torch.permute."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(shape, generator=g, device="cuda", dtype=torch.float32).to(dtype)
+    y = fa.from_channel_last(x)
+    b, s, h, c = shape
+    assert y.shape == (b, h, c, s) and torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(fa.to_channel_last(y), x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_channel_last_activations_through_the_op(dtype):
+    """channel-last activations in, channel-last out: adapters either side of causal_1d."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    q = torch.rand((2, 256, 4, 64), generator=g, device="cuda", dtype=torch.float32).to(dtype) * 4 - 2
+    O = fa.to_channel_last(fa.causal_1d(fa.from_channel_last(q), fa.from_channel_last(q), fa.from_channel_last(q), "none_front"))
+    qcf = q.permute(0, 2, 3, 1).contiguous()
+    ref = fa.causal_1d(qcf, qcf, qcf, "none_front").permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(O, ref)

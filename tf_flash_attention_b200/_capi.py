@@ -15,6 +15,10 @@ RULES = {"full": 0, "causal": 1, "local": 2}
 SYNC_MODES = {"none_front": 0, "scale_front": 1, "scale_end": 2}
 
 FA_OK = 0
+FA_EINVAL_NULL = -1
+FA_EINVAL_DTYPE = -2
+FA_EINVAL_SEQ_DIMS = -3
+FA_EINVAL_RULE = -4
 FA_EINVAL_SYNC_MODE = -5
 FA_EINVAL_WINDOW = -6
 FA_EINVAL_STRIDE = -7
@@ -25,6 +29,7 @@ FA_EINVAL_CHANNEL = -11
 FA_EINVAL_BATCH = -12
 FA_EINVAL_SEQ_SHAPE = -13
 FA_ECUDA = -100
+FA_ENODEVICE = -101
 
 PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_f32_split", 4: "reserved"}
 
@@ -85,6 +90,7 @@ def _load():
         "fa_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_partial_merge": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
         "fa_partial_finalize": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp]),
+        "fa_layout_transpose": (C.c_int, [C.c_int32, vp, vp, i64, i64, C.c_int32, C.c_int32, C.c_int, vp]),
         "fa_grad_accumulate": (C.c_int, [C.c_int32, vp, vp, i64, C.c_int, vp]),
         "fa_grad_finalize": (C.c_int, [C.c_int32, vp, vp, i64, vp]),
         "fa_strerror": (C.c_char_p, [C.c_int]),

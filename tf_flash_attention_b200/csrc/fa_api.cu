@@ -213,6 +213,18 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   return e == cudaSuccess ? FA_OK : cuda_fail(e);
 }
 
+// ---- layout adapter ------------------------------------------------------------------------------
+int fa_layout_transpose(int32_t dtype, const void* x, void* y, int64_t batch, int64_t seq, int32_t heads,
+                        int32_t channels, int to_channel_first, void* stream) {
+  if (dtype < FA_F16 || dtype > FA_F64) return FA_EINVAL_DTYPE;
+  if (batch < 0 || seq < 0 || heads < 0 || channels < 0) return FA_EINVAL_SHAPE;
+  if (batch * heads > 0x7fffffffLL || (seq + 31) / 32 > 65535 || (channels + 31) / 32 > 65535) return FA_EINVAL_SHAPE;
+  if (batch * seq * heads * channels == 0) return FA_OK;
+  if (!x || !y) return FA_EINVAL_NULL;
+  cudaError_t e = fa::layout_transpose(dtype, x, y, batch, seq, heads, channels, to_channel_first, fa::g_path_override, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
 // ---- gradient shards (ring backward) ---------------------------------------------------------
 int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream) {
   if (dtype < FA_F16 || dtype > FA_F64) return FA_EINVAL_DTYPE;

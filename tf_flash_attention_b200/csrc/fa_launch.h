@@ -54,6 +54,10 @@ cudaError_t partial_finalize(const LaunchArgs& a, const void* o_acc, const void*
 cudaError_t grad_accumulate(int dtype, const void* part, void* acc, int64_t n, int first, cudaStream_t stream);
 cudaError_t grad_finalize(int dtype, const void* acc, void* out, int64_t n, cudaStream_t stream);
 
+// channel-last <-> channel-first adapter (fa_layout.cu)
+cudaError_t layout_transpose(int dtype, const void* x, void* y, int64_t B, int64_t S, int32_t H, int32_t C,
+                             int to_channel_first, int variant, cudaStream_t stream);
+
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);
 bool sm100_f16_backward_supports(const LaunchArgs& a);

@@ -255,3 +255,36 @@ def estimate_forward_flops(seq_dims, rule, q_shape, k_shape, v_shape, dtype, syn
     p = _capi.make_problem(code, seq_dims, rule, sync_mode, tuple(q_shape), tuple(k_shape), tuple(v_shape),
                            window_size, log2_stride_size, is_causal)
     return _capi.estimate_forward_flops(p, shared_mem_bytes)
+
+
+# ---- layout adapters (SURVEY.md section 8 f3: the step either side of the op) -----------------------------------
+def from_channel_last(x):
+    """[batch, seq, heads, channels] (torch CUDA tensor) -> the op's channel-first [batch, heads, channels, seq]."""
+    return _layout(x, True)
+
+
+def to_channel_last(x):
+    """The op's channel-first [batch, heads, channels, seq] -> [batch, seq, heads, channels]."""
+    return _layout(x, False)
+
+
+def _layout(x, to_channel_first):
+    import torch
+    if not _is_torch(x) or not x.is_cuda:
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_NULL, "layout adapters take torch CUDA tensors (no CPU fallback)")
+    if x.dim() != 4:
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_RANK, "expected a rank-4 tensor")
+    codes = {torch.float16: _capi.FA_F16, torch.float32: _capi.FA_F32, torch.float64: _capi.FA_F64}
+    if x.dtype not in codes:
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_DTYPE, f"unsupported dtype {x.dtype}")
+    x = x.contiguous()
+    if to_channel_first:
+        b, s, h, c = x.shape
+        y = torch.empty((b, h, c, s), dtype=x.dtype, device=x.device)
+    else:
+        b, h, c, s = x.shape
+        y = torch.empty((b, s, h, c), dtype=x.dtype, device=x.device)
+    _capi.check(_capi.lib.fa_layout_transpose(codes[x.dtype], x.data_ptr(), y.data_ptr(), b, s, h, c,
+                                              int(to_channel_first), torch.cuda.current_stream(x.device).cuda_stream),
+                "fa_layout_transpose")
+    return y
