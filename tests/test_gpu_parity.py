@@ -326,6 +326,45 @@ def test_channel_last_adapters_round_trip(dtype, shape):
     assert torch.equal(fa.to_channel_last(y), x)
 
 
+@pytest.mark.parametrize("variant", [7, 8, 9])
+@pytest.mark.parametrize("shape", [(2, 200, 3, 72), (1, 1096, 2, 64), (1, 130, 3, 70), (2, 260, 1, 132)])
+def test_channel_last_adapter_kernel_variants(variant, shape):
+    """Every kernel variant of the fp16 adapter that `fa_set_path_override` can select (element-wise pairs / singles /
+    quads) gives the same bytes as the default."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand(shape, generator=g, device="cuda", dtype=torch.float32).half()
+    _capi.lib.fa_set_path_override(variant)
+    try:
+        y = fa.from_channel_last(x)
+        back = fa.to_channel_last(y)
+    finally:
+        _capi.lib.fa_set_path_override(0)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous()) and torch.equal(back, x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+@pytest.mark.parametrize("shape,offset", [((2, 200, 3, 72), 64), ((1, 72, 2, 136), 64), ((2, 130, 3, 70), 64),
+                                          ((1, 77, 5, 40), 1), ((2, 200, 3, 72), 3)])
+def test_channel_last_adapter_writes_only_inside_its_output(dtype, shape, offset):
+    """Guard bands either side of the destination stay untouched (ragged tiles, aligned and unaligned bases: the
+    unaligned ones take the one-element-per-thread kernel), both directions, straight through the C ABI."""
+    b, s, h, c = shape
+    n = b * s * h * c
+    code = {torch.float16: _capi.FA_F16, torch.float32: _capi.FA_F32, torch.float64: _capi.FA_F64}[dtype]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(shape, generator=g, device="cuda", dtype=torch.float32).to(dtype)
+    stream = torch.cuda.current_stream().cuda_stream
+    for to_cf, src, ref in ((1, x, x.permute(0, 2, 3, 1).contiguous()),
+                            (0, x.permute(0, 2, 3, 1).contiguous(), x)):
+        buf = torch.full((n + 2 * 256,), -7.0, device="cuda", dtype=dtype)
+        dst = buf[256 - 64 + offset: 256 - 64 + offset + n]
+        _capi.check(_capi.lib.fa_layout_transpose(code, src.data_ptr(), dst.data_ptr(), b, s, h, c, to_cf, stream))
+        torch.cuda.synchronize()
+        assert torch.equal(dst.view(ref.shape), ref)
+        lo = 256 - 64 + offset
+        assert bool((buf[:lo] == -7.0).all()) and bool((buf[lo + n:] == -7.0).all())
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
 def test_channel_last_activations_through_the_op(dtype):
     """channel-last activations in, channel-last out: adapters either side of causal_1d."""
