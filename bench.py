@@ -69,7 +69,8 @@ WORKLOADS = {
 
 # DRAM bytes per launch measured with `ncu --set full` on the GPU (profiles/r1_*_ncu*.md); bench.py cannot
 # run under a profiler, so the captured values are carried here for the workload they were taken on.
-NCU_TRAFFIC = {("C2", "fwd"): 2.153e9, ("C2", "bwd"): 5.35e9}  # bwd: the fused dQ/dK/dV kernel alone
+NCU_TRAFFIC = {("C2", "fwd"): 2.153e9, ("C2", "bwd"): 5.35e9,  # bwd: the fused dQ/dK/dV kernel alone
+               ("T1", "layout"): 1.027e9}                     # profiles/r1_layout_ncu.md
 
 
 def measured_peaks():
@@ -290,7 +291,10 @@ def layout_bench(args, w, rank, world, local_rank):
                                                     "l2": "tensor (537 MB) larger than the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "layout_transpose", "achieved": gbs, "peak": peaks["hbm"],
-                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": NCU_TRAFFIC[("T1", "layout")],
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full "
+                                           "(profiles/r1_layout_ncu.md)",
+                         "algorithmic": f"{2 * nbytes} bytes per launch (the tensor read once and written once)",
                          "peak_source": peaks["source"]}}
     if rank == 0:
         print(json.dumps(line), flush=True)
