@@ -564,38 +564,61 @@ def main():
         nb_b = _capi.lib.fa_host_arena_bytes(C.byref(prob), 1)
         arena = torch.empty(max(nb_f, nb_b), dtype=torch.uint8, device=dev)
 
-        def e2e_step():
+        def fwd_host():
             _capi.check(_capi.lib.fa_forward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
                                                   ho.data_ptr(), hl.data_ptr(), hm.data_ptr(), arena.data_ptr(),
                                                   arena.numel(), sp), "fa_forward_host")
+
+        def e2e_step():
+            # one training step as the reference's host framework runs it: forward op, then its registered gradient
+            # with the forward's tensors still on the device (only dO is uploaded for the backward)
+            fwd_host()
+            if not args.fwd_only:
+                _capi.check(_capi.lib.fa_backward_host_resident(C.byref(prob), hdo.data_ptr(), hdq.data_ptr(),
+                                                                hdk.data_ptr(), hdv.data_ptr(), arena.data_ptr(),
+                                                                arena.numel(), sp), "fa_backward_host_resident")
+
+        def e2e_step_stateless():
+            # the same step with nothing kept on the device between the two calls (every backward input re-uploaded)
+            fwd_host()
             if not args.fwd_only:
                 _capi.check(_capi.lib.fa_backward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
                                                        ho.data_ptr(), hl.data_ptr(), hm.data_ptr(), hdo.data_ptr(),
                                                        hdq.data_ptr(), hdk.data_ptr(), hdv.data_ptr(),
                                                        arena.data_ptr(), arena.numel(), sp), "fa_backward_host")
 
-        e2e_step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        sec = (time.perf_counter() - t0) / args.e2e_steps
-        t = torch.tensor([sec], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
+        def time_e2e(fn):
+            fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                fn()
+            torch.cuda.synchronize()
+            sec = (time.perf_counter() - t0) / args.e2e_steps
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
         nb = lambda x: x.numel() * x.element_size()  # noqa: E731
+        sec = time_e2e(e2e_step)
         h2d = nb(hq) + nb(hk) + nb(hv)
         d2h = nb(ho) + nb(hl) + nb(hm)
         if not args.fwd_only:
-            h2d += nb(hq) + nb(hk) + nb(hv) + nb(ho) + nb(hl) + nb(hm) + nb(hdo)
+            h2d += nb(hdo)
             d2h += nb(hdq) + nb(hdk) + nb(hdv)
         line["e2e"] = {"value": step_flops * world / sec / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
-                       "api": "fa_forward_host + fa_backward_host (C ABI, pinned host buffers, copies inside the call)"}
+                       "api": "fa_forward_host + fa_backward_host_resident (C ABI, pinned host buffers, copies inside "
+                              "the calls; Q, K, V, O, l, m stay on the device between the forward and its gradient)"}
+        if not args.fwd_only:
+            sec2 = time_e2e(e2e_step_stateless)
+            line["e2e_stateless"] = {"value": step_flops * world / sec2 / 1e12, "unit": "TFLOPS",
+                                     "h2d_bytes_per_step": h2d + nb(hq) + nb(hk) + nb(hv) + nb(ho) + nb(hl) + nb(hm),
+                                     "d2h_bytes_per_step": d2h, "ms_per_step": sec2 * 1e3, "steps": args.e2e_steps,
+                                     "api": "fa_forward_host + fa_backward_host (every backward input re-uploaded)"}
         del arena
 
     # ---------------- CPU baseline (rank 0, N = 1) ------------------------------------------------

@@ -193,6 +193,13 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
                      const void* o, const void* l, const void* m, const void* d_o,
                      void* d_q, void* d_k, void* d_v, void* dev_arena, size_t dev_arena_bytes,
                      void* stream);
+/* Backward of the forward that fa_forward_host has just run in the SAME arena. The arena must have been sized with
+ * fa_host_arena_bytes(p, 1) for that forward call too (the forward and backward layouts share the offsets of Q, K, V,
+ * O, l, m) and must not have been written since: those six tensors are taken from the arena and only d_o is uploaded.
+ * This is what the reference's host framework does between the forward op and its registered gradient
+ * (flash_attention.py:374-390: the gradient receives op.inputs / op.outputs, which TensorFlow keeps on the device). */
+int fa_backward_host_resident(const fa_problem_t* p, const void* d_o, void* d_q, void* d_k, void* d_v,
+                              void* dev_arena, size_t dev_arena_bytes, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------- */
 const char* fa_strerror(int status);

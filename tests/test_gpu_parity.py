@@ -177,6 +177,29 @@ def test_host_buffer_entry_points():
         assert scaled_err(g, ref[name]) <= 1e-5, name
 
 
+@pytest.mark.parametrize("dtype,shape", [(np.float32, (2, 2, 16, 24, 100, 150)), (np.float16, (5, 2, 128, 128, 256, 256)),
+                                         (np.float16, (3, 3, 64, 64, 200, 136)), (np.float64, (1, 3, 8, 8, 50, 70))])
+def test_host_training_step_keeps_forward_tensors_resident(dtype, shape):
+    """fa_forward_host + fa_backward_host_resident in one arena (only dO is uploaded for the backward) give the same
+    bytes as the stateless pair fa_forward_host + fa_backward_host, and match the oracle."""
+    b0, b1, d, vd, nq, nk = shape
+    rng = np.random.default_rng(6)
+    Q, K, V, dO = da.random_inputs(rng, dtype, (b0, b1), d, vd, (nq,), (nk,))
+    ref = da.attention(Q, K, V, 1, "causal", "scale_end", dO=dO)
+    O, l, m, dQ, dK, dV = fa.forward_backward_host(1, "causal", Q, K, V, dO, "scale_end")
+    O2, l2, m2 = fa.causal_1d(Q, K, V, "scale_end", returning_l_m=True)
+    assert np.array_equal(O, O2) and np.array_equal(l, l2) and np.array_equal(m, m2)
+    assert max_abs_err(O, ref["O"]) <= TOL[np.dtype(dtype)]
+    g2 = fa.attention_backward(1, "causal", Q, K, V, O2, l2, m2, dO, "scale_end")
+    fused = dtype == np.float16 and d == 128     # the fused fp16 backward sums dQ in a run-dependent order
+    for name, g, h in (("dQ", dQ, g2[0]), ("dK", dK, g2[1]), ("dV", dV, g2[2])):
+        if fused and name == "dQ":
+            assert scaled_err(g, h.astype(np.float64)) <= 2e-3
+        else:
+            assert np.array_equal(g, h), name
+        assert scaled_err(g, ref[name]) <= TOL[np.dtype(dtype)] * (4 if dtype == np.float16 else 10), name
+
+
 def test_readme_example_c1():
     """BASELINE.json configs[0]: local_1d fp32 Q[8,32,1024] K[8,32,2048] V[8,16,2048], window 32,
     stride 0, scale_front (README.md:66-71) -> O [8,16,1024]."""

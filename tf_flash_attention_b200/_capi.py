@@ -88,6 +88,7 @@ def _load():
         "fa_host_arena_bytes": (sz, [PP, C.c_int]),
         "fa_forward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "fa_backward_host_resident": (C.c_int, [PP, vp, vp, vp, vp, vp, sz, vp]),
         "fa_partial_merge": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
         "fa_partial_finalize": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp]),
         "fa_layout_transpose": (C.c_int, [C.c_int32, vp, vp, i64, i64, C.c_int32, C.c_int32, C.c_int, vp]),

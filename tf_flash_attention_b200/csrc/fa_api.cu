@@ -664,14 +664,19 @@ int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const v
   return FA_OK;
 }
 
-int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
-                     const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
-                     void* dev_arena, size_t dev_arena_bytes, void* stream) {
+}  // extern "C" (the shared body of the two backward host entry points follows)
+
+namespace {
+// resident: Q, K, V, O, l, m are already in the arena (left there by fa_forward_host); only dO is uploaded
+int backward_host_impl(const fa_problem_t* p, bool resident, const void* q, const void* k, const void* v,
+                       const void* o, const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
+                       void* dev_arena, size_t dev_arena_bytes, void* stream) {
   Arena a;
   int rc = arena_layout(p, 1, &a);
   if (rc) return rc;
   if (!dev_arena || dev_arena_bytes < a.total) return FA_EINVAL_WORKSPACE;
-  if (!q || !k || !v || !o || !l || !m || !d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
+  if (!resident && (!q || !k || !v || !o || !l || !m)) return FA_EINVAL_NULL;
+  if (!d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
   if (p->batch == 0) return FA_OK;
   char* base = (char*)dev_arena;
   cudaStream_t st = (cudaStream_t)stream;
@@ -684,12 +689,14 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
   const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
   for (int64_t c = 0; c < nch; ++c) {
     const int64_t b0 = B * c / nch, nb = B * (c + 1) / nch - b0;
-    FA_CU(cudaMemcpyAsync(base + a.q + b0 * sq, (const char*)q + b0 * sq, nb * sq, cudaMemcpyHostToDevice, pipe.in));
-    FA_CU(cudaMemcpyAsync(base + a.k + b0 * sk, (const char*)k + b0 * sk, nb * sk, cudaMemcpyHostToDevice, pipe.in));
-    FA_CU(cudaMemcpyAsync(base + a.v + b0 * sv, (const char*)v + b0 * sv, nb * sv, cudaMemcpyHostToDevice, pipe.in));
-    FA_CU(cudaMemcpyAsync(base + a.o + b0 * so, (const char*)o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
-    FA_CU(cudaMemcpyAsync(base + a.l + b0 * sl, (const char*)l + b0 * sl, nb * sl, cudaMemcpyHostToDevice, pipe.in));
-    FA_CU(cudaMemcpyAsync(base + a.m + b0 * sm, (const char*)m + b0 * sm, nb * sm, cudaMemcpyHostToDevice, pipe.in));
+    if (!resident) {
+      FA_CU(cudaMemcpyAsync(base + a.q + b0 * sq, (const char*)q + b0 * sq, nb * sq, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.k + b0 * sk, (const char*)k + b0 * sk, nb * sk, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.v + b0 * sv, (const char*)v + b0 * sv, nb * sv, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.o + b0 * so, (const char*)o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.l + b0 * sl, (const char*)l + b0 * sl, nb * sl, cudaMemcpyHostToDevice, pipe.in));
+      FA_CU(cudaMemcpyAsync(base + a.m + b0 * sm, (const char*)m + b0 * sm, nb * sm, cudaMemcpyHostToDevice, pipe.in));
+    }
     FA_CU(cudaMemcpyAsync(base + a.d_o + b0 * so, (const char*)d_o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
     FA_CU(cudaEventRecord(pipe.ev[2 * c], pipe.in));
     FA_CU(cudaStreamWaitEvent(st, pipe.ev[2 * c], 0));
@@ -708,6 +715,21 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
   FA_CU(cudaStreamSynchronize(pipe.out));
   FA_CU(cudaStreamSynchronize(st));
   return FA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                     const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
+                     void* dev_arena, size_t dev_arena_bytes, void* stream) {
+  return backward_host_impl(p, false, q, k, v, o, l, m, d_o, d_q, d_k, d_v, dev_arena, dev_arena_bytes, stream);
+}
+
+int fa_backward_host_resident(const fa_problem_t* p, const void* d_o, void* d_q, void* d_k, void* d_v,
+                              void* dev_arena, size_t dev_arena_bytes, void* stream) {
+  return backward_host_impl(p, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, d_o, d_q, d_k, d_v,
+                            dev_arena, dev_arena_bytes, stream);
 }
 
 }  // extern "C"
