@@ -129,14 +129,15 @@ class Case:
             shape[-1] = shape[-1] // 2 * 2
         return shape
 
-    def data(self, dtype, how, gen, device):
+    def data(self, dtype, how, gens, device):
+        shape_gen, gen = gens      # shapes are drawn on the host, data on the device
         lo, hi = self.shape_table[dtype]
         sd = self.seq_dims
         if how == "max":
             q_shape = k_shape = list(hi)
         else:
-            k_shape = self._random_shape(gen, lo, hi, dtype == torch.float16)
-            q_shape = k_shape[:-sd] + self._random_shape(gen, lo[-sd:], hi[-sd:], dtype == torch.float16)
+            k_shape = self._random_shape(shape_gen, lo, hi, dtype == torch.float16)
+            q_shape = k_shape[:-sd] + self._random_shape(shape_gen, lo[-sd:], hi[-sd:], dtype == torch.float16)
         do_shape = q_shape[:-sd - 1] + k_shape[-sd - 1:-sd] + q_shape[-sd:]
 
         def u(shape):
@@ -148,7 +149,7 @@ class Case:
 
     def verify(self, runs):
         device = torch.device("cuda", torch.cuda.current_device())
-        gen = torch.Generator(device=device).manual_seed(random_seed)
+        gen = (torch.Generator().manual_seed(random_seed), torch.Generator(device=device).manual_seed(random_seed))
         for dtype in _DTYPES:
             worst = [0.0, 0.0]
             for _ in range(runs):
@@ -175,7 +176,7 @@ class Case:
 
     def benchmark(self, runs, burn):
         device = torch.device("cuda", torch.cuda.current_device())
-        gen = torch.Generator(device=device).manual_seed(random_seed)
+        gen = (torch.Generator().manual_seed(random_seed), torch.Generator(device=device).manual_seed(random_seed))
         report = {}
         for dtype in _DTYPES:
             Q, K, V, dO, mask, window, log2_stride = self.data(dtype, "max", gen, device)
