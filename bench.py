@@ -562,7 +562,8 @@ def main():
         torch.cuda.empty_cache()
         nb_f = _capi.lib.fa_host_arena_bytes(C.byref(prob), 0)
         nb_b = _capi.lib.fa_host_arena_bytes(C.byref(prob), 1)
-        arena = torch.empty(max(nb_f, nb_b), dtype=torch.uint8, device=dev)
+        nb_s = _capi.lib.fa_step_host_arena_bytes(C.byref(prob))
+        arena = torch.empty(max(nb_f, nb_b, nb_s), dtype=torch.uint8, device=dev)
 
         def fwd_host():
             _capi.check(_capi.lib.fa_forward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
@@ -570,7 +571,17 @@ def main():
                                                   arena.numel(), sp), "fa_forward_host")
 
         def e2e_step():
-            # one training step as the reference's host framework runs it: forward op, then its registered gradient
+            # one training step on host buffers through the C ABI: forward + gradient, chunk-pipelined in one call
+            if args.fwd_only:
+                return fwd_host()
+            _capi.check(_capi.lib.fa_forward_backward_host(C.byref(prob), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
+                                                           hdo.data_ptr(), ho.data_ptr(), hl.data_ptr(), hm.data_ptr(),
+                                                           hdq.data_ptr(), hdk.data_ptr(), hdv.data_ptr(),
+                                                           arena.data_ptr(), arena.numel(), sp),
+                        "fa_forward_backward_host")
+
+        def e2e_step_two_calls():
+            # the same step as the reference's host framework runs it: forward op, then its registered gradient
             # with the forward's tensors still on the device (only dO is uploaded for the backward)
             fwd_host()
             if not args.fwd_only:
@@ -611,9 +622,15 @@ def main():
             d2h += nb(hdq) + nb(hdk) + nb(hdv)
         line["e2e"] = {"value": step_flops * world / sec / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
-                       "api": "fa_forward_host + fa_backward_host_resident (C ABI, pinned host buffers, copies inside "
-                              "the calls; Q, K, V, O, l, m stay on the device between the forward and its gradient)"}
+                       "api": "fa_forward_host (C ABI, pinned host buffers, copies inside the call)" if args.fwd_only else
+                              "fa_forward_backward_host (C ABI, pinned host buffers; uploads, kernels and downloads of "
+                              "successive batch chunks overlap inside the call)"}
         if not args.fwd_only:
+            sec1 = time_e2e(e2e_step_two_calls)
+            line["e2e_two_calls"] = {"value": step_flops * world / sec1 / 1e12, "unit": "TFLOPS", "h2d_bytes_per_step": h2d,
+                                     "d2h_bytes_per_step": d2h, "ms_per_step": sec1 * 1e3, "steps": args.e2e_steps,
+                                     "api": "fa_forward_host + fa_backward_host_resident (Q, K, V, O, l, m stay on the "
+                                            "device between the forward and its gradient)"}
             sec2 = time_e2e(e2e_step_stateless)
             line["e2e_stateless"] = {"value": step_flops * world / sec2 / 1e12, "unit": "TFLOPS",
                                      "h2d_bytes_per_step": h2d + nb(hq) + nb(hk) + nb(hv) + nb(ho) + nb(hl) + nb(hm),

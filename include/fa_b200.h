@@ -201,6 +201,15 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
 int fa_backward_host_resident(const fa_problem_t* p, const void* d_o, void* d_q, void* d_k, void* d_v,
                               void* dev_arena, size_t dev_arena_bytes, void* stream);
 
+/* One training step on host buffers: forward, then the gradient, pipelined over batch chunks so that the uploads of
+ * Q, K, V, d_o of the next chunk overlap the kernels of the current one and the downloads of O, l, m, d_q, d_k, d_v of
+ * the previous one (both PCIe directions busy for the whole step). Same results as fa_forward_host followed by
+ * fa_backward_host. Arena >= fa_step_host_arena_bytes(p); p->accumulate must be 0. Returns after the stream drained. */
+size_t fa_step_host_arena_bytes(const fa_problem_t* p);
+int fa_forward_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* d_o,
+                             void* o, void* l, void* m, void* d_q, void* d_k, void* d_v, void* dev_arena,
+                             size_t dev_arena_bytes, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------- */
 const char* fa_strerror(int status);
 int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on this thread */

@@ -178,15 +178,18 @@ def test_host_buffer_entry_points():
 
 
 @pytest.mark.parametrize("dtype,shape", [(np.float32, (2, 2, 16, 24, 100, 150)), (np.float16, (5, 2, 128, 128, 256, 256)),
-                                         (np.float16, (3, 3, 64, 64, 200, 136)), (np.float64, (1, 3, 8, 8, 50, 70))])
-def test_host_training_step_keeps_forward_tensors_resident(dtype, shape):
-    """fa_forward_host + fa_backward_host_resident in one arena (only dO is uploaded for the backward) give the same
-    bytes as the stateless pair fa_forward_host + fa_backward_host, and match the oracle."""
+                                         (np.float16, (3, 3, 64, 64, 200, 136)), (np.float64, (1, 3, 8, 8, 50, 70)),
+                                         (np.float16, (61, 35, 64, 64, 64, 64))])   # 70 MB: the calls split the batch into uneven chunks
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_host_training_step_keeps_forward_tensors_resident(dtype, shape, pipelined):
+    """fa_forward_host + fa_backward_host_resident in one arena (only dO is uploaded for the backward) and the
+    chunk-pipelined single call fa_forward_backward_host give the same bytes as the stateless pair fa_forward_host +
+    fa_backward_host, and match the oracle."""
     b0, b1, d, vd, nq, nk = shape
     rng = np.random.default_rng(6)
     Q, K, V, dO = da.random_inputs(rng, dtype, (b0, b1), d, vd, (nq,), (nk,))
     ref = da.attention(Q, K, V, 1, "causal", "scale_end", dO=dO)
-    O, l, m, dQ, dK, dV = fa.forward_backward_host(1, "causal", Q, K, V, dO, "scale_end")
+    O, l, m, dQ, dK, dV = fa.forward_backward_host(1, "causal", Q, K, V, dO, "scale_end", pipelined=pipelined)
     O2, l2, m2 = fa.causal_1d(Q, K, V, "scale_end", returning_l_m=True)
     assert np.array_equal(O, O2) and np.array_equal(l, l2) and np.array_equal(m, m2)
     assert max_abs_err(O, ref["O"]) <= TOL[np.dtype(dtype)]

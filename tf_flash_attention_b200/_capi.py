@@ -89,6 +89,8 @@ def _load():
         "fa_forward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_backward_host_resident": (C.c_int, [PP, vp, vp, vp, vp, vp, sz, vp]),
+        "fa_step_host_arena_bytes": (sz, [PP]),
+        "fa_forward_backward_host": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "fa_partial_merge": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, C.c_int, vp]),
         "fa_partial_finalize": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp]),
         "fa_layout_transpose": (C.c_int, [C.c_int32, vp, vp, i64, i64, C.c_int32, C.c_int32, C.c_int, vp]),

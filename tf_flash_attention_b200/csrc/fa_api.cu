@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -724,6 +725,66 @@ int fa_backward_host(const fa_problem_t* p, const void* q, const void* k, const 
                      const void* l, const void* m, const void* d_o, void* d_q, void* d_k, void* d_v,
                      void* dev_arena, size_t dev_arena_bytes, void* stream) {
   return backward_host_impl(p, false, q, k, v, o, l, m, d_o, d_q, d_k, d_v, dev_arena, dev_arena_bytes, stream);
+}
+
+// One training step (forward + gradient) on host buffers, pipelined over batch chunks: upload of chunk c+1 (Q, K, V, dO),
+// forward + backward of chunk c and download of chunk c-1 (O, l, m, dQ, dK, dV) overlap, so both PCIe directions are busy
+// for the whole step (the two-call sequence is upload-bound in the forward and download-bound in the backward).
+size_t fa_step_host_arena_bytes(const fa_problem_t* p) {
+  Arena a;
+  if (arena_layout(p, 1, &a)) return 0;
+  return a.ws + align_up(std::max(fa_workspace_bytes(p, 0), fa_workspace_bytes(p, 1)));
+}
+
+int fa_forward_backward_host(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* d_o,
+                             void* o, void* l, void* m, void* d_q, void* d_k, void* d_v, void* dev_arena,
+                             size_t dev_arena_bytes, void* stream) {
+  Arena a;
+  int rc = arena_layout(p, 1, &a);
+  if (rc) return rc;
+  if (p->accumulate) return FA_EINVAL_SHAPE;   // a step starts from fresh outputs
+  const size_t need = fa_step_host_arena_bytes(p);
+  if (!dev_arena || dev_arena_bytes < need) return FA_EINVAL_WORKSPACE;
+  if (!q || !k || !v || !d_o || !o || !l || !m || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
+  if (p->batch == 0) return FA_OK;
+  char* base = (char*)dev_arena;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t B = p->batch;
+  const int64_t nch = p->batch < 2 || a.nq_b + a.nk_b + a.nv_b + a.no_b < (size_t(64) << 20) ? 1 : std::min<int64_t>(B, 16);
+  HostPipe pipe;
+  FA_CU(pipe.init(int(2 * nch + 1)));
+  FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));
+  FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
+  const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
+  for (int64_t c = 0; c < nch; ++c) {
+    const int64_t b0 = B * c / nch, nb = B * (c + 1) / nch - b0;
+    FA_CU(cudaMemcpyAsync(base + a.q + b0 * sq, (const char*)q + b0 * sq, nb * sq, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.k + b0 * sk, (const char*)k + b0 * sk, nb * sk, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.v + b0 * sv, (const char*)v + b0 * sv, nb * sv, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaMemcpyAsync(base + a.d_o + b0 * so, (const char*)d_o + b0 * so, nb * so, cudaMemcpyHostToDevice, pipe.in));
+    FA_CU(cudaEventRecord(pipe.ev[2 * c], pipe.in));
+    FA_CU(cudaStreamWaitEvent(st, pipe.ev[2 * c], 0));
+    fa_problem_t sub = *p;
+    sub.batch = nb;
+    rc = fa_forward(&sub, base + a.q + b0 * sq, base + a.k + b0 * sk, base + a.v + b0 * sv, base + a.o + b0 * so,
+                    base + a.l + b0 * sl, base + a.m + b0 * sm, base + a.ws, need - a.ws, stream);
+    if (rc) return rc;
+    rc = fa_backward(&sub, base + a.q + b0 * sq, base + a.k + b0 * sk, base + a.v + b0 * sv, base + a.o + b0 * so,
+                     base + a.l + b0 * sl, base + a.m + b0 * sm, base + a.d_o + b0 * so, base + a.d_q + b0 * sq,
+                     base + a.d_k + b0 * sk, base + a.d_v + b0 * sv, base + a.ws, need - a.ws, stream);
+    if (rc) return rc;
+    FA_CU(cudaEventRecord(pipe.ev[2 * c + 1], st));
+    FA_CU(cudaStreamWaitEvent(pipe.out, pipe.ev[2 * c + 1], 0));
+    FA_CU(cudaMemcpyAsync((char*)o + b0 * so, base + a.o + b0 * so, nb * so, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)l + b0 * sl, base + a.l + b0 * sl, nb * sl, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)m + b0 * sm, base + a.m + b0 * sm, nb * sm, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)d_q + b0 * sq, base + a.d_q + b0 * sq, nb * sq, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)d_k + b0 * sk, base + a.d_k + b0 * sk, nb * sk, cudaMemcpyDeviceToHost, pipe.out));
+    FA_CU(cudaMemcpyAsync((char*)d_v + b0 * sv, base + a.d_v + b0 * sv, nb * sv, cudaMemcpyDeviceToHost, pipe.out));
+  }
+  FA_CU(cudaStreamSynchronize(pipe.out));
+  FA_CU(cudaStreamSynchronize(st));
+  return FA_OK;
 }
 
 int fa_backward_host_resident(const fa_problem_t* p, const void* d_o, void* d_q, void* d_k, void* d_v,

@@ -247,10 +247,13 @@ def attention_backward(seq_dims, rule, Q, K, V, O, l, m, dO, sync_mode, window_s
     return backward_host(p, Q, K, V, O, l, m, dO)
 
 
-def forward_backward_host(seq_dims, rule, Q, K, V, dO, sync_mode, window_size=1, log2_stride_size=0, is_causal=False):
-    """One training step on host (NumPy) buffers: forward, then the registered backward with the forward's tensors
-    kept on the device in between (`fa_forward_host` + `fa_backward_host_resident` in one arena): Q, K, V and dO
-    cross PCIe once on the way in, O, l, m, dQ, dK, dV once on the way out. Returns (O, l, m, dQ, dK, dV)."""
+def forward_backward_host(seq_dims, rule, Q, K, V, dO, sync_mode, window_size=1, log2_stride_size=0, is_causal=False,
+                          pipelined=True):
+    """One training step on host (NumPy) buffers: forward, then the registered backward. Q, K, V and dO cross PCIe once
+    on the way in, O, l, m, dQ, dK, dV once on the way out. `pipelined` (default): one `fa_forward_backward_host` call
+    that overlaps uploads, kernels and downloads of successive batch chunks; otherwise `fa_forward_host` followed by
+    `fa_backward_host_resident` in one arena (the forward's tensors stay on the device for the gradient).
+    Returns (O, l, m, dQ, dK, dV)."""
     p = _problem(seq_dims, rule, Q, K, V, sync_mode, window_size, log2_stride_size, is_causal)
     Q, K, V, dO = (np.ascontiguousarray(x) for x in (Q, K, V, dO))
     o_shape, lm_shape = _out_shapes(p, Q, V)
@@ -260,8 +263,15 @@ def forward_backward_host(seq_dims, rule, Q, K, V, dO, sync_mode, window_size=1,
     l = np.empty(lm_shape, dtype=_NP_L_DTYPE[p.dtype])
     m = np.empty(lm_shape, dtype=Q.dtype)
     dQ, dK, dV = np.empty_like(Q), np.empty_like(K), np.empty_like(V)
-    arena = _device_arena(_capi.lib.fa_host_arena_bytes(C.byref(p), 1))
     stream = torch.cuda.current_stream().cuda_stream
+    if pipelined:
+        arena = _device_arena(_capi.lib.fa_step_host_arena_bytes(C.byref(p)))
+        _capi.check(_capi.lib.fa_forward_backward_host(C.byref(p), Q.ctypes.data, K.ctypes.data, V.ctypes.data,
+                                                       dO.ctypes.data, O.ctypes.data, l.ctypes.data, m.ctypes.data,
+                                                       dQ.ctypes.data, dK.ctypes.data, dV.ctypes.data, arena.data_ptr(),
+                                                       arena.numel(), stream), "fa_forward_backward_host")
+        return O, l, m, dQ, dK, dV
+    arena = _device_arena(_capi.lib.fa_host_arena_bytes(C.byref(p), 1))
     _capi.check(_capi.lib.fa_forward_host(C.byref(p), Q.ctypes.data, K.ctypes.data, V.ctypes.data, O.ctypes.data,
                                           l.ctypes.data, m.ctypes.data, arena.data_ptr(), arena.numel(), stream),
                 "fa_forward_host")
