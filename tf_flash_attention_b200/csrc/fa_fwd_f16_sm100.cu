@@ -57,7 +57,11 @@ __device__ long long* g_dbg = nullptr;
 // BN = 64 with head_dim 64 needs 256 TMEM columns and ~66 KB of shared memory, so two CTAs share an SM
 // (MINB = 2): short sequences and narrow windows are latency chains per CTA (prologue, 2-3 tiles, epilogue)
 // and HBM-bound overall, and only a second resident CTA hides those chains.
-template <int D, int VD, int BN>
+// VAR: experimental variants of the softmax / MMA hand-off, selectable with fa_set_path_override for A/B runs (bit 0:
+// row max as four independent chains instead of one; bit 1: P is handed to the MMA warp in two halves, so P V of keys
+// 0..63 runs while the exponentials of keys 64..127 are still being computed). VAR = 0 is the measured default; its
+// instantiations are unaffected by the variants (`if constexpr`).
+template <int D, int VD, int BN, int VAR = 0>
 struct FwdCfg {
   static constexpr int kCh = D > VD ? D : VD;
   static constexpr int kQTileBytes = kBlockM * kCh * 2;   // doubles as the O staging tile
@@ -66,14 +70,14 @@ struct FwdCfg {
   static constexpr int kColsUsed = kColO + kQTiles * VD;
   static constexpr int kTmemCols = kColsUsed <= 256 ? 256 : 512;
   static constexpr int kBarOffset = kQTiles * kQTileBytes + kStages * kStageBytes;
-  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2;
+  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2 + ((VAR & 2) ? 2 : 0);
   static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;  // + alignment slack
 };
 
-template <int D, int VD, int BN, int MINB>
+template <int D, int VD, int BN, int MINB, int VAR = 0>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_constant__ FwdParams p) {
-  using Cfg = FwdCfg<D, VD, BN>;
+  using Cfg = FwdCfg<D, VD, BN, VAR>;
   constexpr int kBlockN = BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
   const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;  // [2]
   const uint32_t bar_p_ready = bar_s_full + 16;            // [2]
   const uint32_t bar_o_final = bar_p_ready + 16;           // [2]
-  const uint32_t tmem_slot = bar_o_final + 16;
+  const uint32_t bar_p_half = bar_o_final + 16;            // [2], VAR & 2 only
+  const uint32_t tmem_slot = bars + Cfg::kNumBars * 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
 
   const int warp = threadIdx.x >> 5;
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         mbar_init(bar_s_full + 8 * i, 1);
         mbar_init(bar_p_ready + 8 * i, kBlockM);
         mbar_init(bar_o_final + 8 * i, 1);
+        if constexpr ((VAR & 2) != 0) mbar_init(bar_p_half + 8 * i, kBlockM);
       }
       for (int s = 0; s < kStages; ++s) {
         mbar_init(bar_kv_full + 8 * s, 1);
@@ -197,6 +203,15 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mma_ss(tmem_base + i * kBlockN, da, db, idesc_qk, ks > 0);
           }
         };
+        auto issue_pv_half = [&](int i, int stage, bool accumulate, int half) {   // VAR & 2: keys 64 * half .. + 63
+          const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = half * (kBlockN / 32); ks < (half + 1) * (kBlockN / 32); ++ks) {
+            const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
+            mma_ts(tmem_base + Cfg::kColO + i * VD, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
+                   (accumulate || ks > 0) ? 1u : 0u);
+          }
+        };
         auto issue_pv = [&](int i, int stage, bool accumulate) {
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
@@ -221,10 +236,20 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             const int tk = 2 * j + 2, sk = tk % kStages;
             mbar_wait(bar_kv_full + 8 * sv, (tv / kStages) & 1);
             for (int i = 0; i < kQTiles; ++i) {
-              mbar_wait(bar_p_ready + 8 * i, j & 1);
-              tc_fence_after();
-              FA_STAMP(2 + i, j, 0);
-              issue_pv(i, sv, j > 0);
+              if constexpr ((VAR & 2) != 0) {
+                mbar_wait(bar_p_half + 8 * i, j & 1);
+                tc_fence_after();
+                issue_pv_half(i, sv, j > 0, 0);
+                mbar_wait(bar_p_ready + 8 * i, j & 1);
+                tc_fence_after();
+                FA_STAMP(2 + i, j, 0);
+                issue_pv_half(i, sv, true, 1);
+              } else {
+                mbar_wait(bar_p_ready + 8 * i, j & 1);
+                tc_fence_after();
+                FA_STAMP(2 + i, j, 0);
+                issue_pv(i, sv, j > 0);
+              }
               if (i == kQTiles - 1) mma_commit(bar_kv_empty + 8 * sv);
               if (j + 1 < n) {
                 if (i == 0) {
@@ -305,9 +330,24 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         for (int c = 0; c < kBlockN; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
       }
       if (r == 0) FA_STAMP(i, j, 1);
-      float mx = s[0];
+      float mx;
+      if constexpr ((VAR & 1) != 0) {
+        // four independent chains (each still fuses into 3-input max instructions): the single chain is 63 dependent
+        // FMNMX3, i.e. latency-bound with only two softmax warps per scheduler
+        float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int c = 1; c < kBlockN; ++c) mx = fmaxf(mx, s[c]);
+        for (int c = 4; c + 8 <= kBlockN; c += 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) m4[e] = fmaxf(fmaxf(m4[e], s[c + e]), s[c + 4 + e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], s[kBlockN - 4 + e]);
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+        mx = s[0];
+#pragma unroll
+        for (int c = 1; c < kBlockN; ++c) mx = fmaxf(mx, s[c]);
+      }
       const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
@@ -333,18 +373,44 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
       const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
       // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
       float sum0 = 0.f, sum1 = 0.f;
+      if constexpr ((VAR & 2) != 0) {
+        static_assert((VAR & 2) == 0 || BN == 128, "the two-halves hand-off is written for 128-key tiles");
+        auto exp_chunk = [&](int c, uint32_t* pk) {
 #pragma unroll
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        uint32_t pk[16];
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
+            const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
+            sum0 += p0;
+            sum1 += p1;
+            pk[e >> 1] = pack_half2(p0, p1);
+          }
+        };
+        uint32_t pk0[16], pk1[16];
+        exp_chunk(0, pk0);
+        tmem_st16(t_s + 0, pk0);
+        exp_chunk(1, pk1);
+        tmem_st16(t_s + 16, pk1);
+        exp_chunk(2, pk0);          // the stores of the first half complete under these exponentials
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p_half + 8 * i);   // keys 0..63 of P are in TMEM: P V can start on them
+        tmem_st16(t_s + 32, pk0);
+        exp_chunk(3, pk1);
+        tmem_st16(t_s + 48, pk1);
+      } else {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
-          const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
-          sum0 += p0;
-          sum1 += p1;
-          pk[e >> 1] = pack_half2(p0, p1);
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
+            const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
+            sum0 += p0;
+            sum1 += p1;
+            pk[e >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st16(t_s + c * 16, pk);
         }
-        tmem_st16(t_s + c * 16, pk);
       }
       l_sum += sum0 + sum1;
       if (r == 0) FA_STAMP(i, j, 2);
@@ -433,9 +499,9 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
-template <int D, int VD, int BN, int MINB>
+template <int D, int VD, int BN, int MINB, int VAR = 0>
 cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
-  using Cfg = FwdCfg<D, VD, BN>;
+  using Cfg = FwdCfg<D, VD, BN, VAR>;
   FwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
   if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
@@ -451,7 +517,7 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
   p.batch = int32_t(a.batch);
   p.scale_log2 = kLog2e / sqrtf(float(D));
-  auto kern = fwd_kernel<D, VD, BN, MINB>;
+  auto kern = fwd_kernel<D, VD, BN, MINB, VAR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   ScopedKernel timed(BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64", stream);
@@ -490,7 +556,13 @@ size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
 // S2 3.95 -> 2.01 ms, C3 0.84 -> 0.51 ms, C4 0.86 -> 0.73 ms; profiles/r1_short_sequences.md); override 5 keeps the
 // 128-key / one-CTA configuration reachable for A/B runs.
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 128 && a.v_d == 128) return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
+  if (a.d == 128 && a.v_d == 128) {
+    // developer A/B variants of the softmax / MMA hand-off (see FwdCfg); not measured yet, never taken by default
+    if (a.variant == 10) return sm100::launch_fwd<128, 128, 128, 1, 1>(a, stream);
+    if (a.variant == 11) return sm100::launch_fwd<128, 128, 128, 1, 2>(a, stream);
+    if (a.variant == 12) return sm100::launch_fwd<128, 128, 128, 1, 3>(a, stream);
+    return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
+  }
   if (a.d == 64 && a.v_d == 64) {
     if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
     return sm100::launch_fwd<64, 64, 128, 1>(a, stream);

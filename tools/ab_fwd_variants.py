@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Round-2 A/B of the forward hand-off variants compiled into libfa_b200.so (fa_fwd_f16_sm100.cu, FwdCfg VAR):
+
+  fa_set_path_override(10)  row max as four independent chains
+  fa_set_path_override(11)  P handed to the MMA warp in two halves (P V of keys 0..63 overlaps the second half's exps)
+  fa_set_path_override(12)  both
+
+They have been compiled and their SASS inspected, but NOT run on a GPU yet (round 1 ran out of GPU minutes), so every
+variant runs in its own process under a timeout: a barrier mistake shows up as a timeout here, not as a hung box.
+Per variant: (1) bit-equality of O, l, m against the default kernel on a small causal case and a ragged one,
+(2) C2 forward time (CUDA events, 20 launches).
+
+  gpurun --timeout 300 -- 'python tools/ab_fwd_variants.py'
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import sys, json, torch
+sys.path.insert(0, %(root)r)
+from tf_flash_attention_b200 import _capi
+from tf_flash_attention_b200 import flash_attention as fa
+variant = int(sys.argv[1])
+g = torch.Generator(device="cuda").manual_seed(1)
+def u(*shape):
+    return (torch.rand(shape, generator=g, device="cuda") * 4 - 2).half()
+out = {"variant": variant}
+for name, (b, s) in {"small": (4, 1024), "ragged": (3, 1000)}.items():
+    Q, K, V = u(b, 128, s), u(b, 128, s), u(b, 128, s)
+    ref = fa.causal_1d(Q, K, V, "none_front", returning_l_m=True)
+    _capi.lib.fa_set_path_override(variant)
+    got = fa.causal_1d(Q, K, V, "none_front", returning_l_m=True)
+    _capi.lib.fa_set_path_override(0)
+    torch.cuda.synchronize()
+    out[name + "_bit_equal"] = all(torch.equal(a, c) for a, c in zip(ref, got))
+Q, K, V = u(256, 128, 8192), u(256, 128, 8192), u(256, 128, 8192)
+_capi.lib.fa_set_path_override(variant)
+for _ in range(3):
+    fa.causal_1d(Q, K, V, "none_front")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    fa.causal_1d(Q, K, V, "none_front")
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 20
+out["c2_fwd_ms"] = ms
+out["c2_fwd_tflops"] = 4.398583382016e12 / (ms * 1e-3) / 1e12
+print(json.dumps(out))
+'''
+
+
+def main():
+    for variant in (0, 10, 11, 12, 0):
+        try:
+            r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}, str(variant)], capture_output=True,
+                               text=True, timeout=60)
+            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
+        except subprocess.TimeoutExpired:
+            line = json.dumps({"variant": variant, "error": "timeout (hung kernel?)"})
+        print(line, flush=True)
+
+
+if __name__ == "__main__":
+    main()
