@@ -297,6 +297,45 @@ def test_workspace_sizes_follow_the_dispatch_rules():
         _capi.lib.fa_set_path_override(0)
 
 
+def test_host_step_entry_points_validate_before_touching_the_device():
+    """fa_forward_backward_host / fa_backward_host_resident / fa_step_host_arena_bytes: sizes and argument checks are
+    host-only."""
+    import ctypes as C
+    lib = _capi.lib
+    for dtype, d in ((_capi.FA_F16, 128), (_capi.FA_F32, 64), (_capi.FA_F64, 24)):
+        p = _capi.make_problem(dtype, 1, "causal", "none_front", (2, 3, d, 512), (2, 3, d, 384), (2, 3, d, 384))
+        step = int(lib.fa_step_host_arena_bytes(C.byref(p)))
+        fwd, bwd = int(lib.fa_host_arena_bytes(C.byref(p), 0)), int(lib.fa_host_arena_bytes(C.byref(p), 1))
+        assert step >= bwd >= fwd > 0
+        # the step arena holds the backward layout plus the larger of the two workspaces
+        assert step - bwd == max(0, (int(lib.fa_workspace_bytes(C.byref(p), 0)) + 255) // 256 * 256
+                                 - (int(lib.fa_workspace_bytes(C.byref(p), 1)) + 255) // 256 * 256)
+    one = C.c_void_p(0x1000)    # never dereferenced: every call below fails validation first
+    args = [one] * 10
+    assert lib.fa_forward_backward_host(C.byref(p), *args, None, step, None) == _capi.FA_EINVAL_WORKSPACE
+    assert lib.fa_forward_backward_host(C.byref(p), *args, one, step - 1, None) == _capi.FA_EINVAL_WORKSPACE
+    assert lib.fa_forward_backward_host(C.byref(p), None, *args[1:], one, step, None) == _capi.FA_EINVAL_NULL
+    assert lib.fa_backward_host_resident(C.byref(p), None, one, one, one, one, bwd, None) == _capi.FA_EINVAL_NULL
+    assert lib.fa_backward_host_resident(C.byref(p), one, one, one, one, one, bwd - 1, None) == _capi.FA_EINVAL_WORKSPACE
+    p.accumulate = 1
+    assert lib.fa_forward_backward_host(C.byref(p), *args, one, step, None) == _capi.FA_EINVAL_SHAPE
+    p.accumulate = 0
+    p.batch = 0                 # empty batch: nothing to do
+    assert lib.fa_forward_backward_host(C.byref(p), *args, one, 1 << 30, None) == _capi.FA_OK
+    assert lib.fa_backward_host_resident(C.byref(p), one, one, one, one, one, 1 << 30, None) == _capi.FA_OK
+
+
+def test_round2_ab_script_child_compiles():
+    """tools/ab_fwd_variants.py runs its per-variant body in a child interpreter: the template must at least compile."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ab_fwd_variants.py")
+    spec = importlib.util.spec_from_file_location("ab_fwd_variants", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    compile(mod.CHILD % {"root": "/tmp"}, "child", "exec")
+
+
 def test_tensor_core_paths_decline_sequences_beyond_the_tile_schedule():
     """The per-CTA tile schedule covers 2048 streamed 64-wide tiles (131072 positions); longer sequences must fall back to
     the generic kernels instead of overrunning it. Observable on the host through the fp32 workspace sizes."""
