@@ -138,9 +138,9 @@ int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_
 int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream);
 int fa_grad_finalize(int32_t dtype, const void* acc, void* out, int64_t n, void* stream);
 
-/* Layout adapter for the step either side of the op (the reference's README wraps it in einsums that build the
- * channel-first layout): to_channel_first != 0: x [batch, seq, heads, channels] -> y [batch, heads, channels, seq];
- * otherwise the inverse. Same dtype codes as fa_problem_t. HBM-bound transpose, asynchronous on `stream`.       */
+/* Layout adapter for the step either side of the op (no reference counterpart: README.md:40 of the reference assumes an
+ * einsum either side of the op that builds the channel-first layout).
+ * to_channel_first != 0: x [batch, seq, heads, channels] -> y [batch, heads, channels, seq]; otherwise the inverse. Same dtype codes as fa_problem_t. HBM-bound transpose, asynchronous on `stream`.       */
 int fa_layout_transpose(int32_t dtype, const void* x, void* y, int64_t batch, int64_t seq, int32_t heads,
                         int32_t channels, int to_channel_first, void* stream);
 
