@@ -1,4 +1,5 @@
-"""Developer tool: dump the per-event clock stamps of CTA 0 of the fwd kernel (FA_DBG_TIMELINE build)."""
+"""Developer tool: dump the per-event clock stamps of CTA 0 of the fwd kernel (FA_DBG_TIMELINE build).
+Optional argument: a fa_set_path_override value (10 / 11 / 12 = the forward hand-off variants)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,6 +10,8 @@ _capi.lib.fa_debug_set_buffer(buf.data_ptr())
 B, d, S = 8, 128, 8192
 g = torch.Generator(device="cuda").manual_seed(0)
 Q, K, V = ((torch.rand((B, d, S), generator=g, device="cuda") * 4 - 2).half() for _ in range(3))
+if len(sys.argv) > 1:
+    _capi.lib.fa_set_path_override(int(sys.argv[1]))
 for _ in range(3):
     fa.causal_1d(Q, K, V, "none_front")
 torch.cuda.synchronize()
