@@ -4,6 +4,8 @@
   fa_set_path_override(10)  row max as four independent chains
   fa_set_path_override(11)  P handed to the MMA warp in two halves (P V of keys 0..63 overlaps the second half's exps)
   fa_set_path_override(12)  both
+  fa_set_path_override(13)  both + the upper half of the next Q K^T issued as soon as the S row is in registers, by an MMA
+                            issuer that polls the barriers of both warpgroups
 
 They have been compiled and their SASS inspected, but NOT run on a GPU yet (round 1 ran out of GPU minutes), so every
 variant runs in its own process under a timeout: a barrier mistake shows up as a timeout here, not as a hung box.
@@ -54,7 +56,7 @@ print(json.dumps(out))
 
 
 def main():
-    for variant in (0, 10, 11, 12, 0):
+    for variant in (0, 10, 11, 12, 13, 0):
         try:
             r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}, str(variant)], capture_output=True,
                                text=True, timeout=60)
