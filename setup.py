@@ -21,7 +21,7 @@ setup(
     name="tf_flash_attention_b200",
     version="0.1.0",
     description="B200-native (sm_100a, tcgen05/TMEM/TMA) drop-in engine for tf_flash_attention",
-    packages=["tf_flash_attention_b200"],
+    packages=["tf_flash_attention_b200", "tf_flash_attention_b200.tests"],
     package_data={"tf_flash_attention_b200": ["libfa_b200.so", "kernel/flash_attention.so"]},
     ext_modules=[Extension("tf_flash_attention_b200._native", sources=[])],
     cmdclass={"build_ext": MakeBuild},
