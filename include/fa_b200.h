@@ -226,7 +226,10 @@ void fa_kernel_timing(int enable);
 int fa_kernel_timings(int max_entries, const char** names, float* ms);
 /* Force a kernel family (testing): 0 auto, 1 generic only, 4 fp16 backward as the two-kernel
  * (dQ, then dK/dV) variant instead of the fused kernel, 5 fp16 head_dim-64 forward with 128-key
- * tiles and one CTA per SM instead of 64-key tiles and two CTAs per SM.                    */
+ * tiles and one CTA per SM instead of 64-key tiles and two CTAs per SM. Developer A/B values:
+ * 7 / 8 / 9 = element-wise kernels of fa_layout_transpose (pairs / singles / quads of halves);
+ * 10 / 11 / 12 / 13 = hand-off variants of the fp16 head_dim-128 forward (DESIGN.md section 6b;
+ * compiled, not yet measured, never taken unless selected here).                             */
 void fa_set_path_override(int path);
 const char* fa_version(void);
 
