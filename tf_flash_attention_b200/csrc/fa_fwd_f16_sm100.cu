@@ -641,6 +641,7 @@ cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
     return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
   }
   if (a.d == 64 && a.v_d == 64) {
+    if (a.variant == 10) return sm100::launch_fwd<64, 64, 64, 2, 1>(a, stream);   // row max as four chains (A/B, unmeasured)
     if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
     return sm100::launch_fwd<64, 64, 128, 1>(a, stream);
   }
