@@ -51,6 +51,23 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 out["c2_fwd_ms"] = ms
 out["c2_fwd_tflops"] = 4.398583382016e12 / (ms * 1e-3) / 1e12
+if variant in (0, 10):   # head_dim 64 (64-key tiles, two CTAs per SM): S1-like short sequences and C4-like cross attention
+    del Q, K, V
+    for name, (b, sq, sk, fn) in {"s1": (16384, 256, 256, lambda q, k, v: fa.causal_1d(q, k, v, "none_front")),
+                                  "c4": (256, 1024, 8192, lambda q, k, v: fa.full_1d(q, k, v, "scale_end"))}.items():
+        q, k, v = u(b, 64, sq), u(b, 64, sk), u(b, 64, sk)
+        _capi.lib.fa_set_path_override(0)
+        ref = fn(q, k, v)
+        _capi.lib.fa_set_path_override(variant)
+        got = fn(q, k, v)
+        out[name + "_bit_equal"] = bool(torch.equal(ref, got))
+        e0.record()
+        for _ in range(20):
+            fn(q, k, v)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_fwd_ms"] = e0.elapsed_time(e1) / 20
+        del q, k, v
 print(json.dumps(out))
 '''
 
