@@ -227,10 +227,15 @@ int fa_kernel_timings(int max_entries, const char** names, float* ms);
 /* Force a kernel family (testing): 0 auto, 1 generic only, 4 fp16 backward as the two-kernel
  * (dQ, then dK/dV) variant instead of the fused kernel, 5 fp16 head_dim-64 forward with 128-key
  * tiles and one CTA per SM instead of 64-key tiles and two CTAs per SM. Developer A/B values:
- * 7 / 8 / 9 = element-wise kernels of fa_layout_transpose (pairs / singles / quads of halves);
- * 10 / 11 / 12 / 13 = hand-off variants of the fp16 head_dim-128 forward (DESIGN.md section 6b;
- * compiled, not yet measured, never taken unless selected here).                             */
+ * 7 / 8 / 9 = element-wise kernels of fa_layout_transpose (pairs / singles / quads of halves). */
 void fa_set_path_override(int path);
+/* Precision of the fp16 gradients. The fp16 backward hands P and dS to the tensor cores as fp16; |dS| reaches
+ * several units on rows that attend few keys, where one fp16 rounding is ~1e-3 absolute. mode 0 (default, automatic):
+ * dS goes in as a hi + lo pair of fp16 values (two products for dQ and dK) on every path except the fused
+ * head_dim-128 kernel; mode 1: everywhere (head_dim 128 then runs the two-kernel backward); mode 2: nowhere.
+ * The reference accumulates these products in fp16 altogether (flash_attention.cu:284-286); no counterpart there.
+ * Returns FA_OK or FA_EINVAL_SHAPE for an unknown mode.                                                    */
+int fa_set_grad_precision(int mode);
 const char* fa_version(void);
 
 #ifdef __cplusplus

@@ -348,3 +348,17 @@ def test_tensor_core_paths_decline_sequences_beyond_the_tile_schedule():
     assert ws(1024, 131072, 1) > 2 * 1024 * 4 * 10
     assert ws(1024, 131072 + 64, 1) == 2 * 1024 * 4          # generic: LSE + D only
     assert ws(131072 + 64, 1024, 1) == 2 * (131072 + 64) * 4
+
+
+def test_null_workspace_is_rejected_when_one_is_needed():
+    """fa_forward / fa_backward with workspace == NULL while fa_workspace_bytes() > 0 must fail validation instead of
+    launching kernels that write through address 0 (the fp32 forward keeps its TF32 pieces there)."""
+    import ctypes as C
+    lib = _capi.lib
+    p = _capi.make_problem(_capi.FA_F32, 1, "full", "none_front", (2, 64, 256), (2, 64, 512), (2, 64, 512))
+    need_f, need_b = int(lib.fa_workspace_bytes(C.byref(p), 0)), int(lib.fa_workspace_bytes(C.byref(p), 1))
+    assert need_f > 0 and need_b > 0
+    one = C.c_void_p(0x1000)    # never dereferenced: validation fails first
+    assert lib.fa_forward(C.byref(p), one, one, one, one, one, one, None, need_f, None) == _capi.FA_EINVAL_WORKSPACE
+    assert lib.fa_forward(C.byref(p), one, one, one, one, one, one, one, need_f - 1, None) == _capi.FA_EINVAL_WORKSPACE
+    assert lib.fa_backward(C.byref(p), *([one] * 10), None, need_b, None) == _capi.FA_EINVAL_WORKSPACE

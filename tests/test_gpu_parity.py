@@ -200,7 +200,7 @@ def test_host_training_step_keeps_forward_tensors_resident(dtype, shape, pipelin
             assert scaled_err(g, h.astype(np.float64)) <= 2e-3
         else:
             assert np.array_equal(g, h), name
-        assert scaled_err(g, ref[name]) <= TOL[np.dtype(dtype)] * (4 if dtype == np.float16 else 10), name
+        assert scaled_err(g, ref[name]) <= TOL[np.dtype(dtype)], name
 
 
 def test_readme_example_c1():
@@ -333,8 +333,7 @@ def test_kernels_write_only_inside_their_outputs(dtype, d, vd, nq, nk, rule):
     tol = {np.float16: 2e-3, np.float32: 1e-5, np.float64: 1e-12}[dtype]
     assert max_abs_err(g["O"].cpu().numpy(), ref["O"]) <= tol
     for name in ("dQ", "dK", "dV"):
-        gtol = tol * (4 if dtype == np.float16 else 10)
-        assert scaled_err(g[name].cpu().numpy(), ref[name]) <= gtol, name
+        assert scaled_err(g[name].cpu().numpy(), ref[name]) <= tol, name
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
@@ -400,3 +399,33 @@ def test_channel_last_activations_through_the_op(dtype):
     qcf = q.permute(0, 2, 3, 1).contiguous()
     ref = fa.causal_1d(qcf, qcf, qcf, "none_front").permute(0, 3, 1, 2).contiguous()
     assert torch.equal(O, ref)
+
+
+def test_c4_fp64_at_full_size():
+    """BASELINE.json configs[3], fp64 variant at full size: full_1d cross-attention Lq = 1024, Lk = 8192, scale_end,
+    head_dim 64 (two heads; the dense oracle holds the 1024 x 8192 logits in float64). Bar 1e-12 on O and gradients."""
+    _check(np.float64, 1, "full", "scale_end", 1, 0, 0, (1, 2), 64, 64, (1024,), (8192,), seed=64)
+
+
+def test_fp32_tensors_that_are_only_4_byte_aligned():
+    """A contiguous fp32 tensor whose base is offset by one float (a view into a larger buffer) is only 4-byte aligned:
+    the 3xTF32 forward reads Q, K, V with 16-byte vector loads, so the dispatch must decline it (generic kernels) instead
+    of faulting with a misaligned address, and the result must still match the oracle."""
+    rng = np.random.default_rng(8)
+    Q, K, V, dO = da.random_inputs(rng, np.float32, (2,), 64, 64, (256,), (320,))
+    ref = da.attention(Q, K, V, 1, "full", "none_front", dO=dO)
+
+    def off_by_one(x):
+        buf = torch.empty(x.size + 1, dtype=torch.float32, device="cuda")
+        view = buf[1:].view(x.shape)
+        view.copy_(torch.from_numpy(x))
+        assert view.data_ptr() % 16 == 4 and view.is_contiguous()
+        return view
+    tq, tk, tv = (off_by_one(x).requires_grad_(True) for x in (Q, K, V))
+    O = fa.full_1d(tq, tk, tv, "none_front")
+    torch.cuda.synchronize()
+    assert _capi.lib.fa_last_path() == 1, "misaligned fp32 inputs must not take the vector-load tensor-core path"
+    assert max_abs_err(O.detach().cpu().numpy(), ref["O"]) <= 1e-5
+    dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+    for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+        assert scaled_err(g.cpu().numpy(), ref[name]) <= 1e-5, name

@@ -28,10 +28,10 @@ def test_single_rank_ring_equals_plain_causal(dtype, d, seq, tol):
 
 
 @pytest.mark.parametrize("dtype,d,seq,tol", [(np.float16, 128, 2048, 2e-3), (np.float16, 64, 512, 2e-3),
-                                              (np.float32, 32, 384, 2e-5), (np.float64, 16, 256, 1e-11)])
+                                              (np.float32, 32, 384, 1e-5), (np.float64, 16, 256, 1e-12)])
 def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol):
     """ring_backward: blocks computed by fa_backward with global index bases and the final (O, l, m), summed with
-    fa_grad_accumulate / fa_grad_finalize. fp16 bar as in test_gpu_sm100.grad_tol (sqrt(n/128) growth)."""
+    fa_grad_accumulate / fa_grad_finalize. fp16 bar: the plain 2e-3 * max(1, |ref|)."""
     rng = np.random.default_rng(4)
     Q, K, V, dO = da.random_inputs(rng, dtype, (2, 2), d, d, (seq,), (seq,))
     ref = da.attention(Q, K, V, 1, "causal", "none_front", dO=dO)
@@ -40,7 +40,6 @@ def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol):
     dQ, dK, dV = ring.ring_causal_1d_backward(tq, tk, tv, O, l, m, tdo)
     if dtype == np.float16:
         assert _capi.lib.fa_last_path() == 2
-        tol = tol * max(1.0, float(np.sqrt(seq / 128.0)))
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
         err = np.abs(g.cpu().numpy().astype(np.float64) - ref[name]) / np.maximum(1.0, np.abs(ref[name]))
         assert err.max() <= tol, f"{name}: {err.max()}"

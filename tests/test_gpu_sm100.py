@@ -18,13 +18,10 @@ from tf_flash_attention_b200 import flash_attention as fa  # noqa: E402
 TOL = 2e-3  # BASELINE.json: fp16 max-abs on O and on the gradients (scaled by max(1,|ref|) for gradients)
 
 
-def grad_tol(n_terms):
-    """P and dS enter the tensor cores as fp16 (relative rounding 2^-11), so a gradient element that
-    sums n independent products carries a random-walk error ~ 2^-12 * sqrt(n) * |term|. The 2e-3 bar
-    is kept as is up to 128 terms per output and grows with sqrt(n / 128) beyond (worst measured:
-    4.2e-3 on dK at n = 1000 queries per key with only 88 keys, i.e. large P; 1.4e-3 on the C2 shape;
-    see DESIGN.md "Numerics"); at least 99.5 % of the elements must meet the plain 2e-3."""
-    return TOL * max(1.0, float(np.sqrt(n_terms / 128.0)))
+# fp16 gradients: one bar, BASELINE.json's 2e-3 (scaled by max(1, |ref|)). dS enters the tensor cores as a hi + lo pair
+# of fp16 values on every path but the fused head_dim-128 kernel (fa_set_grad_precision, include/fa_b200.h): with a
+# single fp16 rounding of dS the case "1000 queries x 88 keys" measured 4.2e-3 on dK (rows that attend one or two keys
+# have |dS| of several units) and 2135 heads x 64 x 64 measured 2.005e-3.
 
 
 def _run(dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=0, grads=True):
@@ -57,11 +54,10 @@ def _run(dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=0, grads=True):
         torch.cuda.synchronize()
         assert _capi.lib.fa_last_path() == 2, "backward did not take the tcgen05 path"
         nq, nk = int(np.prod(qs)), int(np.prod(ks))
-        for name, g, n_terms in (("dQ", dQ, nk), ("dK", dK, nq), ("dV", dV, nq)):
-            gn = g.cpu().numpy().astype(np.float64)
-            err = np.abs(gn - ref[name]) / np.maximum(1.0, np.abs(ref[name]))
-            assert err.max() <= grad_tol(n_terms), f"{name} {tag}: {err.max()}"
-            assert np.mean(err <= TOL) >= 0.995, f"{name} {tag}: {np.mean(err <= TOL)}"
+        for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+            err = scaled_err(g.cpu().numpy(), ref[name])
+            print(f"GRADERR {name} {tag}: {err:.3e}")
+            assert err <= TOL, f"{name} {tag}: {err}"
 
 
 CASES = [
@@ -109,8 +105,7 @@ def test_full_size_c2_one_head_vs_chunked_oracle():
         gn = g.cpu().numpy()[0].astype(np.float64)
         err = np.abs(gn - ref[name]) / np.maximum(1.0, np.abs(ref[name]))
         print(name, "max scaled err", err.max(), "frac within 2e-3", np.mean(err <= TOL))
-        assert err.max() <= grad_tol(8192), name
-        assert np.mean(err <= TOL) >= 0.995, name
+        assert err.max() <= TOL, name
 
 
 def test_full_size_properties_c2():
@@ -303,3 +298,68 @@ def test_fp32_3xtf32_forward_matches_oracle(case):
         err = scaled_err(g.cpu().numpy(), ref[name])
         print(name, err)
         assert err <= 1e-5, name
+
+
+def test_full_batch_c2_two_random_heads_vs_chunked_oracle():
+    """BASELINE.json configs[1] exactly as written — batch x heads 16 x 16, head_dim 128, seq 8192, causal, fwd + bwd in
+    ONE call over all 256 heads — spot-checked against the chunked oracle on two heads drawn at random (the oracle needs
+    ~10 s per head; the other heads are covered by the size-independent properties above)."""
+    g = torch.Generator(device="cuda").manual_seed(2026)
+    B0, B1, d, S = 16, 16, 128, 8192
+
+    def u():
+        return (torch.rand((B0, B1, d, S), generator=g, device="cuda") * 4 - 2).half()
+    Q, K, V, dO = u(), u(), u(), u()
+    tq, tk, tv = (x.requires_grad_(True) for x in (Q, K, V))
+    O = fa.causal_1d(tq, tk, tv, "none_front")
+    assert _capi.lib.fa_last_path() == 2
+    dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), dO)
+    assert _capi.lib.fa_last_path() == 2
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(99)
+    for h in rng.choice(B0 * B1, size=2, replace=False):
+        i, j = divmod(int(h), B1)
+        ref = da.forward_backward_chunked(*(x[i, j].detach().cpu().numpy() for x in (Q, K, V, dO)), (S,), (S,),
+                                          "none_front", "causal")
+        assert max_abs_err(O[i, j].detach().cpu().numpy(), ref["O"]) <= TOL, f"O head {h}"
+        for name, gr in (("dQ", dQ), ("dK", dK), ("dV", dV)):
+            err = scaled_err(gr[i, j].cpu().numpy(), ref[name])
+            print(f"GRADERR C2 full batch head {h} {name}: {err:.3e}")
+            assert err <= TOL, f"{name} head {h}: {err}"
+
+
+D128_SQUARE = [c for c in CASES if c[7] == 128 and c[8] == 128]
+
+
+@pytest.mark.parametrize("case", D128_SQUARE, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-w{c[3]}s{c[4]}c{c[5]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_grad_precision_1_head_dim128_split_operands(case):
+    """fa_set_grad_precision(1): head_dim 128 leaves the fused kernel for the two-kernel backward with dS as hi + lo
+    fp16 pairs; same bar."""
+    assert _capi.lib.fa_set_grad_precision(1) == 0
+    try:
+        _run(*case, seed=zlib.crc32(repr(case).encode()) % 1000)
+    finally:
+        _capi.lib.fa_set_grad_precision(0)
+
+
+def test_grad_precision_modes_on_the_large_ds_case():
+    """1000 queries x 88 keys, causal scale_end (rows that attend one or two keys: |dS| of several units). Mode 2 (dS as one
+    fp16 value) is the round-1 behaviour and misses the bar on dK; the default (hi + lo pairs) meets it with margin."""
+    case = (1, "causal", "scale_end", 1, 0, 0, (2,), 64, 64, (1000,), (88,))
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()) % 1000)
+    Q, K, V, dO = da.random_inputs(rng, np.float16, (2,), 64, 64, (1000,), (88,))
+    ref = da.attention(Q, K, V, 1, "causal", "scale_end", dO=dO)
+    errs = {}
+    for mode in (2, 0):
+        assert _capi.lib.fa_set_grad_precision(mode) == 0
+        try:
+            tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (Q, K, V))
+            O = fa.causal_1d(tq, tk, tv, "scale_end")
+            dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
+            errs[mode] = {n: scaled_err(g.cpu().numpy(), ref[n]) for n, g in (("dQ", dQ), ("dK", dK), ("dV", dV))}
+        finally:
+            _capi.lib.fa_set_grad_precision(0)
+    print("GRADERR modes", errs)
+    assert max(errs[0].values()) <= TOL
+    assert errs[0]["dK"] < 0.6 * errs[2]["dK"]
+    assert _capi.lib.fa_set_grad_precision(3) != 0

@@ -101,6 +101,7 @@ def _load():
         "fa_last_path": (C.c_int, []),
         "fa_launch_count": (i64, [C.c_int]),
         "fa_set_path_override": (None, [C.c_int]),
+        "fa_set_grad_precision": (C.c_int, [C.c_int]),
         "fa_kernel_timing": (None, [C.c_int]),
         "fa_kernel_timings": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
         "fa_version": (C.c_char_p, []),

@@ -19,6 +19,7 @@ static std::atomic<int64_t> g_launches{0};
 static thread_local int g_last_cuda = 0;
 static std::atomic<int> g_last_path{0};
 static std::atomic<int> g_path_override{0};
+static std::atomic<int> g_grad_precision{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- optional per-kernel timing ------------------------------------------------------------
@@ -40,7 +41,8 @@ ScopedKernel::ScopedKernel(const char* name, cudaStream_t stream) : stream_(stre
 ScopedKernel::~ScopedKernel() {
   if (slot_ < 0) return;
   std::lock_guard<std::mutex> g(g_timing_mu);
-  cudaEventRecord(g_timed[slot_].stop, stream_);
+  // fa_kernel_timings() on another thread may have drained the list since the constructor ran
+  if (size_t(slot_) < g_timed.size() && g_timed[slot_].stop) cudaEventRecord(g_timed[slot_].stop, stream_);
 }
 }  // namespace fa
 
@@ -72,6 +74,7 @@ int fill_args(const fa_problem_t* p, fa::LaunchArgs* a) {
   a->v_d = p->v_d;
   a->batch = p->batch;
   a->accumulate = p->accumulate;
+  a->grad_split = fa::g_grad_precision;
   // a key shard of a longer sequence (K/V ring): rows do not see all of their keys in this call
   a->partial_keys = (p->k_index_base != 0 || (p->k_full_len != 0 && p->k_full_len != a->rule.k.total)) ? 1 : 0;
   return 0;
@@ -113,6 +116,11 @@ int64_t fa_launch_count(int reset) {
   return reset ? fa::g_launches.exchange(0) : fa::g_launches.load();
 }
 void fa_set_path_override(int path) { fa::g_path_override = path; }
+int fa_set_grad_precision(int mode) {
+  if (mode < 0 || mode > 2) return FA_EINVAL_SHAPE;
+  fa::g_grad_precision = mode;
+  return FA_OK;
+}
 
 void fa_kernel_timing(int enable) { fa::g_timing.store(enable ? 1 : 0); }
 
@@ -164,7 +172,8 @@ int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* 
   if (rc) return rc;
   if (p->batch == 0) return FA_OK;
   if (!q || !k || !v || !o || !l || !m) return FA_EINVAL_NULL;
-  if (workspace_bytes < fa_workspace_bytes(p, 0)) return FA_EINVAL_WORKSPACE;
+  const size_t need = fa_workspace_bytes(p, 0);
+  if (workspace_bytes < need || (!workspace && need)) return FA_EINVAL_WORKSPACE;
   a.q = q; a.k = k; a.v = v; a.o = o; a.l = l; a.m = m;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
   a.variant = fa::g_path_override;
@@ -192,8 +201,8 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   if (rc) return rc;
   if (p->batch == 0) return FA_OK;
   if (!q || !k || !v || !o || !l || !m || !d_o || !d_q || !d_k || !d_v) return FA_EINVAL_NULL;
-  if (workspace_bytes < fa_workspace_bytes(p, 1) || (!workspace && fa_workspace_bytes(p, 1)))
-    return FA_EINVAL_WORKSPACE;
+  const size_t need = fa_workspace_bytes(p, 1);
+  if (workspace_bytes < need || (!workspace && need)) return FA_EINVAL_WORKSPACE;
   a.q = q; a.k = k; a.v = v; a.o = (void*)o; a.l = (void*)l; a.m = (void*)m; a.d_o = d_o;
   a.d_q = d_q; a.d_k = d_k; a.d_v = d_v;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes;
@@ -592,26 +601,55 @@ size_t fa_host_arena_bytes(const fa_problem_t* p, int is_backward) {
 namespace {
 // Host-buffer calls are pipelined over chunks of the batch on three streams: upload of chunk c+1,
 // compute of chunk c (on the caller's stream) and download of chunk c-1 overlap (PCIe is full duplex).
+// One pipe (two copy streams + a growing pool of events) is kept per (device, caller stream) for the life of the
+// process, so a host-buffer call creates nothing on the hot path.
 struct HostPipe {
   cudaStream_t in = nullptr, out = nullptr;
   std::vector<cudaEvent_t> ev;
-  ~HostPipe() {
-    for (auto e : ev) cudaEventDestroy(e);
-    if (in) cudaStreamDestroy(in);
-    if (out) cudaStreamDestroy(out);
-  }
-  cudaError_t init(int n_events) {
-    cudaError_t e = cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return e;
-    ev.resize(n_events);
-    for (auto& x : ev) {
-      x = nullptr;
-      e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
+  std::mutex busy;   // one host-buffer call at a time per (device, stream)
+  cudaError_t reserve(int n_events) {
+    cudaError_t e;
+    if (!in && (e = cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if (!out && (e = cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    while (int(ev.size()) < n_events) {
+      cudaEvent_t x = nullptr;
+      if ((e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming)) != cudaSuccess) return e;
+      ev.push_back(x);
     }
     return cudaSuccess;
+  }
+};
+std::mutex g_pipes_mu;
+std::vector<std::pair<std::pair<int, cudaStream_t>, HostPipe*>> g_pipes;
+HostPipe* pipe_for(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> g(g_pipes_mu);
+  for (auto& kv : g_pipes)
+    if (kv.first.first == dev && kv.first.second == st) return kv.second;
+  g_pipes.push_back({{dev, st}, new HostPipe()});
+  return g_pipes.back().second;
+}
+// Holds the pipe for one call. Whatever way the call returns, no copy may still be reading or writing the caller's host
+// buffers afterwards: the destructor drains the three streams unless the normal path already did.
+struct PipeLease {
+  HostPipe* pipe;
+  cudaStream_t st;
+  bool drained = false;
+  PipeLease(HostPipe* p, cudaStream_t s) : pipe(p), st(s) { pipe->busy.lock(); }
+  ~PipeLease() {
+    if (!drained) {
+      if (pipe->in) cudaStreamSynchronize(pipe->in);
+      cudaStreamSynchronize(st);
+      if (pipe->out) cudaStreamSynchronize(pipe->out);
+    }
+    pipe->busy.unlock();
+  }
+  cudaError_t drain() {
+    cudaError_t e = cudaStreamSynchronize(pipe->out);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    drained = true;
+    return e != cudaSuccess ? e : e2;
   }
 };
 int64_t pick_chunks(const fa_problem_t* p, size_t total_bytes) {
@@ -632,8 +670,11 @@ int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const v
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t B = p->batch;
   const int64_t nch = pick_chunks(p, a.nq_b + a.nk_b + a.nv_b + a.no_b);
-  HostPipe pipe;
-  FA_CU(pipe.init(int(2 * nch + 1)));
+  HostPipe* pp = pipe_for(st);
+  if (!pp) return FA_ENODEVICE;
+  PipeLease lease(pp, st);
+  HostPipe& pipe = *pp;
+  FA_CU(pipe.reserve(int(2 * nch + 1)));
   FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));          // uploads start after prior work on `stream`
   FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
   const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
@@ -660,8 +701,7 @@ int fa_forward_host(const fa_problem_t* p, const void* q, const void* k, const v
     FA_CU(cudaMemcpyAsync((char*)l + b0 * sl, base + a.l + b0 * sl, nb * sl, cudaMemcpyDeviceToHost, pipe.out));
     FA_CU(cudaMemcpyAsync((char*)m + b0 * sm, base + a.m + b0 * sm, nb * sm, cudaMemcpyDeviceToHost, pipe.out));
   }
-  FA_CU(cudaStreamSynchronize(pipe.out));
-  FA_CU(cudaStreamSynchronize(st));
+  FA_CU(lease.drain());
   return FA_OK;
 }
 
@@ -683,8 +723,11 @@ int backward_host_impl(const fa_problem_t* p, bool resident, const void* q, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t B = p->batch;
   const int64_t nch = pick_chunks(p, 2 * (a.nq_b + a.nk_b + a.nv_b + a.no_b));
-  HostPipe pipe;
-  FA_CU(pipe.init(int(2 * nch + 1)));
+  HostPipe* pp = pipe_for(st);
+  if (!pp) return FA_ENODEVICE;
+  PipeLease lease(pp, st);
+  HostPipe& pipe = *pp;
+  FA_CU(pipe.reserve(int(2 * nch + 1)));
   FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));
   FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
   const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
@@ -713,8 +756,7 @@ int backward_host_impl(const fa_problem_t* p, bool resident, const void* q, cons
     FA_CU(cudaMemcpyAsync((char*)d_k + b0 * sk, base + a.d_k + b0 * sk, nb * sk, cudaMemcpyDeviceToHost, pipe.out));
     FA_CU(cudaMemcpyAsync((char*)d_v + b0 * sv, base + a.d_v + b0 * sv, nb * sv, cudaMemcpyDeviceToHost, pipe.out));
   }
-  FA_CU(cudaStreamSynchronize(pipe.out));
-  FA_CU(cudaStreamSynchronize(st));
+  FA_CU(lease.drain());
   return FA_OK;
 }
 }  // namespace
@@ -751,8 +793,11 @@ int fa_forward_backward_host(const fa_problem_t* p, const void* q, const void* k
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t B = p->batch;
   const int64_t nch = p->batch < 2 || a.nq_b + a.nk_b + a.nv_b + a.no_b < (size_t(64) << 20) ? 1 : std::min<int64_t>(B, 16);
-  HostPipe pipe;
-  FA_CU(pipe.init(int(2 * nch + 1)));
+  HostPipe* pp = pipe_for(st);
+  if (!pp) return FA_ENODEVICE;
+  PipeLease lease(pp, st);
+  HostPipe& pipe = *pp;
+  FA_CU(pipe.reserve(int(2 * nch + 1)));
   FA_CU(cudaEventRecord(pipe.ev[2 * nch], st));
   FA_CU(cudaStreamWaitEvent(pipe.in, pipe.ev[2 * nch], 0));
   const size_t sq = a.nq_b / B, sk = a.nk_b / B, sv = a.nv_b / B, so = a.no_b / B, sl = a.nl_b / B, sm = a.nm_b / B;
@@ -782,8 +827,7 @@ int fa_forward_backward_host(const fa_problem_t* p, const void* q, const void* k
     FA_CU(cudaMemcpyAsync((char*)d_k + b0 * sk, base + a.d_k + b0 * sk, nb * sk, cudaMemcpyDeviceToHost, pipe.out));
     FA_CU(cudaMemcpyAsync((char*)d_v + b0 * sv, base + a.d_v + b0 * sv, nb * sv, cudaMemcpyDeviceToHost, pipe.out));
   }
-  FA_CU(cudaStreamSynchronize(pipe.out));
-  FA_CU(cudaStreamSynchronize(st));
+  FA_CU(lease.drain());
   return FA_OK;
 }
 

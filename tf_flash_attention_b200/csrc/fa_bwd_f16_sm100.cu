@@ -37,6 +37,18 @@ constexpr int kBwdThreads = 384;
 constexpr float kLog2eB = 1.4426950408889634f;
 constexpr int kStatPad = 64;    // padding (floats) behind the LSE2 / D arrays for the bulk copies
 
+// dS enters the tensor cores as fp16. |dS| = P |dP - D| reaches several units on rows that attend few keys, where one
+// fp16 rounding (relative 2^-11) is already ~1e-3 absolute, and dK / dQ sum such terms. With SPLIT the softmax warps
+// hand over dS as a hi + lo pair of fp16 values (lo = fp16(dS - hi), written into the TMEM columns the packed hi half
+// leaves free) and the products dQ = dS K, dK = dS^T Q are issued twice, so dS carries ~22 mantissa bits.
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 struct alignas(64) BwdParams {
   CUtensorMap map_q, map_k, map_v, map_do;   // SW128 loads, box 64 x channels
   CUtensorMap map_dq, map_dk, map_dv;        // plain stores, box 64 x channels
@@ -103,7 +115,7 @@ struct DqCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD>
+template <int D, int VD, bool SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DqCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -223,6 +235,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + ks * 8,
                    smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // dS lo halves: the 32 columns behind the packed hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + 32 + ks * 8,
+                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+          }
         };
         if (n > 0) {
           mbar_wait(bar_kv_full + 0, 0);
@@ -304,7 +322,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       tmem_ld32f(t_dp, &dp[0]);
       tmem_ld32f(t_dp + 32, &dp[32]);
       tmem_wait_ld();
-      uint32_t pk[32];
+      uint32_t pk[32], pl[SPLIT ? 32 : 1];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
         const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
@@ -312,9 +330,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
         float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
         p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
         p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
-        pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
+        if constexpr (SPLIT)
+          split_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), pk[c >> 1], pl[c >> 1]);
+        else
+          pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
       }
       tmem_st32(t_s, pk);
+      if constexpr (SPLIT) tmem_st32(t_s + 32, pl);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * i);
@@ -375,7 +397,7 @@ struct DqSmallCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD>
+template <int D, int VD, bool SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DqSmallCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -492,6 +514,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
                    smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // the lo halves sit 16 columns behind their hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
+                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+          }
         };
         if (n > 0) {
           mbar_wait(bar_kv_full + 0, 0);
@@ -557,16 +585,20 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
       tmem_ld32f(t_s, s);
       tmem_ld32f(t_s + 64, dp);
       tmem_wait_ld();
-      uint32_t pk[16];
+      uint32_t pk[16], pl[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         float p0 = ex2(fmaf(s[c], scale_log2, -lse2));
         float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
         p0 = (okmask >> c) & 1u ? p0 : 0.f;
         p1 = (okmask >> (c + 1)) & 1u ? p1 : 0.f;
-        pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
+        if constexpr (SPLIT)
+          split_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), pk[c >> 1], pl[c >> 1]);
+        else
+          pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
       }
       tmem_st16(t_s, pk);
+      if constexpr (SPLIT) tmem_st16(t_s + 16, pl);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready);
@@ -635,7 +667,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                : "memory");
 }
 
-template <int D, int VD>
+template <int D, int VD, bool SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DkvCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -761,6 +793,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(q_s + ks * 32, 16, 1024),
                    idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // dS^T lo halves: the 32 columns behind the packed hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + 32 + ks * 8,
+                     smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, 1u);
+          }
         };
         if (n > 0) {
           mbar_wait(bar_kv_res, 0);
@@ -841,7 +879,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       tmem_wait_ld();
       const float* lse_s = stat_gen + st * (2 * kBN);
       const float* dsum_s = lse_s + kBN;
-      uint32_t pk[32], dk[32];
+      uint32_t pk[32], dk[32], dl[SPLIT ? 32 : 1];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
         const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
@@ -850,10 +888,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
         p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
         p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
         pk[c >> 1] = pack_half2(p0, p1);
-        dk[c >> 1] = pack_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]));
+        if constexpr (SPLIT)
+          split_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]), dk[c >> 1], dl[c >> 1]);
+        else
+          dk[c >> 1] = pack_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]));
       }
       tmem_st32(t_s, pk);
       tmem_st32(t_dp, dk);
+      if constexpr (SPLIT) tmem_st32(t_dp + 32, dl);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * x);
@@ -923,7 +965,7 @@ struct DkvSmallCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD>
+template <int D, int VD, bool SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DkvSmallCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -1052,6 +1094,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
                    smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // dS^T lo halves, 16 columns behind the hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
+                     smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, 1u);
+          }
         };
         if (n > 0) {
           mbar_wait(bar_kv_res, 0);
@@ -1121,7 +1169,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
       tmem_wait_ld();
       const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN) + x * 32);
       const float4* dsum4 = lse4 + kBN / 4;
-      uint32_t pk[16], dk[16];
+      uint32_t pk[16], dk[16], dl[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const uint32_t mword = okmask >> c;
@@ -1137,11 +1185,17 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
         p3 = mword & 8u ? p3 : 0.f;
         pk[c >> 1] = pack_half2(p0, p1);
         pk[(c >> 1) + 1] = pack_half2(p2, p3);
-        dk[c >> 1] = pack_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y));
-        dk[(c >> 1) + 1] = pack_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w));
+        if constexpr (SPLIT) {
+          split_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y), dk[c >> 1], dl[c >> 1]);
+          split_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w), dk[(c >> 1) + 1], dl[(c >> 1) + 1]);
+        } else {
+          dk[c >> 1] = pack_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y));
+          dk[(c >> 1) + 1] = pack_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w));
+        }
       }
       tmem_st16(t_s, pk);          // P^T  over the first 16 columns of this half of S^T
       tmem_st16(t_s + 64, dk);     // dS^T over the first 16 columns of this half of dP^T
+      if constexpr (SPLIT) tmem_st16(t_s + 64 + 16, dl);   // dS^T lo halves over the next 16
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready);
@@ -1682,6 +1736,10 @@ template <int D, int VD>
 cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   BwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
+  // fa_set_grad_precision: 1 = dS as hi + lo fp16 pairs everywhere (head_dim 128 then runs the two-kernel backward),
+  // 2 = never, 0 = automatic: on for every path but the fused head_dim-128 kernel, whose TMEM has no room for the lo
+  // halves and whose shapes (long rows, small P) measure inside the 2e-3 bar without them
+  const bool split = a.grad_split == 1 || (a.grad_split == 0 && D != 128);
   float* lse2 = reinterpret_cast<float*>(a.workspace);
   float* dsum = lse2 + (a.batch * int64_t(nq) + kStatPad);
   if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
@@ -1710,7 +1768,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   if constexpr (D == 128) {
-    if (a.variant != 4) {
+    if (a.variant != 4 && !split) {
       // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics
       float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + stats_bytes(a.batch, nq));
       const size_t acc_bytes = size_t(a.batch) * D * nq * sizeof(float);
@@ -1746,7 +1804,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   bool dq_done = false;
   if constexpr (D == 64 && VD == 64) {
     if (a.variant != 4) {
-      auto kern = bwd_dq_small_kernel<D, VD>;
+      auto kern = split ? bwd_dq_small_kernel<D, VD, true> : bwd_dq_small_kernel<D, VD, false>;
       cudaError_t e =
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
@@ -1759,7 +1817,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     }
   }
   if (!dq_done) {
-    auto kern = bwd_dq_kernel<D, VD>;
+    auto kern = split ? bwd_dq_kernel<D, VD, true> : bwd_dq_kernel<D, VD, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nq + 2 * kBM - 1) / (2 * kBM);
@@ -1770,7 +1828,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   }
   if constexpr (D == 64 && VD == 64) {
     if (a.variant != 4) {
-      auto kern = bwd_dkdv_small_kernel<D, VD>;
+      auto kern = split ? bwd_dkdv_small_kernel<D, VD, true> : bwd_dkdv_small_kernel<D, VD, false>;
       cudaError_t e =
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
@@ -1781,7 +1839,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     }
   }
   {
-    auto kern = bwd_dkdv_kernel<D, VD>;
+    auto kern = split ? bwd_dkdv_kernel<D, VD, true> : bwd_dkdv_kernel<D, VD, false>;
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;

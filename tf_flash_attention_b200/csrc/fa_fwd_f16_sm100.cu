@@ -57,14 +57,14 @@ __device__ long long* g_dbg = nullptr;
 // BN = 64 with head_dim 64 needs 256 TMEM columns and ~66 KB of shared memory, so two CTAs share an SM
 // (MINB = 2): short sequences and narrow windows are latency chains per CTA (prologue, 2-3 tiles, epilogue)
 // and HBM-bound overall, and only a second resident CTA hides those chains.
-// VAR: experimental variants of the softmax / MMA hand-off, selectable with fa_set_path_override for A/B runs (bit 0:
-// row max as four independent chains instead of one; bit 1: P is handed to the MMA warp in two halves, so P V of keys
-// 0..63 runs while the exponentials of keys 64..127 are still being computed; bit 2 (needs bit 1): the upper half of the
-// next Q K^T, S columns 64..127 that P does not alias, is issued as soon as the softmax warps hold the S row in
-// registers, by an MMA issuer that polls the barriers of both warpgroups instead of waiting on them in a fixed order).
-// VAR = 0 is the measured default; its instantiations are unaffected by the variants (`if constexpr`).
-template <int D, int VD, int BN, int VAR = 0>
+// Softmax / MMA hand-off (round-2 A/B on B200, profiles/r2_fwd_variants.md; all variants bit-equal in O, l, m):
+// the row max runs as four independent chains (a single chain is 63 dependent FMNMX3), and with 128-key tiles P is
+// handed to the MMA warp in two halves, so P V of keys 0..63 runs while the exponentials of keys 64..127 are still
+// being computed (C2 forward 1024 -> 1083 TFLOPS). The event-driven issuer that also issued the upper half of the next
+// Q K^T early measured slower (953 TFLOPS) and was removed.
+template <int D, int VD, int BN>
 struct FwdCfg {
+  static constexpr bool kHalves = BN == 128;               // P handed over in two 64-key halves
   static constexpr int kCh = D > VD ? D : VD;
   static constexpr int kQTileBytes = kBlockM * kCh * 2;   // doubles as the O staging tile
   static constexpr int kStageBytes = BN * kCh * 2;
@@ -72,15 +72,14 @@ struct FwdCfg {
   static constexpr int kColsUsed = kColO + kQTiles * VD;
   static constexpr int kTmemCols = kColsUsed <= 256 ? 256 : 512;
   static constexpr int kBarOffset = kQTiles * kQTileBytes + kStages * kStageBytes;
-  static_assert((VAR & 4) == 0 || (VAR & 2) != 0, "the early upper-half Q K^T builds on the two-halves hand-off");
-  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2 + ((VAR & 2) ? 2 : 0) + ((VAR & 4) ? 2 : 0);
+  static constexpr int kNumBars = 2 + 2 * kStages + 2 + 2 + 2 + (kHalves ? 2 : 0);
   static constexpr int kSchedOffset = kBarOffset + kNumBars * 8 + 16;
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;  // + alignment slack
 };
 
-template <int D, int VD, int BN, int MINB, int VAR = 0>
+template <int D, int VD, int BN, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_constant__ FwdParams p) {
-  using Cfg = FwdCfg<D, VD, BN, VAR>;
+  using Cfg = FwdCfg<D, VD, BN>;
   constexpr int kBlockN = BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -94,8 +93,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
   const uint32_t bar_s_full = bar_kv_empty + 8 * kStages;  // [2]
   const uint32_t bar_p_ready = bar_s_full + 16;            // [2]
   const uint32_t bar_o_final = bar_p_ready + 16;           // [2]
-  const uint32_t bar_p_half = bar_o_final + 16;            // [2], VAR & 2 only
-  const uint32_t bar_s_cons = bar_p_half + 16;             // [2], VAR & 4 only
+  const uint32_t bar_p_half = bar_o_final + 16;            // [2], two-halves hand-off only
   const uint32_t tmem_slot = bars + Cfg::kNumBars * 8;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOffset + Cfg::kNumBars * 8);
 
@@ -132,8 +130,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         mbar_init(bar_s_full + 8 * i, 1);
         mbar_init(bar_p_ready + 8 * i, kBlockM);
         mbar_init(bar_o_final + 8 * i, 1);
-        if constexpr ((VAR & 2) != 0) mbar_init(bar_p_half + 8 * i, kBlockM);
-        if constexpr ((VAR & 4) != 0) mbar_init(bar_s_cons + 8 * i, kBlockM);
+        if constexpr (Cfg::kHalves) mbar_init(bar_p_half + 8 * i, kBlockM);
       }
       for (int s = 0; s < kStages; ++s) {
         mbar_init(bar_kv_full + 8 * s, 1);
@@ -208,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mma_ss(tmem_base + i * kBlockN, da, db, idesc_qk, ks > 0);
           }
         };
-        auto issue_pv_half = [&](int i, int stage, bool accumulate, int half) {   // VAR & 2: keys 64 * half .. + 63
+        auto issue_pv_half = [&](int i, int stage, bool accumulate, int half) {   // keys 64 * half .. + 63
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = half * (kBlockN / 32); ks < (half + 1) * (kBlockN / 32); ++ks) {
@@ -227,17 +224,6 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
                    (accumulate || ks > 0) ? 1u : 0u);
           }
         };
-        auto issue_qk_half = [&](int i, int stage, int half) {   // VAR & 4: keys 64 * half .. + 63 -> S columns 64 * half ..
-          constexpr uint32_t idesc_qk_half = idesc_f16(kBlockM, 64, true, true);
-          const uint32_t a0 = q_smem + i * Cfg::kQTileBytes;
-          const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes + half * (D * 128);
-#pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint64_t da = smem_desc_sw128(a0 + ks * 2048, D * 128, 1024);
-            const uint64_t db = smem_desc_sw128(b0 + ks * 2048, D * 128, 1024);
-            mma_ss(tmem_base + i * kBlockN + half * 64, da, db, idesc_qk_half, ks > 0);
-          }
-        };
         if (n > 0) {
           mbar_wait(bar_kv_full + 0, 0);
           for (int i = 0; i < kQTiles; ++i) {
@@ -247,68 +233,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mma_commit(bar_s_full + 8 * i);
           }
           mma_commit(bar_kv_empty + 0);
-          if constexpr ((VAR & 4) != 0) {
-            // Event-driven issue. Ring slot of K_j is t = 2j, of V_j t = 2j + 1. Per warpgroup and tile j, in order:
-            //   A  S row of tile j in registers (s_cons) and K_{j+1} landed -> upper half of Q K_{j+1}^T
-            //   B  first half of P_j stored (p_half) and V_j landed          -> P V over keys 0..63
-            //   C  all of P_j stored (p_ready)                                -> P V over keys 64..127, then the lower
-            //      half of Q K_{j+1}^T (its S columns alias P_j; the tensor pipe executes in issue order) + commit
-            // A warpgroup's next step is taken whenever its barrier (and stage) tests ready; a ring stage is released
-            // once both warpgroups have issued their last MMA on it (the commit covers every MMA issued before it).
-            int tile[2] = {0, 0}, step[2] = {0, 0};
-            uint32_t v_uses = 0, k_uses = 0;   // 4-bit use counters per (tile & 3), packed: stays in registers
-            auto stage_ready = [&](int t) { return mbar_test_wait(bar_kv_full + 8 * (t % kStages), (t / kStages) & 1); };
-            while (tile[0] < n || tile[1] < n) {
-#pragma unroll
-              for (int i = 0; i < kQTiles; ++i) {
-                const int j = tile[i];
-                if (j >= n) continue;
-                if (step[i] == 0) {
-                  if (j + 1 >= n) {
-                    step[i] = 1;
-                  } else if (mbar_test_wait(bar_s_cons + 8 * i, j & 1) && stage_ready(2 * j + 2)) {
-                    tc_fence_after();
-                    issue_qk_half(i, (2 * j + 2) % kStages, 1);
-                    step[i] = 1;
-                  }
-                } else if (step[i] == 1) {
-                  if (mbar_test_wait(bar_p_half + 8 * i, j & 1) && stage_ready(2 * j + 1)) {
-                    tc_fence_after();
-                    issue_pv_half(i, (2 * j + 1) % kStages, j > 0, 0);
-                    step[i] = 2;
-                  }
-                } else if (mbar_test_wait(bar_p_ready + 8 * i, j & 1)) {
-                  tc_fence_after();
-                  issue_pv_half(i, (2 * j + 1) % kStages, true, 1);
-                  const int sh = 4 * (j & 3);
-                  v_uses += 1u << sh;
-                  if (((v_uses >> sh) & 15u) == uint32_t(kQTiles)) {
-                    v_uses &= ~(15u << sh);
-                    mma_commit(bar_kv_empty + 8 * ((2 * j + 1) % kStages));
-                  }
-                  if (j + 1 < n) {
-                    issue_qk_half(i, (2 * j + 2) % kStages, 0);
-                    mma_commit(bar_s_full + 8 * i);
-                    k_uses += 1u << sh;
-                    if (((k_uses >> sh) & 15u) == uint32_t(kQTiles)) {
-                      k_uses &= ~(15u << sh);
-                      mma_commit(bar_kv_empty + 8 * ((2 * j + 2) % kStages));
-                    }
-                  } else {
-                    mma_commit(bar_o_final + 8 * i);
-                  }
-                  tile[i] = j + 1;
-                  step[i] = 0;
-                }
-              }
-            }
-          } else
           for (int j = 0; j < n; ++j) {
             const int tv = 2 * j + 1, sv = tv % kStages;
             const int tk = 2 * j + 2, sk = tk % kStages;
             mbar_wait(bar_kv_full + 8 * sv, (tv / kStages) & 1);
             for (int i = 0; i < kQTiles; ++i) {
-              if constexpr ((VAR & 2) != 0) {
+              if constexpr (Cfg::kHalves) {
                 mbar_wait(bar_p_half + 8 * i, j & 1);
                 tc_fence_after();
                 issue_pv_half(i, sv, j > 0, 0);
@@ -397,33 +327,21 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
 #pragma unroll
       for (int c = 0; c < kBlockN / 32; ++c) tmem_ld32f(t_s + c * 32, &s[c * 32]);
       tmem_wait_ld();
-      if constexpr ((VAR & 4) != 0) {
-        tc_fence_before();
-        mbar_arrive(bar_s_cons + 8 * i);   // S columns 64..127 may be overwritten by the next tile's upper half
-      }
       if (masked) {
 #pragma unroll
         for (int c = 0; c < kBlockN; ++c) s[c] = (okm[c >> 5] >> (c & 31)) & 1u ? s[c] : NEG_INF;
       }
       if (r == 0) FA_STAMP(i, j, 1);
-      float mx;
-      if constexpr ((VAR & 1) != 0) {
-        // four independent chains (each still fuses into 3-input max instructions): the single chain is 63 dependent
-        // FMNMX3, i.e. latency-bound with only two softmax warps per scheduler
-        float m4[4] = {s[0], s[1], s[2], s[3]};
+      // row max as four independent chains (each still fuses into 3-input max instructions)
+      float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int c = 4; c + 8 <= kBlockN; c += 8) {
+      for (int c = 4; c + 8 <= kBlockN; c += 8) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) m4[e] = fmaxf(fmaxf(m4[e], s[c + e]), s[c + 4 + e]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], s[kBlockN - 4 + e]);
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      } else {
-        mx = s[0];
-#pragma unroll
-        for (int c = 1; c < kBlockN; ++c) mx = fmaxf(mx, s[c]);
+        for (int e = 0; e < 4; ++e) m4[e] = fmaxf(fmaxf(m4[e], s[c + e]), s[c + 4 + e]);
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], s[kBlockN - 4 + e]);
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
@@ -449,8 +367,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
       const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
       // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
       float sum0 = 0.f, sum1 = 0.f;
-      if constexpr ((VAR & 2) != 0) {
-        static_assert((VAR & 2) == 0 || BN == 128, "the two-halves hand-off is written for 128-key tiles");
+      if constexpr (Cfg::kHalves) {
         auto exp_chunk = [&](int c, uint32_t* pk) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -575,9 +492,9 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
-template <int D, int VD, int BN, int MINB, int VAR = 0>
+template <int D, int VD, int BN, int MINB>
 cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
-  using Cfg = FwdCfg<D, VD, BN, VAR>;
+  using Cfg = FwdCfg<D, VD, BN>;
   FwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
   if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
@@ -593,7 +510,7 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
   p.batch = int32_t(a.batch);
   p.scale_log2 = kLog2e / sqrtf(float(D));
-  auto kern = fwd_kernel<D, VD, BN, MINB, VAR>;
+  auto kern = fwd_kernel<D, VD, BN, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   ScopedKernel timed(BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64", stream);
@@ -633,15 +550,9 @@ size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
 // 128-key / one-CTA configuration reachable for A/B runs.
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
   if (a.d == 128 && a.v_d == 128) {
-    // developer A/B variants of the softmax / MMA hand-off (see FwdCfg); not measured yet, never taken by default
-    if (a.variant == 10) return sm100::launch_fwd<128, 128, 128, 1, 1>(a, stream);
-    if (a.variant == 11) return sm100::launch_fwd<128, 128, 128, 1, 2>(a, stream);
-    if (a.variant == 12) return sm100::launch_fwd<128, 128, 128, 1, 3>(a, stream);
-    if (a.variant == 13) return sm100::launch_fwd<128, 128, 128, 1, 7>(a, stream);
     return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
   }
   if (a.d == 64 && a.v_d == 64) {
-    if (a.variant == 10) return sm100::launch_fwd<64, 64, 64, 2, 1>(a, stream);   // row max as four chains (A/B, unmeasured)
     if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
     return sm100::launch_fwd<64, 64, 128, 1>(a, stream);
   }

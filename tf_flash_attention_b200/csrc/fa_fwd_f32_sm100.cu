@@ -479,6 +479,8 @@ bool sm100_f32_forward_supports(const LaunchArgs& a) {
   if (nq % 4 || nk % 4) return false;  // TMA: row pitch must be a multiple of 16 bytes
   if (nk > int64_t(sm100::kF32BlockN) * 32 * sm100::kMaxTileWords) return false;
   if ((reinterpret_cast<uintptr_t>(a.o) & 15) || (reinterpret_cast<uintptr_t>(a.workspace) & 255)) return false;
+  // split_tf32_kernel reads the caller's Q, K, V with 16-byte vector loads
+  if ((reinterpret_cast<uintptr_t>(a.q) & 15) || (reinterpret_cast<uintptr_t>(a.k) & 15) || (reinterpret_cast<uintptr_t>(a.v) & 15)) return false;
   if (a.workspace_bytes < sm100_f32_forward_workspace_bytes(a)) return false;
   if (((nq + 127) / 128) * a.batch > 0x7fffffffLL) return false;
   return true;

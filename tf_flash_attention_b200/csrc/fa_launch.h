@@ -24,6 +24,7 @@ struct LaunchArgs {
   void* workspace;
   size_t workspace_bytes;
   int32_t partial_keys;  // the call covers a shard of the keys only (ring): no per-row renormalisation in the backward
+  int32_t grad_split;  // fp16 backward: dS handed to the tensor cores as hi + lo fp16 pairs (fa_set_grad_precision)
   int32_t variant;  // fa_set_path_override value (0 auto; 4 = fp16 backward as two kernels; 5 / 6 = forward tile configuration)
 };
 

@@ -76,7 +76,7 @@ def main():
     for variant in (0, 10, 11, 12, 13, 0):
         try:
             r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}, str(variant)], capture_output=True,
-                               text=True, timeout=60)
+                               text=True, timeout=240)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]
         except subprocess.TimeoutExpired:
             line = json.dumps({"variant": variant, "error": "timeout (hung kernel?)"})
