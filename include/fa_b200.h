@@ -229,12 +229,19 @@ int fa_kernel_timings(int max_entries, const char** names, float* ms);
  * tiles and one CTA per SM instead of 64-key tiles and two CTAs per SM. Developer A/B values:
  * 7 / 8 / 9 = element-wise kernels of fa_layout_transpose (pairs / singles / quads of halves). */
 void fa_set_path_override(int path);
-/* Precision of the fp16 gradients. The fp16 backward hands P and dS to the tensor cores as fp16; |dS| reaches
- * several units on rows that attend few keys, where one fp16 rounding is ~1e-3 absolute. mode 0 (default, automatic):
- * dS goes in as a hi + lo pair of fp16 values (two products for dQ and dK) on every path except the fused
- * head_dim-128 kernel; mode 1: everywhere (head_dim 128 then runs the two-kernel backward); mode 2: nowhere.
+/* Precision of the fp16 gradients. The plain fp16 backward hands P and dS to the tensor cores as single fp16 values
+ * and takes D = rowsum(dO o O) from the fp16 O it is given; where rows attend few keys (P ~ 1) each of the three costs
+ * up to ~1e-3 per term, and a key that collects many such rows ends above the 2e-3 bar (4.2e-3 measured at 1000
+ * queries x 88 keys). The "precise" kernels pass P and dS as hi + lo pairs of fp16 values (two tensor-core products
+ * each) and re-derive D exactly as rowsum(P o dP) inside the dQ kernel: gradients within ~5e-4 (the fp16 rounding of the
+ * result itself) on those cases, for ~12 % more time on HBM-bound problems.
+ *   mode 0 (default): automatic; precise where every row attends at most 32 keys, and under causal rules where the
+ *          sequence is short (<= 128 keys) or has >= 4 queries per key; the plain kernels elsewhere (long rows, small P;
+ *          the fused head_dim-128 kernel always: its TMEM has no room for the lo halves);
+ *   mode 1: precise everywhere (head_dim 128 then runs the two-kernel backward, with the hi + lo operands but D from O);
+ *   mode 2: never (round-1 behaviour).
  * The reference accumulates these products in fp16 altogether (flash_attention.cu:284-286); no counterpart there.
- * Returns FA_OK or FA_EINVAL_SHAPE for an unknown mode.                                                    */
+ * Returns FA_OK or FA_EINVAL_SHAPE for an unknown mode.                                                         */
 int fa_set_grad_precision(int mode);
 const char* fa_version(void);
 

@@ -44,12 +44,15 @@ def _call(dims, rule, Q, K, V, sync_mode, w, s, c):
     return (fa.local_1d if dims == 1 else fa.local_2d)(Q, K, V, w, s, c, sync_mode, returning_l_m=True)
 
 
-def _check(dtype, dims, rule, sync_mode, w, s, c, batch, d, v_d, qs, ks, seed, check_grad=True):
+def _check(dtype, dims, rule, sync_mode, w, s, c, batch, d, v_d, qs, ks, seed, check_grad=True, expect_path=None):
     rng = np.random.default_rng(seed)
     Q, K, V, dO = da.random_inputs(rng, dtype, batch, d, v_d, qs, ks)
     ref = da.attention(Q, K, V, dims, rule, sync_mode, w, s, c, dO=dO if check_grad else None)
     tq, tk, tv = (torch.from_numpy(x).cuda().requires_grad_(check_grad) for x in (Q, K, V))
     O, l, m = _call(dims, rule, tq, tk, tv, sync_mode, w, s, c)
+    if expect_path is not None:
+        torch.cuda.synchronize()
+        assert _capi.lib.fa_last_path() == expect_path, f"forward path {_capi.lib.fa_last_path()} != {expect_path}"
     tol = TOL[np.dtype(dtype)]
     tag = f"{np.dtype(dtype).name} {dims}d {rule} {sync_mode} w{w} s{s} c{c} b{batch} d{d} vd{v_d} q{qs} k{ks}"
     assert O.dtype == NP2T[dtype] and m.dtype == NP2T[dtype]
@@ -76,6 +79,9 @@ def _check(dtype, dims, rule, sync_mode, w, s, c, batch, d, v_d, qs, ks, seed, c
         return
     tdO = torch.from_numpy(dO).cuda()
     dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), tdO)
+    if expect_path is not None:
+        torch.cuda.synchronize()
+        assert _capi.lib.fa_last_path() == expect_path, f"backward path {_capi.lib.fa_last_path()} != {expect_path}"
     for name, got in (("dQ", dQ), ("dK", dK), ("dV", dV)):
         g = got.cpu().numpy()
         err = scaled_err(g, ref[name]) if dtype == np.float16 else max_abs_err(g, ref[name])
@@ -126,7 +132,29 @@ def test_reference_matrix_random_shapes(dims, attn, sync_mode, dtype):
                 w = int(rng.integers(1, max(2, big // 4)))
                 s = int(rng.integers(1, 4)) if cfg["strided"] else 0
             c = cfg["is_causal"]
-        _check(dtype, dims, cfg["rule"], sync_mode, w, s, c, batch, d, d, qs, ks, seed + run)
+        # fp16: the reference's own shape distribution (channels 8..32, arbitrary even lengths) runs on the tensor cores
+        _check(dtype, dims, cfg["rule"], sync_mode, w, s, c, batch, d, d, qs, ks, seed + run,
+               expect_path=2 if dtype == np.float16 else None)
+
+
+@pytest.mark.parametrize("case", [
+    # dims rule mode w s c batch d vd q k: channel counts and lengths the 64 / 128-channel kernels reach through the 3-D
+    # tensor maps (zero fill / clipping) and the pitch-padding pack pass (lengths that are not multiples of 8)
+    (1, "causal", "scale_end", 1, 0, False, (2, 1, 2), 24, 9, (77,), (131,)),        # odd lengths, v_d != d
+    (1, "full", "none_front", 1, 0, False, (3,), 8, 8, (300,), (258,)),
+    (1, "causal", "none_front", 1, 0, False, (2,), 32, 32, (4096,), (4096,)),         # the reference's benchmark maximum
+    (1, "local", "scale_front", 16, 0, True, (2,), 100, 72, (130,), (515,)),          # 64 < channels < 128
+    (1, "causal", "none_front", 1, 0, False, (2,), 128, 128, (1001,), (1001,)),       # fused head_dim-128 backward, packed
+    (1, "full", "scale_end", 1, 0, False, (1,), 96, 128, (250,), (1000,)),
+    (2, "local", "none_front", 3, 0, True, (2,), 17, 31, (13, 9), (13, 9)),
+    (2, "causal", "scale_front", 1, 0, False, (1,), 64, 64, (9, 14), (18, 14)),
+    (1, "full", "none_front", 1, 0, False, (1,), 1, 1, (1,), (1,)),
+    (1, "local", "none_front", 2, 0, False, (2,), 16, 16, (200,), (40,)),             # rows with no keys
+], ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_fp16_any_channels_any_lengths_on_the_tensor_cores(case):
+    dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
+    _check(np.float16, dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=zlib.crc32(repr(case).encode()) % 1000,
+           expect_path=2)
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)

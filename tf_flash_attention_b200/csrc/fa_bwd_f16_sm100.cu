@@ -30,6 +30,16 @@ using namespace ptx;
 
 bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
                  bool swizzle128);  // fa_fwd_f16_sm100.cu
+bool make_map_3d(CUtensorMap* map, const void* base, int64_t batch, int64_t channels, int64_t seq, int64_t pitch,
+                 int box_rows, bool swizzle128);  // fa_fwd_f16_sm100.cu
+
+// Workspace of the fp16 backward: [LSE2, D (+ pad)] [fp32 dQ scratch of the fused head_dim-128 kernel] [pitch-padded
+// copies of the q-length / k-length tensors when their length is not a multiple of 8 (fa_pack.cu)].
+struct BwdLayout {
+  bool pack_q, pack_k;
+  size_t off_acc, off_q, off_do, off_dq, off_k, off_v, off_dk, off_dv, total;
+};
+BwdLayout bwd_layout(const LaunchArgs& a);
 
 constexpr int kBM = 128;        // rows owned by one softmax warpgroup (TMEM lanes)
 constexpr int kBN = 64;         // streamed tile width
@@ -56,24 +66,33 @@ struct alignas(64) BwdParams {
   const float* lse2;   // [batch*nq + pad]  (m + log l) * log2(e), +inf on empty rows
   const float* dsum;   // [batch*nq + pad]  rowsum(dO o O)
   int32_t nq, nk, n_blocks, batch;
+  int32_t stat_pitch;  // floats per batch element in lse2 / dsum: nq rounded up to 4 (16-byte rows for the bulk copies)
+  int32_t exact_d;     // split-operand dQ kernel: replace D = rowsum(dO o O) (O is fp16-rounded) by rowsum(P o dP)
+  float* dsum_out;     // where that kernel leaves the exact D for the dK/dV kernel launched behind it (== dsum)
   float scale_log2, scale;
 };
 
 // ---- preprocess: LSE2 and D -------------------------------------------------------------------
 __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restrict__ d_o,
                              const float* __restrict__ l, const __half* __restrict__ m, float* __restrict__ lse2,
-                             float* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq) {
-  const int64_t total = batch * nq;
-  // the padding behind both arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
-  // (a NaN there would turn the masked 0 * (dP - D) into NaN)
+                             float* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq, int32_t sp) {
+  const int64_t total = batch * sp;
+  // the padding behind both arrays (and behind each batch element's row when nq is not a multiple of 4) is read by the
+  // 64-wide bulk copies of the last, ragged query tile: keep it finite (a NaN there would turn the masked
+  // 0 * (dP - D) into NaN)
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kStatPad) {
     lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
     dsum[total + threadIdx.x] = 0.f;
   }
-  // two adjacent query positions per thread -> half2 loads, coalesced along the sequence
+  // two adjacent query positions per thread -> half2 loads, coalesced along the sequence (nq and sp are even here)
   for (int64_t i2 = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 2; i2 < total;
        i2 += int64_t(gridDim.x) * blockDim.x * 2) {
-    const int64_t b = i2 / nq, r = i2 - b * nq;  // nq is even (multiple of 8)
+    const int64_t b = i2 / sp, r = i2 - b * sp;
+    if (r >= nq) {
+      lse2[i2] = lse2[i2 + 1] = __int_as_float(0x7f800000);
+      dsum[i2] = dsum[i2 + 1] = 0.f;
+      continue;
+    }
     const __half2* op = reinterpret_cast<const __half2*>(o + b * v_d * int64_t(nq) + r);
     const __half2* dp = reinterpret_cast<const __half2*>(d_o + b * v_d * int64_t(nq) + r);
     float a0 = 0.f, a1 = 0.f;
@@ -89,11 +108,40 @@ __global__ void bwd_prep_f16(const __half* __restrict__ o, const __half* __restr
     dsum[i2 + 1] = a1;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float lv = l[i2 + e];
-      const __half mv = m[i2 + e];
+      const float lv = l[b * nq + r + e];
+      const __half mv = m[b * nq + r + e];
       lse2[i2 + e] = (lv > 0.f && !is_sentinel<__half>(mv)) ? (__half2float(mv) + logf(lv)) * kLog2eB
                                                              : __int_as_float(0x7f800000);
     }
+  }
+}
+
+// any query length (odd included): one thread per query position, scalar loads coalesced along the sequence
+__global__ void bwd_prep_f16_any(const __half* __restrict__ o, const __half* __restrict__ d_o,
+                                 const float* __restrict__ l, const __half* __restrict__ m, float* __restrict__ lse2,
+                                 float* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq, int32_t sp) {
+  const int64_t total = batch * sp;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = i / sp, r = i - b * sp;
+    if (r >= nq) {
+      lse2[i] = __int_as_float(0x7f800000);
+      dsum[i] = 0.f;
+      continue;
+    }
+    const __half* op = o + b * v_d * int64_t(nq) + r;
+    const __half* dp = d_o + b * v_d * int64_t(nq) + r;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < v_d; ++c) acc = fmaf(__half2float(op[c * int64_t(nq)]), __half2float(dp[c * int64_t(nq)]), acc);
+    dsum[i] = acc;
+    const float lv = l[b * nq + r];
+    const __half mv = m[b * nq + r];
+    lse2[i] = (lv > 0.f && !is_sentinel<__half>(mv)) ? (__half2float(mv) + logf(lv)) * kLog2eB
+                                                      : __int_as_float(0x7f800000);
   }
 }
 
@@ -119,6 +167,9 @@ template <int D, int VD, bool SPLIT>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DqCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
+  // precise gradients with the exact row sum D = rowsum(P o dP) (see bwd_dq_small_kernel): needs a second accumulator
+  // A2 = P K per Q tile, which fits behind dQ_i only while D <= 64
+  constexpr bool kExact = SPLIT && D <= 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -191,10 +242,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
         for (int i = 0; i < 2; ++i) {
           mbar_arrive_expect_tx(bar_q_full + 8 * i, Cfg::kQBytes + Cfg::kDoBytes);
           for (int h = 0; h < 2; ++h) {
-            tma_load_2d(q_smem + i * Cfg::kQBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
-                        q0 + i * kBM + h * 64, b * D);
-            tma_load_2d(do_smem + i * Cfg::kDoBytes + h * (VD * 128), &p.map_do, bar_q_full + 8 * i,
-                        q0 + i * kBM + h * 64, b * VD);
+            tma_load_bc(q_smem + i * Cfg::kQBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
+                        q0 + i * kBM + h * 64, b);
+            tma_load_bc(do_smem + i * Cfg::kDoBytes + h * (VD * 128), &p.map_do, bar_q_full + 8 * i,
+                        q0 + i * kBM + h * 64, b);
           }
         }
         int t = 0;
@@ -205,8 +256,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
-          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b * D);
-          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b * VD);
+          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b);
+          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b);
           ++t;
         }
       }
@@ -240,6 +291,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + 32 + ks * 8,
                      smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+          }
+          if constexpr (kExact) {   // A2_i += P K: P (fp16) in the dP columns, A2 in the upper half of the dQ_i columns
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 256 + i * 128 + 64, tmem_base + 128 + i * kBN + ks * 8,
+                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           }
         };
         if (n > 0) {
@@ -286,9 +343,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
     const int qi = tq0 + r;
     const bool q_valid = qi < p.nq;
     const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
-    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
-    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.stat_pitch + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.stat_pitch + qi] : 0.f;
     const float scale_log2 = p.scale_log2;
+    float d_exact = 0.f;   // kExact: rowsum(P o dP) of this thread's row
     int j = 0;
     TileIter it;
     it.init(sched, 2, kt_first, kt_last);
@@ -322,7 +380,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       tmem_ld32f(t_dp, &dp[0]);
       tmem_ld32f(t_dp + 32, &dp[32]);
       tmem_wait_ld();
-      uint32_t pk[32], pl[SPLIT ? 32 : 1];
+      uint32_t pk[32], pl[SPLIT ? 32 : 1], pp[kExact ? 32 : 1];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
         const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
@@ -330,6 +388,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
         float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
         p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
         p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
+        if constexpr (kExact) {
+          d_exact = fmaf(p0, dp[c], d_exact);
+          d_exact = fmaf(p1, dp[c + 1], d_exact);
+          pp[c >> 1] = pack_half2(p0, p1);
+        }
         if constexpr (SPLIT)
           split_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), pk[c >> 1], pl[c >> 1]);
         else
@@ -337,6 +400,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       }
       tmem_st32(t_s, pk);
       if constexpr (SPLIT) tmem_st32(t_s + 32, pl);
+      if constexpr (kExact) tmem_st32(t_dp, pp);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * i);
@@ -347,11 +411,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
     if (j > 0) {
       mbar_wait(bar_final + 8 * i, 0);
       tc_fence_after();
+      float delta = 0.f;
+      if constexpr (kExact) {
+        if (p.exact_d) {
+          delta = d_exact - dsum;
+          if (q_valid) p.dsum_out[int64_t(b) * p.stat_pitch + qi] = d_exact;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         float o[32];
         tmem_ld32f(t_dq + c * 32, o);
         tmem_wait_ld();
+        if constexpr (kExact) {
+          float o2[32];
+          tmem_ld32f(t_dq + 64 + c * 32, o2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = fmaf(-delta, o2[e], o[e]);
+        }
 #pragma unroll
         for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
       }
@@ -365,7 +443,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
     if (r == 0 && tile_valid) {
       for (int h = 0; h < 2; ++h)
         if (tq0 + h * 64 < p.nq)
-          tma_store_2d(&p.map_dq, q_smem + i * Cfg::kQBytes + h * (D * 128), tq0 + h * 64, b * D);
+          tma_store_bc(&p.map_dq, q_smem + i * Cfg::kQBytes + h * (D * 128), tq0 + h * 64, b);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -465,7 +543,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // TMEM columns (256 allocated -> two CTAs per SM): S [0, 64)  dP [64, 128)  dQ [128, +D); one 128-row Q tile,
-  // both softmax warpgroups split the 64 key columns of every tile
+  // both softmax warpgroups split the 64 key columns of every tile.
+  // SPLIT (precise gradients): each warpgroup's 32 S columns hold dS as hi (first 16) + lo (next 16) fp16 pairs, its
+  // first 16 dP columns hold P (fp16), and a second accumulator A2 = P K sits at [192, +D): the row sum D is
+  // re-derived exactly as rowsum(P o dP) while the tiles stream by (the D handed in comes from the fp16-rounded O and is
+  // off by up to ~5e-3, which P ~ 1 rows pass straight into dS), and dQ = scale (A1 - (D_exact - D) A2) at the end.
+  static_assert(!SPLIT || 192 + D <= 256, "the P K accumulator of the precise variant needs 2 * D <= 128 columns");
 
   if (warp >= 8) {
     setmaxnreg_dec<32>();
@@ -473,8 +556,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_q_full, Cfg::kQBytes + Cfg::kDoBytes);
         for (int h = 0; h < 2; ++h) {
-          tma_load_2d(q_smem + h * (D * 128), &p.map_q, bar_q_full, q0 + h * 64, b * D);
-          tma_load_2d(do_smem + h * (VD * 128), &p.map_do, bar_q_full, q0 + h * 64, b * VD);
+          tma_load_bc(q_smem + h * (D * 128), &p.map_q, bar_q_full, q0 + h * 64, b);
+          tma_load_bc(do_smem + h * (VD * 128), &p.map_do, bar_q_full, q0 + h * 64, b);
         }
         int t = 0;
         TileIter it;
@@ -484,8 +567,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
-          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b * D);
-          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b * VD);
+          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b);
+          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b);
           ++t;
         }
       }
@@ -519,6 +602,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
                      smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)   // A2 += P K (P in the dP columns)
+              mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
+                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           }
         };
         if (n > 0) {
@@ -555,9 +642,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
     const int qi = q0 + r;
     const bool q_valid = qi < p.nq;
     const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
-    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
-    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.stat_pitch + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.stat_pitch + qi] : 0.f;
     const float scale_log2 = p.scale_log2;
+    float d_exact = 0.f;   // SPLIT: this warpgroup's half of rowsum(P o dP)
     int j = 0;
     TileIter it;
     it.init(sched, 1, kt_first, kt_last);
@@ -585,20 +673,27 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
       tmem_ld32f(t_s, s);
       tmem_ld32f(t_s + 64, dp);
       tmem_wait_ld();
-      uint32_t pk[16], pl[16];
+      uint32_t pk[16], pl[16], pp[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         float p0 = ex2(fmaf(s[c], scale_log2, -lse2));
         float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse2));
         p0 = (okmask >> c) & 1u ? p0 : 0.f;
         p1 = (okmask >> (c + 1)) & 1u ? p1 : 0.f;
-        if constexpr (SPLIT)
+        if constexpr (SPLIT) {
+          d_exact = fmaf(p0, dp[c], d_exact);
+          d_exact = fmaf(p1, dp[c + 1], d_exact);
           split_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), pk[c >> 1], pl[c >> 1]);
-        else
+          pp[c >> 1] = pack_half2(p0, p1);
+        } else {
           pk[c >> 1] = pack_half2(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum));
+        }
       }
       tmem_st16(t_s, pk);
-      if constexpr (SPLIT) tmem_st16(t_s + 16, pl);
+      if constexpr (SPLIT) {
+        tmem_st16(t_s + 16, pl);
+        tmem_st16(t_s + 64, pp);
+      }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready);
@@ -609,10 +704,29 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
     if (j > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
+      float delta = 0.f;
+      if constexpr (SPLIT) {
+        // both halves of the exact row sum meet in shared memory (the dO tile is no longer read: every MMA has completed)
+        float* dx = reinterpret_cast<float*>(smem_gen + Cfg::kQBytes);
+        dx[x * kBM + r] = d_exact;
+        named_bar_sync(2, 2 * kBM);
+        const float d_full = dx[r] + dx[kBM + r];
+        if (p.exact_d) {
+          delta = d_full - dsum;
+          if (x == 0 && q_valid) p.dsum_out[int64_t(b) * p.stat_pitch + qi] = d_full;
+        }
+      }
       for (int c = x; c < D / 32; c += 2) {
         float o[32];
         tmem_ld32f(t_dq + c * 32, o);
         tmem_wait_ld();
+        if constexpr (SPLIT) {
+          float o2[32];
+          tmem_ld32f(t_dq + 64 + c * 32, o2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = fmaf(-delta, o2[e], o[e]);
+        }
 #pragma unroll
         for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
       }
@@ -626,7 +740,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
     named_bar_sync(1, 2 * kBM);
     if (threadIdx.x == 0) {
       for (int h = 0; h < 2; ++h)
-        if (q0 + h * 64 < p.nq) tma_store_2d(&p.map_dq, q_smem + h * (D * 128), q0 + h * 64, b * D);
+        if (q0 + h * 64 < p.nq) tma_store_bc(&p.map_dq, q_smem + h * (D * 128), q0 + h * 64, b);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -745,8 +859,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
         for (int h = 0; h < 2; ++h) {
-          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
-          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
+          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
         }
         int t = 0;
         TileIter it;
@@ -756,9 +870,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
-          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
-          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
+          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
           ++t;
@@ -789,6 +903,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
                    idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // P^T lo halves: the 32 columns behind the packed hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 256, tmem_base + x * kBN + 32 + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+                     idesc_dv, 1u);
+          }
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(q_s + ks * 32, 16, 1024),
@@ -879,7 +999,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       tmem_wait_ld();
       const float* lse_s = stat_gen + st * (2 * kBN);
       const float* dsum_s = lse_s + kBN;
-      uint32_t pk[32], dk[32], dl[SPLIT ? 32 : 1];
+      uint32_t pk[32], dk[32], dl[SPLIT ? 32 : 1], pl[SPLIT ? 32 : 1];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
         const uint32_t mword = c < 32 ? okmask_lo : okmask_hi;
@@ -887,7 +1007,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
         float p1 = ex2(fmaf(s[c + 1], scale_log2, -lse_s[c + 1]));
         p0 = (mword >> (c & 31)) & 1u ? p0 : 0.f;
         p1 = (mword >> ((c + 1) & 31)) & 1u ? p1 : 0.f;
-        pk[c >> 1] = pack_half2(p0, p1);
+        if constexpr (SPLIT)
+          split_half2(p0, p1, pk[c >> 1], pl[c >> 1]);
+        else
+          pk[c >> 1] = pack_half2(p0, p1);
         if constexpr (SPLIT)
           split_half2(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]), dk[c >> 1], dl[c >> 1]);
         else
@@ -895,7 +1018,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       }
       tmem_st32(t_s, pk);
       tmem_st32(t_dp, dk);
-      if constexpr (SPLIT) tmem_st32(t_dp + 32, dl);
+      if constexpr (SPLIT) {
+        tmem_st32(t_s + 32, pl);
+        tmem_st32(t_dp + 32, dl);
+      }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready + 8 * x);
@@ -928,9 +1054,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
       for (int h = 0; h < 2; ++h)
         if (k0 + h * 64 < p.nk) {
           if (x == 0)
-            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
           else
-            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
         }
       tma_store_commit();
       tma_store_wait_read();
@@ -1045,8 +1171,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
         for (int h = 0; h < 2; ++h) {
-          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
-          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
+          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
         }
         int t = 0;
         TileIter it;
@@ -1056,9 +1182,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
-          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
-          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
+          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
           ++t;
@@ -1090,6 +1216,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
                    smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+          if constexpr (SPLIT) {   // P^T lo halves, 16 columns behind the hi halves
+#pragma unroll
+            for (int ks = 0; ks < kBN / 16; ++ks)
+              mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
+                     smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, 1u);
+          }
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
@@ -1169,7 +1301,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
       tmem_wait_ld();
       const float4* lse4 = reinterpret_cast<const float4*>(stat_gen + st * (2 * kBN) + x * 32);
       const float4* dsum4 = lse4 + kBN / 4;
-      uint32_t pk[16], dk[16], dl[16];
+      uint32_t pk[16], dk[16], dl[16], pl[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         const uint32_t mword = okmask >> c;
@@ -1183,8 +1315,13 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
         p1 = mword & 2u ? p1 : 0.f;
         p2 = mword & 4u ? p2 : 0.f;
         p3 = mword & 8u ? p3 : 0.f;
-        pk[c >> 1] = pack_half2(p0, p1);
-        pk[(c >> 1) + 1] = pack_half2(p2, p3);
+        if constexpr (SPLIT) {
+          split_half2(p0, p1, pk[c >> 1], pl[c >> 1]);
+          split_half2(p2, p3, pk[(c >> 1) + 1], pl[(c >> 1) + 1]);
+        } else {
+          pk[c >> 1] = pack_half2(p0, p1);
+          pk[(c >> 1) + 1] = pack_half2(p2, p3);
+        }
         if constexpr (SPLIT) {
           split_half2(p0 * (dp[c] - dd.x), p1 * (dp[c + 1] - dd.y), dk[c >> 1], dl[c >> 1]);
           split_half2(p2 * (dp[c + 2] - dd.z), p3 * (dp[c + 3] - dd.w), dk[(c >> 1) + 1], dl[(c >> 1) + 1]);
@@ -1195,7 +1332,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
       }
       tmem_st16(t_s, pk);          // P^T  over the first 16 columns of this half of S^T
       tmem_st16(t_s + 64, dk);     // dS^T over the first 16 columns of this half of dP^T
-      if constexpr (SPLIT) tmem_st16(t_s + 64 + 16, dl);   // dS^T lo halves over the next 16
+      if constexpr (SPLIT) {
+        tmem_st16(t_s + 16, pl);        // P^T lo halves
+        tmem_st16(t_s + 64 + 16, dl);   // dS^T lo halves
+      }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p_ready);
@@ -1228,9 +1368,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
       for (int h = 0; h < 2; ++h)
         if (k0 + h * 64 < p.nk) {
           if (x == 0)
-            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
           else
-            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
         }
       tma_store_commit();
       tma_store_wait_read();
@@ -1246,8 +1386,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
 
 
 // LSE2 + D arrays (padded), rounded up so that the fp32 dQ scratch behind them is 256-byte aligned
+static int64_t stat_pitch_of(int64_t nq) { return (nq + 3) & ~int64_t(3); }
 static size_t stats_bytes(int64_t batch, int64_t nq) {
-  return (size_t(2) * (batch * nq + kStatPad) * sizeof(float) + 255) & ~size_t(255);
+  return (size_t(2) * (batch * stat_pitch_of(nq) + kStatPad) * sizeof(float) + 255) & ~size_t(255);
 }
 
 static bool make_map_f32_sw128(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols,
@@ -1474,8 +1615,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
         for (int h = 0; h < 2; ++h) {
-          tma_load_2d(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b * D);
-          tma_load_2d(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b * VD);
+          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
+          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
         }
         int t = 0;
         TileIter it;
@@ -1485,9 +1626,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_2d(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b * D);
-          tma_load_2d(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b * VD);
-          const int64_t off = int64_t(b) * p.nq + qt * kBN;
+          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
+          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
           FB_STAMP(3, t, 3);
@@ -1702,9 +1843,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       for (int h = 0; h < 2; ++h)
         if (k0 + h * 64 < p.nk) {
           if (x == 0)
-            tma_store_2d(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b * VD);
+            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
           else
-            tma_store_2d(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b * D);
+            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
         }
       tma_store_commit();
       tma_store_wait_read();
@@ -1731,24 +1872,53 @@ __global__ void bwd_dq_convert(const float4* __restrict__ acc, uint4* __restrict
   }
 }
 
+// fa_set_grad_precision(0): which problems get the split-operand ("precise") backward on their own. The operand rounding
+// (and the D = rowsum(dO o O) taken from the fp16-rounded O) only matters where P is large, i.e. where rows attend few
+// keys and a key collects many such rows; measured without it: 4.2e-3 on dK at 1000 queries x 88 keys (causal,
+// scale_end), 2.1e-3 on 2-D strided windows of 2..3 positions, 2.005e-3 at 2135 heads x 64 x 64 causal. The precise
+// kernels cost ~12 % on the HBM-bound workloads (S1, S2, C3: profiles/r2_grad_precision.md), so problems whose rows are
+// long (P small) keep the plain ones.
+static bool precise_auto(const FaRule& r) {
+  const int64_t nq = r.q.total, nk = r.k.total;
+  int64_t row_max = nk;   // upper bound on the keys one row attends
+  if (r.rule == 2) {
+    const int64_t ext[2] = {r.ref0, r.ref1};
+    int64_t win = 1;
+    for (int i = 0; i < r.dims; ++i) {
+      const int64_t per_dim = std::min<int64_t>(2 * int64_t(r.window) - 1, 2 * ((ext[i] - 1) >> r.log2_stride) + 1);
+      win = std::min<int64_t>(win * per_dim, nk);
+    }
+    row_max = win;
+  }
+  if (row_max <= 32) return true;                       // every row is short: P ~ 1/16 and larger everywhere
+  const bool causal_type = r.rule == 1 || (r.rule == 2 && r.causal);
+  // causal rules: the first rows of every key attend one, two, ... keys; one such row per key is harmless (measured
+  // 1.2e-3 at the C2 shape), nq / nk of them per key are not, and in short sequences they are all there is
+  return causal_type && (nk <= 128 || nq >= 4 * nk);
+}
+
 // ---- host side ---------------------------------------------------------------------------------
+// D, VD: the kernels' padded channel counts (a.d <= D, a.v_d <= VD; the 3-D tensor maps zero-fill / clip the rest)
 template <int D, int VD>
 cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   BwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
+  const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
   // fa_set_grad_precision: 1 = dS as hi + lo fp16 pairs everywhere (head_dim 128 then runs the two-kernel backward),
   // 2 = never, 0 = automatic: on for every path but the fused head_dim-128 kernel, whose TMEM has no room for the lo
   // halves and whose shapes (long rows, small P) measure inside the 2e-3 bar without them
-  const bool split = a.grad_split == 1 || (a.grad_split == 0 && D != 128);
+  const bool fused_shape = D == 128 && a.d == 128;
+  const bool split = a.grad_split == 1 || (a.grad_split == 0 && !fused_shape && precise_auto(a.rule));
   float* lse2 = reinterpret_cast<float*>(a.workspace);
-  float* dsum = lse2 + (a.batch * int64_t(nq) + kStatPad);
-  if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
-      !make_map_2d(&p.map_k, a.k, a.batch * D, nk, 64, D, true) ||
-      !make_map_2d(&p.map_v, a.v, a.batch * VD, nk, 64, VD, true) ||
-      !make_map_2d(&p.map_do, a.d_o, a.batch * VD, nq, 64, VD, true) ||
-      !make_map_2d(&p.map_dq, a.d_q, a.batch * D, nq, 64, D, false) ||
-      !make_map_2d(&p.map_dk, a.d_k, a.batch * D, nk, 64, D, false) ||
-      !make_map_2d(&p.map_dv, a.d_v, a.batch * VD, nk, 64, VD, false))
+  const int64_t sp = stat_pitch_of(nq);
+  float* dsum = lse2 + (a.batch * sp + kStatPad);
+  if (!make_map_3d(&p.map_q, a.q, a.batch, a.d, nq, qp, D, true) ||
+      !make_map_3d(&p.map_k, a.k, a.batch, a.d, nk, kp, D, true) ||
+      !make_map_3d(&p.map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) ||
+      !make_map_3d(&p.map_do, a.d_o, a.batch, a.v_d, nq, qp, VD, true) ||
+      !make_map_3d(&p.map_dq, a.d_q, a.batch, a.d, nq, qp, D, false) ||
+      !make_map_3d(&p.map_dk, a.d_k, a.batch, a.d, nk, kp, D, false) ||
+      !make_map_3d(&p.map_dv, a.d_v, a.batch, a.v_d, nk, kp, VD, false))
     return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.lse2 = lse2;
@@ -1756,25 +1926,37 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   p.nq = nq;
   p.nk = nk;
   p.batch = int32_t(a.batch);
-  p.scale = 1.f / sqrtf(float(D));
+  p.stat_pitch = int32_t(sp);
+  // the exact row sum needs every key of a row in this call (a ring block sees a key shard only)
+  p.exact_d = (split && !a.partial_keys) ? 1 : 0;
+  p.dsum_out = dsum;
+  p.scale = 1.f / sqrtf(float(a.d));
   p.scale_log2 = p.scale * kLog2eB;
   {
-    const int64_t total = a.batch * int64_t(nq);
-    const int blocks = int(std::min<int64_t>((total / 2 + 255) / 256, 148 * 16));
+    // statistics from the caller's own (dense) O and dO
+    const int64_t total = a.batch * sp;
     ScopedKernel timed("bwd_prep_f16", stream);
-    bwd_prep_f16<<<blocks, 256, 0, stream>>>((const __half*)a.o, (const __half*)a.d_o, (const float*)a.l,
-                                             (const __half*)a.m, lse2, dsum, a.batch, VD, nq);
+    if (nq % 2 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.prep_d_o) & 3) == 0) {
+      const int blocks = int(std::min<int64_t>((total / 2 + 255) / 256, 148 * 16));
+      bwd_prep_f16<<<blocks, 256, 0, stream>>>((const __half*)a.o, (const __half*)a.prep_d_o, (const float*)a.l,
+                                               (const __half*)a.m, lse2, dsum, a.batch, a.v_d, nq, int32_t(sp));
+    } else {
+      const int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 16));
+      bwd_prep_f16_any<<<blocks, 256, 0, stream>>>((const __half*)a.o, (const __half*)a.prep_d_o, (const float*)a.l,
+                                                   (const __half*)a.m, lse2, dsum, a.batch, a.v_d, nq, int32_t(sp));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   if constexpr (D == 128) {
-    if (a.variant != 4 && !split) {
-      // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics
-      float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + stats_bytes(a.batch, nq));
-      const size_t acc_bytes = size_t(a.batch) * D * nq * sizeof(float);
+    if (a.variant != 4 && !split && fused_shape) {
+      // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics, with the row pitch of the dQ tensor the convert pass
+      // writes (the padded pitch when the q side is packed; the columns past nq only ever receive zeros)
+      float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + bwd_layout(a).off_acc);
+      const size_t acc_bytes = size_t(a.batch) * D * qp * sizeof(float);
       FusedParams fp;
       fp.base = p;
-      if (!make_map_f32_sw128(&fp.map_dq_acc, acc, a.batch * D, nq, 32, D)) return cudaErrorInvalidValue;
+      if (!make_map_f32_sw128(&fp.map_dq_acc, acc, a.batch * D, qp, 32, D)) return cudaErrorInvalidValue;
       {
         ScopedKernel timed("bwd_dq_zero", stream);
         cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, stream);
@@ -1792,7 +1974,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
       }
       {
-        const int64_t n8 = a.batch * int64_t(D) * nq / 8;
+        const int64_t n8 = a.batch * int64_t(D) * qp / 8;
         const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 148 * 16));
         ScopedKernel timed("bwd_dq_convert", stream);
         bwd_dq_convert<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(acc),
@@ -1854,10 +2036,32 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
 extern "C" void fa_debug_set_buffer_bwd(void* buf) { cudaMemcpyToSymbol(g_dbg_bwd, &buf, sizeof(buf)); }
 #endif
 
-size_t bwd_workspace_bytes(int64_t batch, int64_t nq, int d, int variant) {
-  size_t s = stats_bytes(batch, nq);
-  if (d == 128 && variant != 4) s += size_t(batch) * d * nq * sizeof(float);
-  return s;
+static int64_t pad8b(int64_t n) { return (n + 7) & ~int64_t(7); }
+static size_t al256b(size_t v) { return (v + 255) & ~size_t(255); }
+
+BwdLayout bwd_layout(const LaunchArgs& a) {
+  BwdLayout w{};
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  w.pack_q = (nq % 8) != 0;
+  w.pack_k = (nk % 8) != 0;
+  const int64_t qp = pad8b(nq), kp = pad8b(nk);
+  size_t off = stats_bytes(a.batch, nq);
+  auto take = [&off](size_t n) { size_t o = off; off += al256b(n); return o; };
+  w.off_acc = off;
+  if (a.d == 128 && a.variant != 4) take(size_t(a.batch) * 128 * qp * sizeof(float));
+  if (w.pack_q) {
+    w.off_q = take(size_t(a.batch) * a.d * qp * 2);
+    w.off_do = take(size_t(a.batch) * a.v_d * qp * 2);
+    w.off_dq = take(size_t(a.batch) * a.d * qp * 2);
+  }
+  if (w.pack_k) {
+    w.off_k = take(size_t(a.batch) * a.d * kp * 2);
+    w.off_v = take(size_t(a.batch) * a.v_d * kp * 2);
+    w.off_dk = take(size_t(a.batch) * a.d * kp * 2);
+    w.off_dv = take(size_t(a.batch) * a.v_d * kp * 2);
+  }
+  w.total = off;
+  return w;
 }
 
 }  // namespace sm100
@@ -1866,30 +2070,62 @@ static bool aligned16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) &
 
 bool sm100_f16_backward_supports(const LaunchArgs& a) {
   if (a.dtype != 0) return false;
-  if (!((a.d == 64 || a.d == 128) && (a.v_d == 64 || a.v_d == 128))) return false;
+  if (a.d < 1 || a.v_d < 1 || a.d > 128 || a.v_d > 128) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
-  if (nq % 8 || nk % 8) return false;
-  if (!aligned16b(a.q) || !aligned16b(a.k) || !aligned16b(a.v) || !aligned16b(a.d_o) || !aligned16b(a.d_q) ||
-      !aligned16b(a.d_k) || !aligned16b(a.d_v) || !aligned16b(a.o) || !aligned16b(a.workspace))
-    return false;
-  if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
+  const sm100::BwdLayout w = sm100::bwd_layout(a);
+  if (!w.pack_q && (!aligned16b(a.q) || !aligned16b(a.d_o) || !aligned16b(a.d_q))) return false;
+  if (!w.pack_k && (!aligned16b(a.k) || !aligned16b(a.v) || !aligned16b(a.d_k) || !aligned16b(a.d_v))) return false;
+  if (!a.workspace || (reinterpret_cast<uintptr_t>(a.workspace) & 255) || a.workspace_bytes < w.total) return false;
+  if (a.batch > 0x7fffffffLL) return false;
   if (((nq + 255) / 256) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
-  if (a.workspace_bytes < sm100::bwd_workspace_bytes(a.batch, nq, a.d, a.variant)) return false;
   // the per-CTA tile schedules hold 32 * kMaxTileWords streamed 64-wide tiles (keys in the dQ kernels, queries in the
   // dK/dV and fused kernels)
   if ((nk + 63) / 64 > 32 * sm100::kMaxTileWords || (nq + 63) / 64 > 32 * sm100::kMaxTileWords) return false;
   return true;
 }
 
-size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) {
-  return sm100::bwd_workspace_bytes(a.batch, a.rule.q.total, a.d, a.variant);
+size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) { return sm100::bwd_layout(a).total; }
+
+static cudaError_t backward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+  const bool d_small = a.d <= 64, v_small = a.v_d <= 64;
+  if (!d_small && !v_small) return sm100::launch_bwd<128, 128>(a, stream);
+  if (d_small && v_small) return sm100::launch_bwd<64, 64>(a, stream);
+  if (!d_small) return sm100::launch_bwd<128, 64>(a, stream);
+  return sm100::launch_bwd<64, 128>(a, stream);
 }
 
-cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 128 && a.v_d == 128) return sm100::launch_bwd<128, 128>(a, stream);
-  if (a.d == 64 && a.v_d == 64) return sm100::launch_bwd<64, 64>(a, stream);
-  if (a.d == 128 && a.v_d == 64) return sm100::launch_bwd<128, 64>(a, stream);
-  return sm100::launch_bwd<64, 128>(a, stream);
+cudaError_t sm100_f16_backward(const LaunchArgs& a0, cudaStream_t stream) {
+  const sm100::BwdLayout w = sm100::bwd_layout(a0);
+  LaunchArgs a = a0;
+  a.prep_d_o = a0.d_o;   // the statistics pass reads the caller's dense O / dO
+  if (!w.pack_q && !w.pack_k) return backward_dispatch(a, stream);
+  char* ws = static_cast<char*>(a0.workspace);
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  cudaError_t e;
+  if (w.pack_q) {
+    a.q_pitch = sm100::pad8b(nq);
+    if ((e = pack_rows(2, a0.q, ws + w.off_q, a.batch * a.d, nq, nq, a.q_pitch, stream)) != cudaSuccess) return e;
+    if ((e = pack_rows(2, a0.d_o, ws + w.off_do, a.batch * a.v_d, nq, nq, a.q_pitch, stream)) != cudaSuccess) return e;
+    a.q = ws + w.off_q;
+    a.d_o = ws + w.off_do;
+    a.d_q = ws + w.off_dq;
+  }
+  if (w.pack_k) {
+    a.k_pitch = sm100::pad8b(nk);
+    if ((e = pack_rows(2, a0.k, ws + w.off_k, a.batch * a.d, nk, nk, a.k_pitch, stream)) != cudaSuccess) return e;
+    if ((e = pack_rows(2, a0.v, ws + w.off_v, a.batch * a.v_d, nk, nk, a.k_pitch, stream)) != cudaSuccess) return e;
+    a.k = ws + w.off_k;
+    a.v = ws + w.off_v;
+    a.d_k = ws + w.off_dk;
+    a.d_v = ws + w.off_dv;
+  }
+  if ((e = backward_dispatch(a, stream)) != cudaSuccess) return e;
+  if (w.pack_q && (e = pack_rows(2, a.d_q, a0.d_q, a.batch * a.d, nq, a.q_pitch, nq, stream)) != cudaSuccess) return e;
+  if (w.pack_k) {
+    if ((e = pack_rows(2, a.d_k, a0.d_k, a.batch * a.d, nk, a.k_pitch, nk, stream)) != cudaSuccess) return e;
+    if ((e = pack_rows(2, a.d_v, a0.d_v, a.batch * a.v_d, nk, a.k_pitch, nk, stream)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace fa

@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         for (int i = 0; i < kQTiles; ++i) {
           mbar_arrive_expect_tx(bar_q_full + 8 * i, kBlockM * D * 2);
           for (int h = 0; h < 2; ++h)
-            tma_load_2d(q_smem + i * Cfg::kQTileBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
-                        q0 + i * kBlockM + h * 64, b * D);
+            tma_load_bc(q_smem + i * Cfg::kQTileBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
+                        q0 + i * kBlockM + h * 64, b);
         }
         int t = 0;
         TileIter it;
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * D * 2);
             for (int h = 0; h < kBlockN / 64; ++h)
-              tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
-                          kt * kBlockN + h * 64, b * D);
+              tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
+                          kt * kBlockN + h * 64, b);
             ++t;
           }
           {
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * VD * 2);
             for (int h = 0; h < kBlockN / 64; ++h)
-              tma_load_2d(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
-                          kt * kBlockN + h * 64, b * VD);
+              tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
+                          kt * kBlockN + h * 64, b);
             ++t;
           }
         }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
     if (r == 0 && tile_valid) {
       for (int h = 0; h < 2; ++h)
         if (tq0 + h * 64 < p.nq)
-          tma_store_2d(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b * VD);
+          tma_store_bc(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -492,15 +492,34 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
   return r == CUDA_SUCCESS;
 }
 
+// 3-D view [batch][channels][sequence] of a channel-first fp16 tensor (`pitch` elements between channel rows): the box is
+// 64 positions x box_rows channels of one batch element; channels past `channels` are zero-filled / clipped.
+bool make_map_3d(CUtensorMap* map, const void* base, int64_t batch, int64_t channels, int64_t seq, int64_t pitch,
+                 int box_rows, bool swizzle128) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {cuuint64_t(seq), cuuint64_t(channels), cuuint64_t(batch)};
+  cuuint64_t gstride[2] = {cuuint64_t(pitch) * 2, cuuint64_t(pitch) * 2 * cuuint64_t(channels)};
+  cuuint32_t box[3] = {64u, cuuint32_t(box_rows), 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <int D, int VD, int BN, int MINB>
 cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   using Cfg = FwdCfg<D, VD, BN>;
   FwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
-  if (!make_map_2d(&p.map_q, a.q, a.batch * D, nq, 64, D, true) ||
-      !make_map_2d(&p.map_k, a.k, a.batch * D, nk, 64, D, true) ||
-      !make_map_2d(&p.map_v, a.v, a.batch * VD, nk, 64, VD, true) ||
-      !make_map_2d(&p.map_o, a.o, a.batch * VD, nq, 64, VD, false))
+  // D, VD are the kernel's padded channel counts (a.d <= D, a.v_d <= VD)
+  const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
+  if (!make_map_3d(&p.map_q, a.q, a.batch, a.d, nq, qp, D, true) ||
+      !make_map_3d(&p.map_k, a.k, a.batch, a.d, nk, kp, D, true) ||
+      !make_map_3d(&p.map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) ||
+      !make_map_3d(&p.map_o, a.o, a.batch, a.v_d, nq, qp, VD, false))
     return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.l = (float*)a.l;
@@ -509,7 +528,7 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.nk = nk;
   p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
   p.batch = int32_t(a.batch);
-  p.scale_log2 = kLog2e / sqrtf(float(D));
+  p.scale_log2 = kLog2e / sqrtf(float(a.d));
   auto kern = fwd_kernel<D, VD, BN, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
@@ -524,40 +543,99 @@ extern "C" void fa_debug_set_buffer(void* buf) { cudaMemcpyToSymbol(g_dbg, &buf,
 }  // namespace sm100
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int64_t pad8(int64_t n) { return (n + 7) & ~int64_t(7); }
+static size_t al256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// Pitch-padded copies in the workspace for lengths that are not multiples of 8 halves (fa_pack.cu).
+struct FwdPack {
+  bool q, k;
+  size_t off_q, off_k, off_v, off_o, total;
+};
+static FwdPack fwd_pack_layout(const LaunchArgs& a) {
+  FwdPack w{};
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  w.q = (nq % 8) != 0;
+  w.k = (nk % 8) != 0;
+  size_t off = 0;
+  auto take = [&off](size_t n) { size_t o = off; off += al256(n); return o; };
+  if (w.q) {
+    w.off_q = take(size_t(a.batch) * a.d * pad8(nq) * 2);
+    w.off_o = take(size_t(a.batch) * a.v_d * pad8(nq) * 2);
+  }
+  if (w.k) {
+    w.off_k = take(size_t(a.batch) * a.d * pad8(nk) * 2);
+    w.off_v = take(size_t(a.batch) * a.v_d * pad8(nk) * 2);
+  }
+  w.total = off;
+  return w;
+}
+
+// Any channel counts up to 128 (zero-filled up to the kernel's 64 / 128 through the 3-D tensor maps) and any sequence
+// lengths (packed to a 16-byte pitch when needed): the shapes the reference's own tests draw (tests/test_1d.py:57-66,
+// test_2d.py:85-94: channels 8..32, arbitrary even lengths) run on the tensor cores.
 bool sm100_f16_forward_supports(const LaunchArgs& a) {
   if (a.dtype != 0 || a.accumulate) return false;
-  if (!((a.d == 64 || a.d == 128) && (a.v_d == 64 || a.v_d == 128))) return false;
+  if (a.d < 1 || a.v_d < 1 || a.d > 128 || a.v_d > 128) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
-  if (nq % 8 || nk % 8) return false;  // TMA: row pitch must be a multiple of 16 bytes
-  if (!aligned16(a.q) || !aligned16(a.k) || !aligned16(a.v) || !aligned16(a.o)) return false;
-  if (a.batch * std::max(a.d, a.v_d) > 0x7fffffffLL) return false;
+  const FwdPack w = fwd_pack_layout(a);
+  // TMA: base addresses and row pitches must be multiples of 16 bytes; a side whose length is not a multiple of 8 is
+  // copied into the workspace, a misaligned base with an aligned length is left to the generic kernels
+  if (!w.q && (!aligned16(a.q) || !aligned16(a.o))) return false;
+  if (!w.k && (!aligned16(a.k) || !aligned16(a.v))) return false;
+  if (w.total && (!a.workspace || (reinterpret_cast<uintptr_t>(a.workspace) & 255) || a.workspace_bytes < w.total))
+    return false;
+  if (a.batch > 0x7fffffffLL) return false;
   const int64_t pairs = (nq + 255) / 256;
   if (pairs * a.batch > 0x7fffffffLL) return false;
-  // the per-CTA tile schedule holds 32 * kMaxTileWords streamed tiles (64-key tiles for head_dim 64, else 128-key)
-  const int64_t tile = (a.d == 64 && a.v_d == 64 && a.variant != 5) ? 64 : 128;
+  // the per-CTA tile schedule holds 32 * kMaxTileWords streamed tiles (64-key tiles for head_dim <= 64, else 128-key)
+  const int64_t tile = (a.d <= 64 && a.v_d <= 64 && a.variant != 5) ? 64 : 128;
   if ((nk + tile - 1) / tile > 32 * sm100::kMaxTileWords) return false;
   return true;
 }
 
 size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a);  // fa_bwd_f16_sm100.cu
 size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
-  return backward ? sm100_f16_bwd_workspace_bytes(a) : 0;
+  if (a.d > 128 || a.v_d > 128) return 0;
+  return backward ? sm100_f16_bwd_workspace_bytes(a) : fwd_pack_layout(a).total;
 }
 
-// head_dim 64: the 64-key / two-CTAs-per-SM configuration is faster on every workload measured (S1 1.01 -> 0.67 ms,
+// head_dim <= 64: the 64-key / two-CTAs-per-SM configuration is faster on every workload measured (S1 1.01 -> 0.67 ms,
 // S2 3.95 -> 2.01 ms, C3 0.84 -> 0.51 ms, C4 0.86 -> 0.73 ms; profiles/r1_short_sequences.md); override 5 keeps the
 // 128-key / one-CTA configuration reachable for A/B runs.
-cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 128 && a.v_d == 128) {
-    return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
-  }
-  if (a.d == 64 && a.v_d == 64) {
+static cudaError_t forward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+  const bool d_small = a.d <= 64, v_small = a.v_d <= 64;
+  if (!d_small && !v_small) return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
+  if (d_small && v_small) {
     if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
     return sm100::launch_fwd<64, 64, 128, 1>(a, stream);
   }
-  if (a.d == 128 && a.v_d == 64) return sm100::launch_fwd<128, 64, 128, 1>(a, stream);
+  if (!d_small) return sm100::launch_fwd<128, 64, 128, 1>(a, stream);
   return sm100::launch_fwd<64, 128, 128, 1>(a, stream);
+}
+
+cudaError_t sm100_f16_forward(const LaunchArgs& a0, cudaStream_t stream) {
+  const FwdPack w = fwd_pack_layout(a0);
+  if (!w.total) return forward_dispatch(a0, stream);
+  LaunchArgs a = a0;
+  char* ws = static_cast<char*>(a0.workspace);
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  cudaError_t e;
+  if (w.q) {
+    a.q_pitch = pad8(nq);
+    if ((e = pack_rows(2, a0.q, ws + w.off_q, a.batch * a.d, nq, nq, a.q_pitch, stream)) != cudaSuccess) return e;
+    a.q = ws + w.off_q;
+    a.o = ws + w.off_o;
+  }
+  if (w.k) {
+    a.k_pitch = pad8(nk);
+    if ((e = pack_rows(2, a0.k, ws + w.off_k, a.batch * a.d, nk, nk, a.k_pitch, stream)) != cudaSuccess) return e;
+    if ((e = pack_rows(2, a0.v, ws + w.off_v, a.batch * a.v_d, nk, nk, a.k_pitch, stream)) != cudaSuccess) return e;
+    a.k = ws + w.off_k;
+    a.v = ws + w.off_v;
+  }
+  if ((e = forward_dispatch(a, stream)) != cudaSuccess) return e;
+  if (w.q) return pack_rows(2, ws + w.off_o, a0.o, a.batch * a.v_d, nq, a.q_pitch, nq, stream);
+  return cudaSuccess;
 }
 
 }  // namespace fa

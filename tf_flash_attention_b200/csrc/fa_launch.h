@@ -20,10 +20,15 @@ struct LaunchArgs {
   const void *q, *k, *v;
   void *o, *l, *m;                // forward outputs / backward inputs
   const void* d_o;
+  const void* prep_d_o;  // dense dO for the statistics pass (d_o itself may point at a pitch-padded copy)
   void *d_q, *d_k, *d_v;
   void* workspace;
   size_t workspace_bytes;
   int32_t partial_keys;  // the call covers a shard of the keys only (ring): no per-row renormalisation in the backward
+  // elements between consecutive channel rows of the q-length tensors (Q, O, dO, dQ) and the k-length tensors (K, V, dK,
+  // dV); 0 = dense (the sequence length). Set by the pitch-padding pack pass (fa_pack.cu) for lengths that are not
+  // multiples of 8 halves, which TMA cannot address directly (row pitch must be a multiple of 16 bytes).
+  int64_t q_pitch, k_pitch;
   int32_t grad_split;  // fp16 backward: dS handed to the tensor cores as hi + lo fp16 pairs (fa_set_grad_precision)
   int32_t variant;  // fa_set_path_override value (0 auto; 4 = fp16 backward as two kernels; 5 / 6 = forward tile configuration)
 };
@@ -58,6 +63,10 @@ cudaError_t grad_finalize(int dtype, const void* acc, void* out, int64_t n, cuda
 // channel-last <-> channel-first adapter (fa_layout.cu)
 cudaError_t layout_transpose(int dtype, const void* x, void* y, int64_t B, int64_t S, int32_t H, int32_t C,
                              int to_channel_first, int variant, cudaStream_t stream);
+
+// pitch-padding copies for the TMA paths (fa_pack.cu): rows of `len` elements, source / destination pitches in elements
+cudaError_t pack_rows(int elt_bytes, const void* src, void* dst, int64_t rows, int64_t len, int64_t src_pitch,
+                      int64_t dst_pitch, cudaStream_t stream);
 
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);

@@ -81,6 +81,21 @@ __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t smem_src,
                "r"(smem_src), "r"(x), "r"(y)
                : "memory");
 }
+// Channel-first tensors are described to TMA as 3-D [batch][channels][sequence] (fa::sm100::make_map_3d): the box spans
+// 64 sequence positions x the kernel's padded channel count of ONE batch element, so channels beyond the tensor's own
+// count are zero-filled on loads and clipped on stores instead of reading / writing the next batch element.
+__device__ __forceinline__ void tma_load_bc(uint32_t smem_dst, const void* map, uint32_t bar, int32_t x, int32_t b) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(0), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_bc(const void* map, uint32_t smem_src, int32_t x, int32_t b) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(x), "r"(0), "r"(b)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // shared-memory source of every committed bulk store has been read (enough before the CTA reuses the tile or exits;
 // the global writes complete on their own before the grid does)
