@@ -60,11 +60,17 @@ __device__ long long* g_dbg = nullptr;
 // Softmax / MMA hand-off (round-2 A/B on B200, profiles/r2_fwd_variants.md; all variants bit-equal in O, l, m):
 // the row max runs as four independent chains (a single chain is 63 dependent FMNMX3), and with 128-key tiles P is
 // handed to the MMA warp in two halves, so P V of keys 0..63 runs while the exponentials of keys 64..127 are still
-// being computed (C2 forward 1024 -> 1083 TFLOPS). The event-driven issuer that also issued the upper half of the next
-// Q K^T early measured slower (953 TFLOPS) and was removed.
+// being computed (C2 forward 1024 -> 1083 TFLOPS). Measured and removed (profiles/r2_fwd_variants.md): an event-driven
+// issuer that also issued the upper half of the next Q K^T early (953), a 96 + 32 key hand-off (1059), exponentials
+// issued against the previous reference max with the row max computed in their shadow (1069), an FA-3 style turn on
+// the MUFU pipe between the two warpgroups (1080), 12.5 / 25 / 37.5 % of the exponentials as FMA-pipe polynomials
+// (1076 / 1045 / 1004). The kernel runs under the board's power cap (1.58 GHz, sw_power_cap active for the whole
+// run), so shortening stall chains buys nothing once the clock governor takes the cycles back: what counts is
+// energy per tile.
 template <int D, int VD, int BN>
 struct FwdCfg {
-  static constexpr bool kHalves = BN == 128;               // P handed over in two 64-key halves
+  static constexpr bool kHalves = BN == 128;               // P handed over in two parts
+  static constexpr int kSplitKs = 4;                       // first part: keys 0..63 (four K = 16 steps of P V)
   static constexpr int kCh = D > VD ? D : VD;
   static constexpr int kQTileBytes = kBlockM * kCh * 2;   // doubles as the O staging tile
   static constexpr int kStageBytes = BN * kCh * 2;
@@ -205,10 +211,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             mma_ss(tmem_base + i * kBlockN, da, db, idesc_qk, ks > 0);
           }
         };
-        auto issue_pv_half = [&](int i, int stage, bool accumulate, int half) {   // keys 64 * half .. + 63
+        // first part: keys [0, 16 * kSplitKs), handed over while the last exponentials are still running; second part: the rest
+        auto issue_pv_half = [&](int i, int stage, bool accumulate, int half) {
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
-          for (int ks = half * (kBlockN / 32); ks < (half + 1) * (kBlockN / 32); ++ks) {
+          for (int ks = half * Cfg::kSplitKs; ks < (half ? kBlockN / 16 : Cfg::kSplitKs); ++ks) {
             const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
             mma_ts(tmem_base + Cfg::kColO + i * VD, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
                    (accumulate || ks > 0) ? 1u : 0u);
@@ -333,16 +340,19 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
       }
       if (r == 0) FA_STAMP(i, j, 1);
       // row max as four independent chains (each still fuses into 3-input max instructions)
-      float m4[4] = {s[0], s[1], s[2], s[3]};
+      auto row_max = [&]() {
+        float m4[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int c = 4; c + 8 <= kBlockN; c += 8) {
+        for (int c = 4; c + 8 <= kBlockN; c += 8) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) m4[e] = fmaxf(fmaxf(m4[e], s[c + e]), s[c + 4 + e]);
-      }
+          for (int e = 0; e < 4; ++e) m4[e] = fmaxf(fmaxf(m4[e], s[c + e]), s[c + 4 + e]);
+        }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], s[kBlockN - 4 + e]);
-      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      const float mx2 = mx * scale_log2;  // -inf stays -inf (scale > 0)
+        for (int e = 0; e < 4; ++e) m4[e] = fmaxf(m4[e], s[kBlockN - 4 + e]);
+        return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      };
+      uint32_t pk0[16], pk1[16];
+      const float mx2 = row_max() * scale_log2;   // -inf stays -inf (scale > 0)
       m_true = fmaxf(m_true, mx2);
       if (j == 0) {
         m_ref = mx2;
@@ -365,44 +375,35 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         }
       }
       const float m_use = (m_ref == NEG_INF) ? 0.f : m_ref;
-      // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
       float sum0 = 0.f, sum1 = 0.f;
-      if constexpr (Cfg::kHalves) {
-        auto exp_chunk = [&](int c, uint32_t* pk) {
+      auto exp_cols = [&](int c0, int n, uint32_t* pk) {   // columns [c0, c0 + n) -> fp16 pairs
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
-            const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
-            sum0 += p0;
-            sum1 += p1;
-            pk[e >> 1] = pack_half2(p0, p1);
-          }
-        };
-        uint32_t pk0[16], pk1[16];
-        exp_chunk(0, pk0);
+        for (int e = 0; e < n; e += 2) {
+          const float p0 = ex2(fmaf(s[c0 + e], scale_log2, -m_use));
+          const float p1 = ex2(fmaf(s[c0 + e + 1], scale_log2, -m_use));
+          sum0 += p0;
+          sum1 += p1;
+          pk[e >> 1] = pack_half2(p0, p1);
+        }
+      };
+      // P = exp2(S*scale*log2e - m) -> fp16 pairs written over S, 32 columns at a time
+      if constexpr (Cfg::kHalves) {
+        exp_cols(0, 32, pk0);
         tmem_st16(t_s + 0, pk0);
-        exp_chunk(1, pk1);
+        exp_cols(32, 32, pk1);
         tmem_st16(t_s + 16, pk1);
-        exp_chunk(2, pk0);          // the stores of the first half complete under these exponentials
+        exp_cols(64, 32, pk0);        // the stores of the first half complete under these exponentials
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(bar_p_half + 8 * i);   // keys 0..63 of P are in TMEM: P V can start on them
         tmem_st16(t_s + 32, pk0);
-        exp_chunk(3, pk1);
+        exp_cols(96, 32, pk1);
         tmem_st16(t_s + 48, pk1);
       } else {
 #pragma unroll
         for (int c = 0; c < kBlockN / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(s[c * 32 + e], scale_log2, -m_use));
-            const float p1 = ex2(fmaf(s[c * 32 + e + 1], scale_log2, -m_use));
-            sum0 += p0;
-            sum1 += p1;
-            pk[e >> 1] = pack_half2(p0, p1);
-          }
-          tmem_st16(t_s + c * 16, pk);
+          exp_cols(c * 32, 32, pk0);
+          tmem_st16(t_s + c * 16, pk0);
         }
       }
       l_sum += sum0 + sum1;
