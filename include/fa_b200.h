@@ -245,6 +245,31 @@ void fa_set_path_override(int path);
 int fa_set_grad_precision(int mode);
 const char* fa_version(void);
 
+/* ---- K/V ring data plane (single long sequence sharded over the GPUs of a node; new functionality, the reference is
+ * single-GPU). Shards move between neighbouring ranks as peer copies on the copy engines (NVLink 5 / NVSwitch) into
+ * receive slots exported with CUDA IPC; arrival and reuse are stream-ordered flag waits (no kernel, no host sync). One
+ * process per GPU; every rank makes the same sequence of calls. csrc/fa_ring.cu.
+ *   fa_ring_create        allocates n_slots receive slots of slot_bytes on the current device and fills handle_blob
+ *                         (FA_RING_HANDLE_BYTES) for the neighbours; the caller exchanges the blobs (any channel);
+ *   fa_ring_connect       opens the blobs of rank+1 (destination of fa_ring_send) and rank-1;
+ *   fa_ring_slot          device pointer of a local receive slot;
+ *   fa_ring_send          after the work queued on after_stream so far (and, when forwarded_slot >= 0, once that local
+ *                         slot has been filled; and once the neighbour has released dst_slot), copies n_parts pieces
+ *                         (each placed at the next 256-byte boundary) into dst_slot of rank+1 and marks it filled;
+ *   fa_ring_recv_wait     `stream` waits until the next fill of `slot` has arrived;
+ *   fa_ring_recv_release  after the work queued on `stream` so far (and after any forwarding copy of the slot), marks
+ *                         the slot reusable for rank-1.                                                              */
+#define FA_RING_HANDLE_BYTES 128
+typedef struct fa_ring fa_ring_t;
+int fa_ring_create(int32_t rank, int32_t world, size_t slot_bytes, int32_t n_slots, fa_ring_t** out, void* handle_blob);
+int fa_ring_connect(fa_ring_t* ring, const void* next_rank_blob, const void* prev_rank_blob);
+void* fa_ring_slot(fa_ring_t* ring, int32_t slot);
+int fa_ring_send(fa_ring_t* ring, int32_t dst_slot, int32_t n_parts, const void* const* src, const size_t* bytes,
+                 int32_t forwarded_slot, void* after_stream);
+int fa_ring_recv_wait(fa_ring_t* ring, int32_t slot, void* stream);
+int fa_ring_recv_release(fa_ring_t* ring, int32_t slot, void* stream);
+int fa_ring_destroy(fa_ring_t* ring);
+
 #ifdef __cplusplus
 }
 #endif

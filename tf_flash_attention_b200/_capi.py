@@ -11,6 +11,7 @@ _HERE = os.path.abspath(os.path.dirname(__file__))
 LIB_PATH = os.environ.get("FA_B200_LIB") or os.path.join(_HERE, "libfa_b200.so")  # env override: developer A/B builds
 
 FA_F16, FA_F32, FA_F64 = 0, 1, 2
+FA_RING_HANDLE_BYTES = 128
 RULES = {"full": 0, "causal": 1, "local": 2}
 SYNC_MODES = {"none_front": 0, "scale_front": 1, "scale_end": 2}
 
@@ -105,6 +106,13 @@ def _load():
         "fa_kernel_timing": (None, [C.c_int]),
         "fa_kernel_timings": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
         "fa_version": (C.c_char_p, []),
+        "fa_ring_create": (C.c_int, [i32, i32, sz, i32, C.POINTER(vp), vp]),
+        "fa_ring_connect": (C.c_int, [vp, vp, vp]),
+        "fa_ring_slot": (vp, [vp, i32]),
+        "fa_ring_send": (C.c_int, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), i32, vp]),
+        "fa_ring_recv_wait": (C.c_int, [vp, i32, vp]),
+        "fa_ring_recv_release": (C.c_int, [vp, i32, vp]),
+        "fa_ring_destroy": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
