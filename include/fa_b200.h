@@ -244,6 +244,10 @@ void fa_set_path_override(int path);
  * Returns FA_OK or FA_EINVAL_SHAPE for an unknown mode.                                                         */
 int fa_set_grad_precision(int mode);
 const char* fa_version(void);
+/* Launch-plan cache counters (csrc/fa_plan.h): out4 = {tensor-map encodes, tensor-map cache hits,
+ * cudaFuncSetAttribute calls, attribute cache hits} since the last reset. A repeated call on the same buffers makes no
+ * driver call besides its kernel launches: the first two / second two counters move only in their "hits" half.    */
+int fa_plan_stats(uint64_t* out4, int reset);
 
 /* ---- K/V ring data plane (single long sequence sharded over the GPUs of a node; new functionality, the reference is
  * single-GPU). Shards move between neighbouring ranks as peer copies on the copy engines (NVLink 5 / NVSwitch) into

@@ -106,6 +106,7 @@ def _load():
         "fa_kernel_timing": (None, [C.c_int]),
         "fa_kernel_timings": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
         "fa_version": (C.c_char_p, []),
+        "fa_plan_stats": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
         "fa_ring_create": (C.c_int, [i32, i32, sz, i32, C.POINTER(vp), vp]),
         "fa_ring_connect": (C.c_int, [vp, vp, vp]),
         "fa_ring_slot": (vp, [vp, i32]),

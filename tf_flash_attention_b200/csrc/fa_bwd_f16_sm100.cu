@@ -18,6 +18,7 @@
 // dS = P (dP - D) scale (:1544-1546), D = rowsum(dO o O) (:1882-1891).
 #include "fa_common.cuh"
 #include "fa_launch.h"
+#include "fa_plan.h"
 #include "sm100_ptx.cuh"
 #include "sm100_tiles.cuh"
 
@@ -1393,20 +1394,10 @@ static size_t stats_bytes(int64_t batch, int64_t nq) {
 
 static bool make_map_f32_sw128(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols,
                                int box_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 enc = []() {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
-  }();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t gstride[1] = {cuuint64_t(cols) * 4};
-  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const uint64_t gdim[2] = {uint64_t(cols), uint64_t(rows)};
+  const uint64_t gstride[1] = {uint64_t(cols) * 4};
+  const uint32_t box[2] = {uint32_t(box_cols), uint32_t(box_rows)};
+  return plan::tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // =================================================================================================
@@ -1965,7 +1956,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       {
         auto kern = bwd_fused_kernel<D, VD>;
         cudaError_t e =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<D, VD>::kSmemBytes);
+            plan::ensure_smem(kern, FusedCfg<D, VD>::kSmemBytes);
         if (e != cudaSuccess) return e;
         fp.base.n_blocks = (nk + kBM - 1) / kBM;
         ScopedKernel timed("bwd_fused_f16_sm100", stream);
@@ -1988,7 +1979,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     if (a.variant != 4) {
       auto kern = split ? bwd_dq_small_kernel<D, VD, true> : bwd_dq_small_kernel<D, VD, false>;
       cudaError_t e =
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmallCfg<D, VD>::kSmemBytes);
+          plan::ensure_smem(kern, DqSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
       p.n_blocks = (nq + kBM - 1) / kBM;
       ScopedKernel timed("bwd_dq_f16_sm100_2cta", stream);
@@ -2000,7 +1991,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   }
   if (!dq_done) {
     auto kern = split ? bwd_dq_kernel<D, VD, true> : bwd_dq_kernel<D, VD, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DqCfg<D, VD>::kSmemBytes);
+    cudaError_t e = plan::ensure_smem(kern, DqCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nq + 2 * kBM - 1) / (2 * kBM);
     ScopedKernel timed("bwd_dq_f16_sm100", stream);
@@ -2012,7 +2003,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     if (a.variant != 4) {
       auto kern = split ? bwd_dkdv_small_kernel<D, VD, true> : bwd_dkdv_small_kernel<D, VD, false>;
       cudaError_t e =
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmallCfg<D, VD>::kSmemBytes);
+          plan::ensure_smem(kern, DkvSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
       p.n_blocks = (nk + kBM - 1) / kBM;
       ScopedKernel timed("bwd_dkdv_f16_sm100_2cta", stream);
@@ -2023,7 +2014,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   {
     auto kern = split ? bwd_dkdv_kernel<D, VD, true> : bwd_dkdv_kernel<D, VD, false>;
     cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvCfg<D, VD>::kSmemBytes);
+        plan::ensure_smem(kern, DkvCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nk + kBM - 1) / kBM;
     ScopedKernel timed("bwd_dkdv_f16_sm100", stream);

@@ -21,6 +21,7 @@
 
 #include "fa_common.cuh"
 #include "fa_launch.h"
+#include "fa_plan.h"
 #include "sm100_ptx.cuh"
 #include "sm100_tiles.cuh"
 
@@ -62,9 +63,16 @@ struct alignas(64) BwdF32Params {
 };
 
 // ---- operand split and row statistics --------------------------------------------------------------------
-__global__ void bwd_prep_f32(const float* __restrict__ o, const float* __restrict__ d_o, const float* __restrict__ l,
-                             const float* __restrict__ m, float* __restrict__ lse2, float* __restrict__ dsum,
-                             float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
+struct PrepJob {
+  const float *o, *d_o, *l, *m;
+  float *lse2, *dsum, *lse2_refined;
+  int64_t batch;
+  int32_t v_d, nq;
+};
+__device__ __forceinline__ void bwd_prep_f32(const float* __restrict__ o, const float* __restrict__ d_o,
+                                             const float* __restrict__ l, const float* __restrict__ m,
+                                             float* __restrict__ lse2, float* __restrict__ dsum,
+                                             float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
   const int64_t total = batch * nq;
   // the padding behind the arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kXStatPad) {
@@ -646,9 +654,14 @@ struct SplitJobs {
   __nv_bfloat16* dst[4][3];
   int64_t n[4];
 };
-// one launch for the four operands: blockIdx.y selects the tensor
-__global__ void split_bf16x3_all(const SplitJobs jobs) {
+// one launch for the four operands and the row statistics: blockIdx.y selects the tensor, y == 4 the statistics pass
+__global__ void split_bf16x3_all(const SplitJobs jobs, const PrepJob prep) {
   const int t = blockIdx.y;
+  if (t == 4) {
+    bwd_prep_f32(prep.o, prep.d_o, prep.l, prep.m, prep.lse2, prep.dsum, prep.lse2_refined, prep.batch, prep.v_d,
+                 prep.nq);
+    return;
+  }
   const float* __restrict__ x = jobs.src[t];
   const int64_t n = jobs.n[t];
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
@@ -714,21 +727,15 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
       nmax = std::max(nmax, n[t]);
     }
     const int blocks = int(std::min<int64_t>((nmax + 255) / 256, 148 * 8));
-    ScopedKernel timed("split_bf16x3", stream);
-    split_bf16x3_all<<<dim3(blocks, 4), 256, 0, stream>>>(jobs);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
-  {
-    const int64_t total = a.batch * int64_t(nq);
-    const int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 16));
-    ScopedKernel timed("bwd_prep_f32", stream);
-    bwd_prep_f32<<<blocks, 256, 0, stream>>>((const float*)a.o, (const float*)a.d_o, (const float*)a.l,
-                                             (const float*)a.m, lse2, dsum, lse2_refined, a.batch, VD, nq);
+    const PrepJob prep{(const float*)a.o, (const float*)a.d_o, (const float*)a.l, (const float*)a.m, lse2, dsum,
+                       lse2_refined, a.batch, VD, nq};
+    ScopedKernel timed("split_bf16x3+prep", stream);
+    split_bf16x3_all<<<dim3(blocks, 5), 256, 0, stream>>>(jobs, prep);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
     auto kern = bwd_dq_f32_kernel<D, VD>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    e = plan::ensure_smem(kern, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nq + kXM - 1) / kXM;
     ScopedKernel timed("bwd_dq_f32_bf16x3_sm100", stream);
@@ -737,7 +744,7 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   }
   {
     auto kern = bwd_dkdv_f32_kernel<D, VD>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    e = plan::ensure_smem(kern, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nk + kXM - 1) / kXM;
     ScopedKernel timed("bwd_dkdv_f32_bf16x3_sm100", stream);

@@ -14,6 +14,7 @@
 // so no transposes are needed anywhere.
 #include "fa_common.cuh"
 #include "fa_launch.h"
+#include "fa_plan.h"
 #include "sm100_ptx.cuh"
 #include "sm100_tiles.cuh"
 
@@ -467,47 +468,26 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
-  }();
-  return fn;
-}
-
-// 2-D view [rows = batch*channels][cols = sequence] of a channel-first fp16 tensor
+// 2-D view [rows = batch*channels][cols = sequence] of a channel-first fp16 tensor (the fp32 families' bf16 / workspace
+// tensors are described this way)
 bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_cols, int box_rows,
                  bool swizzle128) {
-  auto enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t gstride[1] = {cuuint64_t(cols) * 2};
-  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  const uint64_t gdim[2] = {uint64_t(cols), uint64_t(rows)};
+  const uint64_t gstride[1] = {uint64_t(cols) * 2};
+  const uint32_t box[2] = {uint32_t(box_cols), uint32_t(box_rows)};
+  return plan::tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 // 3-D view [batch][channels][sequence] of a channel-first fp16 tensor (`pitch` elements between channel rows): the box is
 // 64 positions x box_rows channels of one batch element; channels past `channels` are zero-filled / clipped.
 bool make_map_3d(CUtensorMap* map, const void* base, int64_t batch, int64_t channels, int64_t seq, int64_t pitch,
                  int box_rows, bool swizzle128) {
-  auto enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gdim[3] = {cuuint64_t(seq), cuuint64_t(channels), cuuint64_t(batch)};
-  cuuint64_t gstride[2] = {cuuint64_t(pitch) * 2, cuuint64_t(pitch) * 2 * cuuint64_t(channels)};
-  cuuint32_t box[3] = {64u, cuuint32_t(box_rows), 1u};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  const uint64_t gdim[3] = {uint64_t(seq), uint64_t(channels), uint64_t(batch)};
+  const uint64_t gstride[2] = {uint64_t(pitch) * 2, uint64_t(pitch) * 2 * uint64_t(channels)};
+  const uint32_t box[3] = {64u, uint32_t(box_rows), 1u};
+  return plan::tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 template <int D, int VD, int BN, int MINB>
@@ -531,7 +511,7 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.batch = int32_t(a.batch);
   p.scale_log2 = kLog2e / sqrtf(float(a.d));
   auto kern = fwd_kernel<D, VD, BN, MINB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  cudaError_t e = plan::ensure_smem(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   ScopedKernel timed(BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64", stream);
   kern<<<unsigned(int64_t(p.n_qpairs) * p.batch), kThreads, Cfg::kSmemBytes, stream>>>(p);

@@ -14,6 +14,7 @@
 // 425-1077, FFMA). The fp32 backward and fp64 run on the FFMA / DFMA kernels of fa_generic.cu.
 #include "fa_common.cuh"
 #include "fa_launch.h"
+#include "fa_plan.h"
 #include "sm100_ptx.cuh"
 #include "sm100_tiles.cuh"
 
@@ -42,8 +43,19 @@ struct alignas(64) F32FwdParams {
 };
 
 // hi = x with the low 13 mantissa bits cleared (exactly representable in TF32), lo = x - hi (exact)
-__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
-                                  int64_t n) {
+struct SplitTf32Jobs {
+  const float* src[3];
+  float* hi[3];
+  float* lo[3];
+  int64_t n[3];
+};
+// one launch for Q, K and V: blockIdx.y selects the tensor
+__global__ void split_tf32_kernel(const SplitTf32Jobs jobs) {
+  const int t = blockIdx.y;
+  const float* __restrict__ x = jobs.src[t];
+  float* __restrict__ hi = jobs.hi[t];
+  float* __restrict__ lo = jobs.lo[t];
+  const int64_t n = jobs.n[t];
   for (int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 4; i < n;
        i += int64_t(gridDim.x) * blockDim.x * 4) {
     if (i + 3 < n) {
@@ -398,21 +410,12 @@ __global__ void __launch_bounds__(kF32Threads, 1) fwd_f32_kernel(const __grid_co
 // ---- host side ---------------------------------------------------------------------------------
 // swizzle: 0 none, 1 = 128B (K-major operands), 2 = 128B with 32-byte atoms (MN-major TF32 operands)
 static bool make_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int swizzle) {
-  static PFN_cuTensorMapEncodeTiled_v12000 enc = []() {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
-  }();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t gstride[1] = {cuuint64_t(cols) * 4};
-  cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE,
-             swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const uint64_t gdim[2] = {uint64_t(cols), uint64_t(rows)};
+  const uint64_t gstride[1] = {uint64_t(cols) * 4};
+  const uint32_t box[2] = {32u, uint32_t(box_rows)};
+  return plan::tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box,
+                          swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                       : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
@@ -433,10 +436,19 @@ cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   float* hi[3] = {qh, kh, vh};
   float* lo[3] = {ql, kl, vl};
   const size_t cnt[3] = {nqe, nke, nve};
-  for (int t = 0; t < 3; ++t) {
-    const int blocks = int(std::min<size_t>((cnt[t] / 4 + 255) / 256 + 1, 148 * 16));
+  {
+    SplitTf32Jobs jobs;
+    size_t most = 0;
+    for (int t = 0; t < 3; ++t) {
+      jobs.src[t] = src[t];
+      jobs.hi[t] = hi[t];
+      jobs.lo[t] = lo[t];
+      jobs.n[t] = int64_t(cnt[t]);
+      most = std::max(most, cnt[t]);
+    }
+    const int blocks = int(std::min<size_t>((most / 4 + 255) / 256 + 1, 148 * 8));
     ScopedKernel timed("split_tf32", stream);
-    split_tf32_kernel<<<blocks, 256, 0, stream>>>(src[t], hi[t], lo[t], int64_t(cnt[t]));
+    split_tf32_kernel<<<dim3(blocks, 3), 256, 0, stream>>>(jobs);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
@@ -455,7 +467,7 @@ cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   p.batch = int32_t(a.batch);
   p.scale_log2 = kF32Log2e / sqrtf(float(D));
   auto kern = fwd_f32_kernel<D, VD>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  cudaError_t e = plan::ensure_smem(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
   ScopedKernel timed("fwd_f32_3xtf32_sm100", stream);
   kern<<<unsigned(int64_t(p.n_qtiles) * p.batch), kF32Threads, Cfg::kSmemBytes, stream>>>(p);

@@ -15,6 +15,7 @@
 //   fully masked rows: O=0, l=0, m=0xFA… flash_attention_forward.cc:352-365
 #include "fa_common.cuh"
 #include "fa_launch.h"
+#include "fa_plan.h"
 
 namespace fa {
 namespace generic {
@@ -489,7 +490,7 @@ static size_t dkdv_smem(int d, int v_d, int BM) {
 template <typename K, typename P>
 static cudaError_t launch(const char* name, K kernel, const P& params, int64_t grid, size_t smem,
                           cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = plan::ensure_smem(kernel, int(smem));
   if (e != cudaSuccess) return e;
   ScopedKernel timed(name, stream);
   kernel<<<unsigned(grid), NT, smem, stream>>>(params);
