@@ -521,6 +521,10 @@ cudaError_t forward_t(const LaunchArgs& a, cudaStream_t stream) {
     return launch("generic_fwd", fwd_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                   \
                   fwd_smem<T>(a.d, a.v_d, BM_), stream);                                   \
   } while (0)
+  // fp64, up to 64 channels: 64 x 64 tiles (4 x 4 accumulators per thread: one shared-memory load per two DFMAs instead
+  // of one per DFMA with the 32 x 32 tiles; C4 fp64 and the reference's fp64 benchmark shapes)
+  if (sizeof(typename AccOf<T>::type) == 8 && ns <= 4 && a.d <= 64 && fwd_smem<T>(a.d, a.v_d, 64) <= kSmemMax)
+    FA_FWD(64, 4);
   if (ns <= 2 && fwd_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_FWD(BIG, 2);
   if (ns <= 8 && fwd_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_FWD(BIG, 8);
   if (ns <= 16 && fwd_smem<T>(a.d, a.v_d, SMALL) <= kSmemMax) FA_FWD(SMALL, 16);
@@ -564,6 +568,7 @@ cudaError_t backward_t(const LaunchArgs& a, cudaStream_t stream) {
     return launch("generic_bwd_dkdv", bwd_dkdv_kernel<T, BM_, BM_, NS_>, p, p.batch * p.n_rtiles,                 \
                   dkdv_smem<T>(a.d, a.v_d, BM_), stream);                                     \
   } while (0)
+  if (sizeof(A) == 8 && ns <= 4 && dkdv_smem<T>(a.d, a.v_d, 64) <= kSmemMax) FA_BWD(64, 4);
   if (ns <= 2 && dkdv_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_BWD(BIG, 2);
   if (ns <= 8 && dkdv_smem<T>(a.d, a.v_d, BIG) <= kSmemMax) FA_BWD(BIG, 8);
   if (ns <= 16 && dkdv_smem<T>(a.d, a.v_d, SMALL) <= kSmemMax) FA_BWD(SMALL, 16);
