@@ -215,7 +215,7 @@ const char* fa_strerror(int status);
 int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on this thread */
 /* Which kernel family the last fa_forward/fa_backward in this process dispatched to:
  * 0 none, 1 generic SIMT (FFMA / DFMA), 2 tcgen05 fp16, 3 tcgen05 fp32 split precision
- * (forward: 3xTF32; backward: three bf16 pieces per operand).                             */
+ * (forward: 3xTF32; backward: three bf16 pieces per operand), 4 fp64 on the FP64 tensor cores (DMMA). */
 int fa_last_path(void);
 /* Number of kernel launches issued by this library in this process since the last reset. */
 int64_t fa_launch_count(int reset);

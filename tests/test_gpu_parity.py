@@ -431,8 +431,29 @@ def test_channel_last_activations_through_the_op(dtype):
 
 def test_c4_fp64_at_full_size():
     """BASELINE.json configs[3], fp64 variant at full size: full_1d cross-attention Lq = 1024, Lk = 8192, scale_end,
-    head_dim 64 (two heads; the dense oracle holds the 1024 x 8192 logits in float64). Bar 1e-12 on O and gradients."""
-    _check(np.float64, 1, "full", "scale_end", 1, 0, 0, (1, 2), 64, 64, (1024,), (8192,), seed=64)
+    head_dim 64 (two heads; the dense oracle holds the 1024 x 8192 logits in float64). Bar 1e-12 on O and gradients.
+    Runs on the FP64 tensor-core kernels (fa_f64_dmma.cu, fa_last_path() == 4)."""
+    _check(np.float64, 1, "full", "scale_end", 1, 0, 0, (1, 2), 64, 64, (1024,), (8192,), seed=64, expect_path=4)
+
+
+@pytest.mark.parametrize("case", [
+    (1, "causal", "scale_end", 1, 0, False, (2, 1, 2), 24, 9, (77,), (131,)),      # odd lengths, v_d != d
+    (1, "local", "none_front", 2, 0, False, (2,), 16, 16, (200,), (40,)),           # rows with no keys
+    (2, "local", "scale_front", 3, 1, True, (3,), 16, 40, (7, 9), (13, 5)),
+    (1, "full", "none_front", 1, 0, False, (1,), 1, 1, (1,), (1,)),
+    (1, "causal", "none_front", 1, 0, False, (2,), 64, 33, (300,), (300,)),
+], ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_fp64_tensor_core_kernels_match_oracle(case):
+    """fp64 up to 64 channels runs on `mma.sync.m8n8k4.f64` (DMMA) kernels, forward and backward, at the 1e-12 bar; the
+    generic DFMA kernels (`fa_set_path_override(1)`) give the same results within the same bar."""
+    dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
+    seed = zlib.crc32(repr(case).encode()) % 1000
+    _check(np.float64, dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=seed, expect_path=4)
+    _capi.lib.fa_set_path_override(1)
+    try:
+        _check(np.float64, dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=seed, expect_path=1)
+    finally:
+        _capi.lib.fa_set_path_override(0)
 
 
 def test_fp32_tensors_that_are_only_4_byte_aligned():

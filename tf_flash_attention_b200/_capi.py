@@ -32,7 +32,7 @@ FA_EINVAL_SEQ_SHAPE = -13
 FA_ECUDA = -100
 FA_ENODEVICE = -101
 
-PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_f32_split", 4: "reserved"}
+PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_f32_split", 4: "dmma_f64"}
 
 
 class Problem(C.Structure):

@@ -185,6 +185,9 @@ int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* 
   } else if (fa::g_path_override != 1 && p->dtype == FA_F32 && fa::sm100_f32_forward_supports(a)) {
     fa::g_last_path = 3;
     e = fa::sm100_f32_forward(a, st);
+  } else if (fa::g_path_override != 1 && p->dtype == FA_F64 && fa::f64_dmma_forward_supports(a)) {
+    fa::g_last_path = 4;
+    e = fa::f64_dmma_forward(a, st);
   } else {
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;
@@ -215,6 +218,9 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   } else if (fa::g_path_override != 1 && p->dtype == FA_F32 && fa::sm100_f32_backward_supports(a)) {
     fa::g_last_path = 3;
     e = fa::sm100_f32_backward(a, st);
+  } else if (fa::g_path_override != 1 && p->dtype == FA_F64 && fa::f64_dmma_backward_supports(a)) {
+    fa::g_last_path = 4;
+    e = fa::f64_dmma_backward(a, st);
   } else {
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;

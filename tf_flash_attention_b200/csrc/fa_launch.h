@@ -85,4 +85,10 @@ bool sm100_f32_backward_supports(const LaunchArgs& a);
 size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a);
 cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream);
 
+// fp64 on the FP64 tensor cores (mma.sync.m8n8k4.f64), up to 64 channels (fa_f64_dmma.cu)
+bool f64_dmma_forward_supports(const LaunchArgs& a);
+cudaError_t f64_dmma_forward(const LaunchArgs& a, cudaStream_t stream);
+bool f64_dmma_backward_supports(const LaunchArgs& a);
+cudaError_t f64_dmma_backward(const LaunchArgs& a, cudaStream_t stream);
+
 }  // namespace fa
