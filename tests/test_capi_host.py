@@ -64,6 +64,37 @@ def test_tile_schedule_is_conservative(tile):
                     assert cls[a, b] == 1
 
 
+def test_tile_schedule_is_conservative_on_random_strided_windows():
+    """Strided local windows (|delta| a multiple of 2^s): tiles whose delta interval holds no such multiple are skipped;
+    SKIP must still imply that no pair attends, FULL that all do, and the skipping must actually happen."""
+    rng = np.random.default_rng(7)
+    skipped = live_partial = 0
+    for _ in range(120):
+        dims = int(rng.integers(1, 3))
+        if dims == 1:
+            qs, ks = (int(rng.integers(1, 400)),), (int(rng.integers(1, 400)),)
+        else:
+            qs = (int(rng.integers(1, 14)), int(rng.integers(1, 40)))
+            ks = (int(rng.integers(1, 14)), int(rng.integers(1, 40)))
+        mode = pattern.SYNC_MODES[int(rng.integers(0, 3))]
+        w, st, cz = int(rng.integers(1, 40)), int(rng.integers(1, 9)), bool(rng.integers(0, 2))
+        tq, tk = [(8, 16), (32, 32), (64, 64), (128, 64)][int(rng.integers(0, 4))]
+        p = _capi.make_problem(0, dims, "local", mode, (1, 4) + qs, (1, 4) + ks, (1, 4) + ks, w, st, cz)
+        cls = _capi.classify_tiles(p, tq, tk)
+        m = pattern.tests_mask(qs, ks, mode, "local", w, st, cz)
+        for a in range(cls.shape[0]):
+            for b in range(cls.shape[1]):
+                blk = m[a * tq:(a + 1) * tq, b * tk:(b + 1) * tk]
+                if cls[a, b] == 0:
+                    assert not blk.any(), (dims, qs, ks, mode, w, st, cz, tq, tk, a, b)
+                    skipped += 1
+                elif cls[a, b] == 2:
+                    assert blk.all()
+                else:
+                    live_partial += 1
+    assert skipped > live_partial // 4
+
+
 def test_tile_schedule_prunes_baseline_configs():
     # C3 (BASELINE.md): 150 of the 1024 128x128 tiles are live
     p = _capi.make_problem(0, 2, "local", "none_front", (1, 64, 64, 64), (1, 64, 64, 64), (1, 64, 64, 64), 8, 0, True)
@@ -237,16 +268,14 @@ def test_estimate_forward_flops_matches_reference():
 
 @pytest.mark.parametrize("tile,resident_is_q", [(64, 1), (128, 1), (64, 0)])
 def test_closed_form_tile_masks_match_reference(tile, resident_is_q):
-    """The 32-column masks the tcgen05 kernels build per PARTIAL tile (fa_fast_mask32: intervals per grid row
-    instead of 32 evaluations of the element rule) reproduce the reference pattern bit for bit, with
-    queries resident (forward / dQ kernels) and with keys resident (dK/dV kernel)."""
+    """The 32-column masks the tcgen05 kernels build per PARTIAL tile (fa_fast_mask32: intervals per grid row, and for
+    strided windows the multiples of 2^s inside them, instead of 32 evaluations of the element rule) reproduce the
+    reference pattern bit for bit, with queries resident (forward / dQ kernels) and with keys resident (dK/dV kernel)."""
     n = 0
     for c in CASES:
-        if c["rule"] == "local" and c["log2_stride_size"] != 0:
-            continue  # strided windows use the element rule in the kernels as well
         assert np.array_equal(_capi.pattern_mask_fast(_problem(c), tile, resident_is_q), c["mask"]), case_id(c)
         n += 1
-    assert n >= 40
+    assert n >= 70
     rng = np.random.default_rng(tile + resident_is_q)
     for _ in range(150):
         dims = int(rng.integers(1, 3))
@@ -258,9 +287,10 @@ def test_closed_form_tile_masks_match_reference(tile, resident_is_q):
         rule = ["full", "causal", "local"][int(rng.integers(0, 3))]
         mode = pattern.SYNC_MODES[int(rng.integers(0, 3))]
         w, cz = int(rng.integers(1, 10)), bool(rng.integers(0, 2))
-        p = _capi.make_problem(0, dims, rule, mode, (1, 4) + qs, (1, 4) + ks, (1, 4) + ks, w, 0, cz)
+        st = int(rng.integers(0, 5)) if rule == "local" else 0      # strided windows: |delta| a multiple of 2^st
+        p = _capi.make_problem(0, dims, rule, mode, (1, 4) + qs, (1, 4) + ks, (1, 4) + ks, w, st, cz)
         assert np.array_equal(_capi.pattern_mask_fast(p, tile, resident_is_q),
-                              pattern.tests_mask(qs, ks, mode, rule, w, 0, cz)), (dims, qs, ks, rule, mode, w, cz)
+                              pattern.tests_mask(qs, ks, mode, rule, w, st, cz)), (dims, qs, ks, rule, mode, w, st, cz)
 
 
 def test_workspace_sizes_follow_the_dispatch_rules():

@@ -341,7 +341,6 @@ int fa_pattern_mask_fast(const fa_problem_t* p, int32_t tile, int32_t resident_i
   int rc = make_rule(p, &r);
   if (rc) return rc;
   if (!mask || tile < 32 || tile % 32) return FA_EINVAL_NULL;
-  if (r.rule == 2 && r.log2_stride != 0) return FA_EINVAL_RULE;
   const FaSeqMap& res_map = resident_is_q ? r.q : r.k;
   const FaSeqMap& str_map = resident_is_q ? r.k : r.q;
   for (int32_t i = 0; i < res_map.total; ++i) {

@@ -18,8 +18,8 @@
 namespace fa {
 namespace f64 {
 
-constexpr int kThreads = 128;   // 4 warps
-constexpr int kRows = 64;       // resident rows per CTA (16 per warp = two m8 tiles)
+constexpr int kRows = 64;       // resident rows per CTA: MT m8 tiles per warp, 64 / (8 MT) warps (MT = 2: 4 warps, MT = 1: 8)
+__host__ __device__ constexpr int threads_of(int mt) { return kRows / (8 * mt) * 32; }
 constexpr int kTile = 32;       // streamed positions per tile
 constexpr int kPitch = 36;      // doubles per shared-memory row of a streamed tile (conflict-free 64-bit reads)
 constexpr int kRPitch = 68;     // doubles per row of a resident tile [channel][64 rows]
@@ -42,7 +42,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int C_PAD>
 __device__ __forceinline__ void load_stream_tile(double* dst, const double* __restrict__ src, int channels, int64_t n,
                                                  int64_t x0) {
-  for (int idx = threadIdx.x; idx < C_PAD * kTile; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < C_PAD * kTile; idx += blockDim.x) {
     const int c = idx / kTile, x = idx - c * kTile;
     const bool ok = c < channels && x0 + x < n;
     cp_async8(dst + c * kPitch + x, ok ? src + int64_t(c) * n + x0 + x : src, ok);
@@ -81,8 +81,8 @@ struct FwdSmem {
   static constexpr int kBytes = kDoubles * 8;
 };
 
-template <int DP, int VP>
-__global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
+template <int DP, int VP, int MT>
+__global__ void __launch_bounds__(threads_of(MT), 2) fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -96,25 +96,25 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
   // Q tile -> shared memory [channel][row] -> A fragments (pre-scaled), two m-tiles per warp
   {
     const double* qg = p.q + b * p.d * int64_t(p.nq);
-    for (int idx = threadIdx.x; idx < DP * kRows; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < DP * kRows; idx += blockDim.x) {
       const int c = idx / kRows, r = idx - c * kRows;
       sm[c * kRPitch + r] = (c < p.d && q0 + r < p.nq) ? qg[int64_t(c) * p.nq + q0 + r] * scale : 0.0;
     }
   }
   __syncthreads();
-  double qa[2][DP / 4];
+  double qa[MT][DP / 4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int ks = 0; ks < DP / 4; ++ks) qa[mt][ks] = sm[(4 * ks + t) * kRPitch + warp * 16 + mt * 8 + g];
+    for (int ks = 0; ks < DP / 4; ++ks) qa[mt][ks] = sm[(4 * ks + t) * kRPitch + warp * (8 * MT) + mt * 8 + g];
   __syncthreads();
 
-  int row[2];
-  FaPos qpos[2];
-  double m_i[2], l_i[2], o[2][VP / 8][2];
+  int row[MT];
+  FaPos qpos[MT];
+  double m_i[MT], l_i[MT], o[MT][VP / 8][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    row[mt] = q0 + warp * 16 + mt * 8 + g;
+  for (int mt = 0; mt < MT; ++mt) {
+    row[mt] = q0 + warp * (8 * MT) + mt * 8 + g;
     qpos[mt] = fa_pos(rule, rule.q, min(row[mt], p.nq - 1));
     m_i[mt] = neg_inf<double>();
     l_i[mt] = 0.0;
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
     const int cls = fa_classify(rule, q0, q_hi, k0, min(k0 + kTile, p.nk) - 1);
 
     // S = (Q scale) K^T : 2 m-tiles x 4 n-tiles
-    double s[2][4][2];
+    double s[MT][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = 0.0;
 #pragma unroll
@@ -164,30 +164,27 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bk[nt] = Ks[(4 * ks + t) * kPitch + nt * 8 + g];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma(s[mt][nt], qa[mt][ks], bk[nt]);
     }
-    // mask
+    // mask: one closed-form 32-bit word per row and tile (fa_fast_mask32), bit = streamed column
     const bool full = cls == FA_TILE_FULL && k0 + kTile <= p.nk;
     if (!full) {
+      const int nvalid = min(kTile, p.nk - k0);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t bits = fa_fast_mask32(rule, true, qpos[mt], k0, 0, nvalid);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int kj = k0 + nt * 8 + 2 * t + e;
-          const bool kvalid = kj < p.nk;
-          const FaPos kpos = fa_pos(rule, rule.k, kvalid ? kj : p.nk - 1);
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            const bool ok = kvalid && (cls == FA_TILE_FULL || fa_attend(rule, qpos[mt], kpos));
-            if (!ok) s[mt][nt][e] = neg_inf<double>();
-          }
-        }
+          for (int e = 0; e < 2; ++e)
+            if (!((bits >> (nt * 8 + 2 * t + e)) & 1u)) s[mt][nt][e] = neg_inf<double>();
+      }
     }
     // online softmax per row (a row lives in the 4 lanes of a quad)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       double mx = s[mt][0][0];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) mx = fmax(mx, fmax(s[mt][nt][0], s[mt][nt][1]));
@@ -218,14 +215,14 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
     // O += P V : k-steps of 4 keys; A from the S fragments through quad shuffles
 #pragma unroll
     for (int kk = 0; kk < kTile / 4; ++kk) {
-      double pa[2];
+      double pa[MT];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) pa[mt] = c_to_a(s[mt][kk >> 1], kk & 1, lane);
+      for (int mt = 0; mt < MT; ++mt) pa[mt] = c_to_a(s[mt][kk >> 1], kk & 1, lane);
 #pragma unroll
       for (int vt = 0; vt < VP / 8; ++vt) {
         const double bv = Vs[(vt * 8 + g) * kPitch + 4 * kk + t];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) dmma(o[mt][vt], pa[mt], bv);
+        for (int mt = 0; mt < MT; ++mt) dmma(o[mt][vt], pa[mt], bv);
       }
     }
     __syncthreads();   // every warp is done with this stage before it is refilled
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
   // epilogue: O = acc / l, m, l (channel-first stores: 8 consecutive rows per channel and quad column)
   double* og = p.o + b * p.v_d * int64_t(p.nq);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const double l_row = quad_sum(l_i[mt]);
     const double inv = l_row > 0.0 ? 1.0 / l_row : 0.0;
     if (row[mt] < p.nq) {
@@ -261,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) fwd_kernel(const FwdParams p) {
   }
 }
 
-template <int DP, int VP>
+template <int DP, int VP, int MT>
 static cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   FwdParams p;
   p.q = (const double*)a.q; p.k = (const double*)a.k; p.v = (const double*)a.v;
@@ -270,11 +267,11 @@ static cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.n_rtiles = (p.nq + kRows - 1) / kRows;
   p.batch = a.batch;
   p.rule = a.rule;
-  auto kern = fwd_kernel<DP, VP>;
+  auto kern = fwd_kernel<DP, VP, MT>;
   cudaError_t e = plan::ensure_smem(kern, FwdSmem<DP, VP>::kBytes);
   if (e != cudaSuccess) return e;
   ScopedKernel timed("fwd_f64_dmma", stream);
-  kern<<<unsigned(p.batch * p.n_rtiles), kThreads, FwdSmem<DP, VP>::kBytes, stream>>>(p);
+  kern<<<unsigned(p.batch * p.n_rtiles), threads_of(MT), FwdSmem<DP, VP>::kBytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -312,7 +309,7 @@ __global__ void bwd_prep_kernel(const double* __restrict__ o, const double* __re
 template <int C_PAD>
 __device__ __forceinline__ void load_resident_tile(double* dst, const double* __restrict__ src, int channels, int64_t n,
                                                    int64_t x0, double scale) {
-  for (int idx = threadIdx.x; idx < C_PAD * kRows; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < C_PAD * kRows; idx += blockDim.x) {
     const int c = idx / kRows, r = idx - c * kRows;
     dst[c * kRPitch + r] = (c < channels && x0 + r < n) ? src[int64_t(c) * n + x0 + r] * scale : 0.0;
   }
@@ -326,8 +323,8 @@ struct BwdSmem {
   static constexpr int kBytes = (kResident + 2 * kStage + kStats) * 8;
 };
 
-template <int DP, int VP>
-__global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const BwdParams p) {
+template <int DP, int VP, int MT>
+__global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Qs = reinterpret_cast<double*>(smem_raw);          // [DP][kRPitch], pre-scaled by 1/sqrt(d)
   double* dOs = Qs + DP * kRPitch;                            // [VP][kRPitch]
@@ -342,12 +339,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const BwdParams p) 
   load_resident_tile<DP>(Qs, p.q + b * p.d * int64_t(p.nq), p.d, p.nq, q0, scale);
   load_resident_tile<VP>(dOs, p.d_o + b * p.v_d * int64_t(p.nq), p.v_d, p.nq, q0, 1.0);
 
-  int row[2];
-  FaPos qpos[2];
-  double lse[2], dsum[2], dq[2][DP / 8][2];
+  int row[MT];
+  FaPos qpos[MT];
+  double lse[MT], dsum[MT], dq[MT][DP / 8][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    row[mt] = q0 + warp * 16 + mt * 8 + g;
+  for (int mt = 0; mt < MT; ++mt) {
+    row[mt] = q0 + warp * (8 * MT) + mt * 8 + g;
     const bool valid = row[mt] < p.nq;
     qpos[mt] = fa_pos(rule, rule.q, min(row[mt], p.nq - 1));
     lse[mt] = valid ? p.lse[b * p.nq + row[mt]] : -neg_inf<double>();
@@ -384,63 +381,61 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const BwdParams p) 
     const double* Vs = Ks + DP * kPitch;
     const int k0 = kt * kTile;
     const int cls = fa_classify(rule, q0, q_hi, k0, min(k0 + kTile, p.nk) - 1);
-    double s[2][4][2], dp[2][4][2];
+    double s[MT][4][2], dp[MT][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = dp[mt][nt][0] = dp[mt][nt][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < DP / 4; ++ks) {
-      double a[2], bk[4];
+      double a[MT], bk[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = Qs[(4 * ks + t) * kRPitch + warp * 16 + mt * 8 + g];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = Qs[(4 * ks + t) * kRPitch + warp * (8 * MT) + mt * 8 + g];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bk[nt] = Ks[(4 * ks + t) * kPitch + nt * 8 + g];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma(s[mt][nt], a[mt], bk[nt]);
     }
 #pragma unroll
     for (int ks = 0; ks < VP / 4; ++ks) {
-      double a[2], bv[4];
+      double a[MT], bv[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = dOs[(4 * ks + t) * kRPitch + warp * 16 + mt * 8 + g];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = dOs[(4 * ks + t) * kRPitch + warp * (8 * MT) + mt * 8 + g];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bv[nt] = Vs[(4 * ks + t) * kPitch + nt * 8 + g];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma(dp[mt][nt], a[mt], bv[nt]);
     }
-    // dS = P (dP - D), P = exp(s - lse), masked; written over s
+    // dS = P (dP - D), P = exp(s - lse), masked (closed-form 32-bit word per row and tile); written over s
     const bool full = cls == FA_TILE_FULL && k0 + kTile <= p.nk;
+    const int nvalid = min(kTile, p.nk - k0);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t bits = full ? 0xffffffffu : fa_fast_mask32(rule, true, qpos[mt], k0, 0, nvalid);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int kj = k0 + nt * 8 + 2 * t + e;
-        const bool kvalid = kj < p.nk;
-        FaPos kpos;
-        if (!full) kpos = fa_pos(rule, rule.k, kvalid ? kj : p.nk - 1);
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const bool ok = full || (kvalid && (cls == FA_TILE_FULL || fa_attend(rule, qpos[mt], kpos)));
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = (bits >> (nt * 8 + 2 * t + e)) & 1u;
           const double pv = ok ? exp(s[mt][nt][e] - lse[mt]) : 0.0;   // lse = +inf on empty rows -> 0
           s[mt][nt][e] = pv * (dp[mt][nt][e] - dsum[mt]);
         }
-      }
+    }
     // dQ += dS K
 #pragma unroll
     for (int kk = 0; kk < kTile / 4; ++kk) {
-      double da[2];
+      double da[MT];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) da[mt] = c_to_a(s[mt][kk >> 1], kk & 1, lane);
+      for (int mt = 0; mt < MT; ++mt) da[mt] = c_to_a(s[mt][kk >> 1], kk & 1, lane);
 #pragma unroll
       for (int ct = 0; ct < DP / 8; ++ct) {
         const double bk = Ks[(ct * 8 + g) * kPitch + 4 * kk + t];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) dmma(dq[mt][ct], da[mt], bk);
+        for (int mt = 0; mt < MT; ++mt) dmma(dq[mt][ct], da[mt], bk);
       }
     }
     __syncthreads();
@@ -449,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const BwdParams p) 
   }
   double* dqg = p.d_q + b * p.d * int64_t(p.nq);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
     if (row[mt] < p.nq) {
 #pragma unroll
       for (int ct = 0; ct < DP / 8; ++ct)
@@ -461,8 +456,8 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dq_kernel(const BwdParams p) 
     }
 }
 
-template <int DP, int VP>
-__global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p) {
+template <int DP, int VP, int MT>
+__global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ks = reinterpret_cast<double*>(smem_raw);          // [DP][kRPitch], pre-scaled by 1/sqrt(d)
   double* Vs = Ks + DP * kRPitch;                             // [VP][kRPitch]
@@ -478,12 +473,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p
   load_resident_tile<DP>(Ks, p.k + b * p.d * int64_t(p.nk), p.d, p.nk, k0, scale);
   load_resident_tile<VP>(Vs, p.v + b * p.v_d * int64_t(p.nk), p.v_d, p.nk, k0, 1.0);
 
-  int row[2];
-  FaPos kpos[2];
-  double dk[2][DP / 8][2], dv[2][VP / 8][2];
+  int row[MT];
+  FaPos kpos[MT];
+  double dk[MT][DP / 8][2], dv[MT][VP / 8][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    row[mt] = k0 + warp * 16 + mt * 8 + g;
+  for (int mt = 0; mt < MT; ++mt) {
+    row[mt] = k0 + warp * (8 * MT) + mt * 8 + g;
     kpos[mt] = fa_pos(rule, rule.k, min(row[mt], p.nk - 1));
 #pragma unroll
     for (int ct = 0; ct < DP / 8; ++ct) dk[mt][ct][0] = dk[mt][ct][1] = 0.0;
@@ -528,61 +523,59 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p
     const int q0 = qt * kTile;
     const int cls = fa_classify(rule, q0, min(q0 + kTile, p.nq) - 1, k0, k_hi);
     // S^T = (K scale) Q^T, dP^T = V dO^T : rows = keys, columns = queries
-    double s[2][4][2], dp[2][4][2];
+    double s[MT][4][2], dp[MT][4][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) s[mt][nt][0] = s[mt][nt][1] = dp[mt][nt][0] = dp[mt][nt][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < DP / 4; ++ks) {
-      double a[2], bq[4];
+      double a[MT], bq[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = Ks[(4 * ks + t) * kRPitch + warp * 16 + mt * 8 + g];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = Ks[(4 * ks + t) * kRPitch + warp * (8 * MT) + mt * 8 + g];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bq[nt] = Qs[(4 * ks + t) * kPitch + nt * 8 + g];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma(s[mt][nt], a[mt], bq[nt]);
     }
 #pragma unroll
     for (int ks = 0; ks < VP / 4; ++ks) {
-      double a[2], bo[4];
+      double a[MT], bo[4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) a[mt] = Vs[(4 * ks + t) * kRPitch + warp * 16 + mt * 8 + g];
+      for (int mt = 0; mt < MT; ++mt) a[mt] = Vs[(4 * ks + t) * kRPitch + warp * (8 * MT) + mt * 8 + g];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) bo[nt] = dOs[(4 * ks + t) * kPitch + nt * 8 + g];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) dmma(dp[mt][nt], a[mt], bo[nt]);
     }
-    // P^T -> s, dS^T -> dp (column statistics: the queries of this tile)
+    // P^T -> s, dS^T -> dp (column statistics: the queries of this tile); one closed-form mask word per key row
     const bool full = cls == FA_TILE_FULL && q0 + kTile <= p.nq && k0 + kRows <= p.nk;
+    const int nvalid = min(kTile, p.nq - q0);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t bits = full ? 0xffffffffu
+                                 : (row[mt] < p.nk ? fa_fast_mask32(rule, false, kpos[mt], q0, 0, nvalid) : 0u);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int x = nt * 8 + 2 * t + e;
-        const int qi = q0 + x;
-        const bool qvalid = qi < p.nq;
-        const double lse_q = lse[x], d_q = dsum[x];   // zero-filled past the sequence; masked below
-        FaPos qpos;
-        if (!full) qpos = fa_pos(rule, rule.q, qvalid ? qi : p.nq - 1);
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const bool ok = full || (qvalid && row[mt] < p.nk && (cls == FA_TILE_FULL || fa_attend(rule, qpos, kpos[mt])));
-          const double pv = ok ? exp(s[mt][nt][e] - lse_q) : 0.0;
+        for (int e = 0; e < 2; ++e) {
+          const int x = nt * 8 + 2 * t + e;
+          const bool ok = (bits >> x) & 1u;
+          const double pv = ok ? exp(s[mt][nt][e] - lse[x]) : 0.0;   // stats are zero-filled past the sequence
           s[mt][nt][e] = pv;
-          dp[mt][nt][e] = pv * (dp[mt][nt][e] - d_q);
+          dp[mt][nt][e] = pv * (dp[mt][nt][e] - dsum[x]);
         }
-      }
+    }
     // dV += P^T dO, dK += dS^T Q (k-steps of 4 queries)
 #pragma unroll
     for (int kk = 0; kk < kTile / 4; ++kk) {
-      double pa[2], da[2];
+      double pa[MT], da[MT];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         pa[mt] = c_to_a(s[mt][kk >> 1], kk & 1, lane);
         da[mt] = c_to_a(dp[mt][kk >> 1], kk & 1, lane);
       }
@@ -590,13 +583,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p
       for (int ct = 0; ct < VP / 8; ++ct) {
         const double bo = dOs[(ct * 8 + g) * kPitch + 4 * kk + t];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) dmma(dv[mt][ct], pa[mt], bo);
+        for (int mt = 0; mt < MT; ++mt) dmma(dv[mt][ct], pa[mt], bo);
       }
 #pragma unroll
       for (int ct = 0; ct < DP / 8; ++ct) {
         const double bq = Qs[(ct * 8 + g) * kPitch + 4 * kk + t];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) dmma(dk[mt][ct], da[mt], bq);
+        for (int mt = 0; mt < MT; ++mt) dmma(dk[mt][ct], da[mt], bq);
       }
     }
     __syncthreads();
@@ -606,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p
   double* dkg = p.d_k + b * p.d * int64_t(p.nk);
   double* dvg = p.d_v + b * p.v_d * int64_t(p.nk);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
     if (row[mt] < p.nk) {
 #pragma unroll
       for (int ct = 0; ct < DP / 8; ++ct)
@@ -625,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_dkdv_kernel(const BwdParams p
     }
 }
 
-template <int DP, int VP>
+template <int DP, int VP, int MT>
 static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   BwdParams p;
   p.q = (const double*)a.q; p.k = (const double*)a.k; p.v = (const double*)a.v; p.d_o = (const double*)a.d_o;
@@ -647,21 +640,21 @@ static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
   }
   {
-    auto kern = bwd_dq_kernel<DP, VP>;
+    auto kern = bwd_dq_kernel<DP, VP, MT>;
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
     p.n_tiles = (p.nq + kRows - 1) / kRows;
     ScopedKernel timed("bwd_dq_f64_dmma", stream);
-    kern<<<unsigned(p.batch * p.n_tiles), kThreads, BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<unsigned(p.batch * p.n_tiles), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    auto kern = bwd_dkdv_kernel<DP, VP>;
+    auto kern = bwd_dkdv_kernel<DP, VP, MT>;
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
     p.n_tiles = (p.nk + kRows - 1) / kRows;
     ScopedKernel timed("bwd_dkdv_f64_dmma", stream);
-    kern<<<unsigned(p.batch * p.n_tiles), kThreads, BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<unsigned(p.batch * p.n_tiles), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     return cudaGetLastError();
   }
 }
@@ -686,18 +679,34 @@ bool f64_dmma_backward_supports(const LaunchArgs& a) {
 
 cudaError_t f64_dmma_backward(const LaunchArgs& a, cudaStream_t stream) {
   const bool d_small = a.d <= 32, v_small = a.v_d <= 32;
-  if (d_small && v_small) return f64::launch_bwd<32, 32>(a, stream);
-  if (d_small) return f64::launch_bwd<32, 64>(a, stream);
-  if (v_small) return f64::launch_bwd<64, 32>(a, stream);
-  return f64::launch_bwd<64, 64>(a, stream);
+  // 8 warps x one m8 tile each by default; fa_set_path_override(6): 4 warps x two m8 tiles (half the B-fragment loads
+  // per DMMA, half the warps to hide latency with)
+  if (a.variant == 6) {
+    if (d_small && v_small) return f64::launch_bwd<32, 32, 2>(a, stream);
+    if (d_small) return f64::launch_bwd<32, 64, 2>(a, stream);
+    if (v_small) return f64::launch_bwd<64, 32, 2>(a, stream);
+    return f64::launch_bwd<64, 64, 2>(a, stream);
+  }
+  if (d_small && v_small) return f64::launch_bwd<32, 32, 1>(a, stream);
+  if (d_small) return f64::launch_bwd<32, 64, 1>(a, stream);
+  if (v_small) return f64::launch_bwd<64, 32, 1>(a, stream);
+  return f64::launch_bwd<64, 64, 1>(a, stream);
 }
 
 cudaError_t f64_dmma_forward(const LaunchArgs& a, cudaStream_t stream) {
   const bool d_small = a.d <= 32, v_small = a.v_d <= 32;
-  if (d_small && v_small) return f64::launch_fwd<32, 32>(a, stream);
-  if (d_small) return f64::launch_fwd<32, 64>(a, stream);
-  if (v_small) return f64::launch_fwd<64, 32>(a, stream);
-  return f64::launch_fwd<64, 64>(a, stream);
+  // 8 warps x one m8 tile each by default; fa_set_path_override(6): 4 warps x two m8 tiles (half the B-fragment loads
+  // per DMMA, half the warps to hide latency with)
+  if (a.variant == 6) {
+    if (d_small && v_small) return f64::launch_fwd<32, 32, 2>(a, stream);
+    if (d_small) return f64::launch_fwd<32, 64, 2>(a, stream);
+    if (v_small) return f64::launch_fwd<64, 32, 2>(a, stream);
+    return f64::launch_fwd<64, 64, 2>(a, stream);
+  }
+  if (d_small && v_small) return f64::launch_fwd<32, 32, 1>(a, stream);
+  if (d_small) return f64::launch_fwd<32, 64, 1>(a, stream);
+  if (v_small) return f64::launch_fwd<64, 32, 1>(a, stream);
+  return f64::launch_fwd<64, 64, 1>(a, stream);
 }
 
 }  // namespace fa

@@ -186,6 +186,14 @@ FA_HD int32_t fa_max_absdiff(int32_t alo, int32_t ahi, int32_t blo, int32_t bhi)
   return a > b ? a : b;
 }
 
+FA_HD int64_t fa_i64max(int64_t a, int64_t b) { return a > b ? a : b; }
+FA_HD int64_t fa_i64min(int64_t a, int64_t b) { return a < b ? a : b; }
+// smallest multiple of S (> 0) that is >= v
+FA_HD int64_t fa_ceil_mult(int64_t v, int64_t S) {
+  const int64_t q = v >= 0 ? (v + S - 1) / S : -((-v) / S);
+  return q * S;
+}
+
 // Classifies the block of local q rows [q_lo, q_hi] x local k columns [k_lo, k_hi]
 // (both already clamped to valid elements). SKIP => no pair attends. FULL => every pair
 // attends. Anything else is PARTIAL and must evaluate fa_attend per element.
@@ -203,6 +211,17 @@ FA_HD int fa_classify(const FaRule& r, int32_t q_lo, int32_t q_hi, int32_t k_lo,
     if (r.dims == 2 && int64_t(fa_min_absdiff(q.c1_lo, q.c1_hi, k.c1_lo, k.c1_hi)) >= sw) return FA_TILE_SKIP;
     if (r.log2_stride != 0) {
       full = false;
+      // strided window: |delta| must be a multiple of 2^s below sw. A tile whose delta interval holds no such multiple
+      // attends nothing (conservative: the interval ignores the lattice the sync strides put the coordinates on).
+      const int64_t S = int64_t(1) << r.log2_stride;
+      {
+        const int64_t lo = fa_i64max(int64_t(q.c0_lo) - k.c0_hi, -(sw - 1)), hi = fa_i64min(int64_t(q.c0_hi) - k.c0_lo, sw - 1);
+        if (lo > hi || fa_ceil_mult(lo, S) > hi) return FA_TILE_SKIP;
+      }
+      if (r.dims == 2) {
+        const int64_t lo = fa_i64max(int64_t(q.c1_lo) - k.c1_hi, -(sw - 1)), hi = fa_i64min(int64_t(q.c1_hi) - k.c1_lo, sw - 1);
+        if (lo > hi || fa_ceil_mult(lo, S) > hi) return FA_TILE_SKIP;
+      }
     } else {
       if (fa_max_absdiff(q.c0_lo, q.c0_hi, k.c0_lo, k.c0_hi) >= r.window) full = false;
       if (r.dims == 2 && fa_max_absdiff(q.c1_lo, q.c1_hi, k.c1_lo, k.c1_hi) >= r.window) full = false;
@@ -318,16 +337,48 @@ FA_HD uint32_t interval_bits32(int32_t lo, int32_t hi, int32_t col0) {
 }
 
 // 32-bit attended mask of streamed entries [s0+col0, s0+col0+32) (only the first `nvalid` entries of
-// the tile starting at s0 exist) against one fixed resident position, for rules whose attended set
-// is an interval per grid row: full, causal, and local with log2_stride == 0; 1-D and 2-D; any sync
+// the tile starting at s0 exist) against one fixed resident position: full, causal and local rules (plain windows are an
+// interval per grid row; strided windows the multiples of 2^s inside it, fa_strided_row_bits); 1-D and 2-D; any sync
 // mode. For one grid row y of the streamed sequence the attended x are
 //   { x : |res.c0 - cx| < W and causal(order) },  cx = off0 + x*stride0,  provided |res.c1 - cy| < W,
 // an x-interval, so a chunk costs a few integer ops per grid row it touches instead of 32 evaluations
 // of the element rule.
+// bits of the streamed entries row0 + x, x in [xa, xb] (one grid row; coordinate cx = off0 + (x + xbase) * stride0), whose
+// coordinate lies in [clo, chi] and differs from c_res by a multiple of 2^s: enumerates whichever is fewer, the
+// multiples inside the interval or the positions of the row segment.
+FA_HD uint32_t fa_strided_row_bits(int32_t c_res, int32_t clo, int32_t chi, int32_t log2_stride, int32_t off0,
+                                   int32_t stride0, int32_t xbase, int32_t xa, int32_t xb, int32_t bit0) {
+  // clip the coordinate interval to the segment
+  clo = fa_imax(clo, off0 + (xa + xbase) * stride0);
+  chi = fa_imin(chi, off0 + (xb + xbase) * stride0);
+  if (clo > chi) return 0u;
+  const int32_t S = int32_t(1) << log2_stride;
+  uint32_t bits = 0;
+  const int32_t m_lo = fa_cdiv(c_res - chi, S), m_hi = fa_fdiv(c_res - clo, S);
+  if (m_hi - m_lo <= xb - xa) {
+    for (int32_t m = m_lo; m <= m_hi; ++m) {
+      const int32_t t = c_res - m * S - off0;
+      if (t % stride0 != 0) continue;
+      const int32_t x = t / stride0 - xbase;
+      if (x >= xa && x <= xb) bits |= 1u << (bit0 + x - xa);
+    }
+  } else {
+    const int32_t rem = S - 1;
+    for (int32_t x = xa; x <= xb; ++x) {
+      const int32_t cx = off0 + (x + xbase) * stride0;
+      if (cx >= clo && cx <= chi && ((c_res - cx) & rem) == 0) bits |= 1u << (bit0 + x - xa);
+    }
+  }
+  return bits;
+}
+
 FA_HD uint32_t fa_fast_mask32(const FaRule& rule, bool resident_is_q, const FaPos& res, int32_t s0,
                               int32_t col0, int32_t nvalid) {
   const FaSeqMap& sm = resident_is_q ? rule.k : rule.q;
-  const int32_t W = rule.rule == 2 ? rule.window : 0x3fffffff;
+  const bool strided = rule.rule == 2 && rule.log2_stride != 0;
+  // |delta| < W (plain windows) or |delta| < W * 2^s and a multiple of 2^s (strided windows)
+  const int64_t w64 = rule.rule == 2 ? (int64_t(rule.window) << rule.log2_stride) : int64_t(0x3fffffff);
+  const int32_t W = int32_t(w64 < 0x3fffffff ? w64 : 0x3fffffff);
   const int32_t j0 = s0 + col0;
   const int32_t jend = fa_imin(j0 + 31, s0 + nvalid - 1);
   if (jend < j0) return 0u;
@@ -338,6 +389,8 @@ FA_HD uint32_t fa_fast_mask32(const FaRule& rule, bool resident_is_q, const FaPo
       if (resident_is_q) chi = fa_imin(chi, res.c0);  // k.c0 <= q.c0
       else clo = fa_imax(clo, res.c0);                // q.c0 >= k.c0
     }
+    if (strided)
+      return fa_strided_row_bits(res.c0, clo, chi, rule.log2_stride, sm.off0, sm.stride0, sm.base0, j0, jend, 0);
     const int32_t jlo = fa_cdiv(clo - sm.off0, sm.stride0) - sm.base0;
     const int32_t jhi = fa_fdiv(chi - sm.off0, sm.stride0) - sm.base0;
     return interval_bits32(fa_imax(jlo, j0) - j0, fa_imin(jhi, jend) - j0, 0);
@@ -347,6 +400,7 @@ FA_HD uint32_t fa_fast_mask32(const FaRule& rule, bool resident_is_q, const FaPo
   for (int32_t y = y_first; y <= y_last; ++y) {
     const int32_t cy = sm.off1 + y * sm.stride1;
     if (fa_iabs(res.c1 - cy) >= W) continue;
+    if (strided && (fa_iabs(res.c1 - cy) & ((int32_t(1) << rule.log2_stride) - 1)) != 0) continue;
     int32_t clo = res.c0 - W + 1, chi = res.c0 + W - 1;
     if (rule.causal) {
       if (resident_is_q) {  // order(q) >= order(k)
@@ -357,10 +411,16 @@ FA_HD uint32_t fa_fast_mask32(const FaRule& rule, bool resident_is_q, const FaPo
         if (cy == res.c1) clo = fa_imax(clo, res.c0);
       }
     }
+    const int32_t row0 = y * sm.n0;
+    if (strided) {
+      const int32_t xa = fa_imax(j0 - row0, 0), xb = fa_imin(jend - row0, sm.n0 - 1);
+      if (xa <= xb)
+        bits |= fa_strided_row_bits(res.c0, clo, chi, rule.log2_stride, sm.off0, sm.stride0, 0, xa, xb, row0 + xa - j0);
+      continue;
+    }
     const int32_t xlo = fa_imax(fa_cdiv(clo - sm.off0, sm.stride0), 0);
     const int32_t xhi = fa_imin(fa_fdiv(chi - sm.off0, sm.stride0), sm.n0 - 1);
     if (xlo > xhi) continue;
-    const int32_t row0 = y * sm.n0;
     bits |= interval_bits32(fa_imax(row0 + xlo, j0) - j0, fa_imin(row0 + xhi, jend) - j0, 0);
   }
   return bits;

@@ -98,58 +98,6 @@ struct TileIter {
   }
 };
 
-// incremental walk over consecutive entries of one sequence map
-struct SeqWalker {
-  int32_t x, c0, c1;
-  __device__ __forceinline__ void init(const FaRule& r, const FaSeqMap& s, int32_t idx) {
-    if (r.dims == 1) {
-      x = idx;
-      c0 = s.off0 + (idx + s.base0) * s.stride0;
-      c1 = 0;
-    } else {
-      int32_t y = idx / s.n0;
-      x = idx - y * s.n0;
-      c0 = s.off0 + x * s.stride0;
-      c1 = s.off1 + y * s.stride1;
-    }
-  }
-  __device__ __forceinline__ FaPos pos(const FaRule& r) const {
-    FaPos p;
-    p.c0 = c0;
-    p.c1 = c1;
-    p.order = (c1 << r.ref_log2_0) + c0;
-    return p;
-  }
-  __device__ __forceinline__ void next(const FaRule& r, const FaSeqMap& s) {
-    ++x;
-    c0 += s.stride0;
-    if (r.dims == 2 && x == s.n0) {
-      x = 0;
-      c0 = s.off0;
-      c1 += s.stride1;
-    }
-  }
-};
-
-// 32-bit attended mask of columns [col0, col0+32) of a streamed tile starting at stream index s0,
-// for one fixed resident position. Generic (any rule / dims); kept out of line so that the big
-// unrolled softmax loops stay small in the instruction cache.
-static __device__ __noinline__ uint32_t element_mask32(const FaRule& rule, bool resident_is_q, FaPos res, int s0,
-                                               int col0, int nvalid) {
-  const FaSeqMap& sm = resident_is_q ? rule.k : rule.q;
-  SeqWalker w;
-  w.init(rule, sm, s0 + col0);
-  uint32_t bits = 0;
-#pragma unroll 1
-  for (int e = 0; e < 32; ++e) {
-    const FaPos sp = w.pos(rule);
-    const bool ok = (col0 + e < nvalid) && (resident_is_q ? fa_attend(rule, res, sp) : fa_attend(rule, sp, res));
-    bits |= ok ? (1u << e) : 0u;
-    w.next(rule, sm);
-  }
-  return bits;
-}
-
 // 1-D full/causal rows: the attended streamed columns form one interval [lo, hi] of the tile.
 // resident q: keys attended iff k.c0 <= q.c0  -> prefix      [0, limit]
 // resident k: queries attended iff q.c0 >= k.c0 -> suffix    [cmin, nvalid-1]
@@ -172,8 +120,7 @@ __device__ __forceinline__ void interval_1d(const FaRule& rule, bool resident_is
 // mask builder used by all tcgen05 kernels: closed form whenever the rule allows it
 __device__ __forceinline__ uint32_t tile_mask32(const FaRule& rule, bool resident_is_q, const FaPos& res, int s0,
                                                int col0, int nvalid) {
-  if (rule.rule != 2 || rule.log2_stride == 0) return fa_fast_mask32(rule, resident_is_q, res, s0, col0, nvalid);
-  return element_mask32(rule, resident_is_q, res, s0, col0, nvalid);
+  return fa_fast_mask32(rule, resident_is_q, res, s0, col0, nvalid);
 }
 
 }  // namespace sm100
