@@ -392,3 +392,24 @@ def test_null_workspace_is_rejected_when_one_is_needed():
     assert lib.fa_forward(C.byref(p), one, one, one, one, one, one, None, need_f, None) == _capi.FA_EINVAL_WORKSPACE
     assert lib.fa_forward(C.byref(p), one, one, one, one, one, one, one, need_f - 1, None) == _capi.FA_EINVAL_WORKSPACE
     assert lib.fa_backward(C.byref(p), *([one] * 10), None, need_b, None) == _capi.FA_EINVAL_WORKSPACE
+
+
+def test_ring_data_plane_argument_checks_and_no_device():
+    """fa_ring_* (csrc/fa_ring.cu): argument validation is host-only; without a CUDA device fa_ring_create fails with a
+    status instead of crashing (there is no CPU fallback for the data plane either)."""
+    import ctypes as C
+    lib = _capi.lib
+    blob = C.create_string_buffer(_capi.FA_RING_HANDLE_BYTES)
+    h = C.c_void_p()
+    assert lib.fa_ring_create(0, 2, 1024, 2, None, blob) == _capi.FA_EINVAL_NULL
+    assert lib.fa_ring_create(0, 2, 1024, 2, C.byref(h), None) == _capi.FA_EINVAL_NULL
+    assert lib.fa_ring_create(2, 2, 1024, 2, C.byref(h), blob) == _capi.FA_EINVAL_SHAPE      # rank out of range
+    assert lib.fa_ring_create(0, 2, 0, 2, C.byref(h), blob) == _capi.FA_EINVAL_SHAPE         # empty slots
+    assert lib.fa_ring_create(0, 2, 1024, 9, C.byref(h), blob) == _capi.FA_EINVAL_SHAPE      # too many slots
+    assert lib.fa_ring_send(None, 0, 1, None, None, -1, None) == _capi.FA_EINVAL_NULL
+    assert lib.fa_ring_recv_wait(None, 0, None) == _capi.FA_EINVAL_NULL
+    assert lib.fa_ring_destroy(None) == _capi.FA_OK
+    import torch
+    if not torch.cuda.is_available():
+        rc = lib.fa_ring_create(0, 2, 1024, 2, C.byref(h), blob)
+        assert rc in (_capi.FA_ECUDA, _capi.FA_ENODEVICE)

@@ -43,3 +43,19 @@ def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol):
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):
         err = np.abs(g.cpu().numpy().astype(np.float64) - ref[name]) / np.maximum(1.0, np.abs(ref[name]))
         assert err.max() <= tol, f"{name}: {err.max()}"
+
+
+def test_two_rank_ring_over_the_peer_copy_data_plane():
+    """N > 1 on the GPU: two ranks under torchrun run ring_causal_1d and its backward over the fa_ring_* data plane
+    (CUDA IPC slots, peer copies, stream-ordered flags) and compare their rows with the dense oracle
+    (tools/ring_check.py). Needs two GPUs in the box; skipped on the single-GPU test boxes."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "ring_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "RING_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -797,7 +798,11 @@ int fa_forward_backward_host(const fa_problem_t* p, const void* q, const void* k
   char* base = (char*)dev_arena;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t B = p->batch;
-  const int64_t nch = p->batch < 2 || a.nq_b + a.nk_b + a.nv_b + a.no_b < (size_t(64) << 20) ? 1 : std::min<int64_t>(B, 16);
+  // chunks of the batch in flight: fill + drain cost two chunk transfers, so more chunks are better until a chunk's
+  // kernels stop filling the GPU (FA_HOST_CHUNKS overrides for A/B runs)
+  int64_t want = 16;
+  if (const char* e = getenv("FA_HOST_CHUNKS")) want = std::max<int64_t>(1, atoll(e));
+  const int64_t nch = p->batch < 2 || a.nq_b + a.nk_b + a.nv_b + a.no_b < (size_t(64) << 20) ? 1 : std::min<int64_t>(B, want);
   HostPipe* pp = pipe_for(st);
   if (!pp) return FA_ENODEVICE;
   PipeLease lease(pp, st);
