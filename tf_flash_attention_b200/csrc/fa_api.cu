@@ -85,7 +85,7 @@ int fill_args(const fa_problem_t* p, fa::LaunchArgs* a) {
 
 extern "C" {
 
-const char* fa_version(void) { return "tf_flash_attention_b200 0.1 (sm_100a)"; }
+const char* fa_version(void) { return "tf_flash_attention_b200 0.2 (sm_100a)"; }
 
 const char* fa_strerror(int s) {
   switch (s) {
