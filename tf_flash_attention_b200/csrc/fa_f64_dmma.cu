@@ -305,6 +305,22 @@ __global__ void bwd_prep_kernel(const double* __restrict__ o, const double* __re
   }
 }
 
+// Problems with fewer CTAs than SMs (the reference's fp64 benchmark shapes: 8 heads x 1024 positions = 128 CTAs, each a
+// serial loop over 32 tiles) share the streamed range out over gridDim.y CTAs per resident tile; the partial gradients
+// are then added into zero-initialised outputs with fp64 atomics (the order of two or four fp64 additions is the only
+// thing that varies from run to run: ~1e-16 relative).
+__device__ __forceinline__ void split_range(int* first, int* last) {
+  if (gridDim.y == 1 || *first > *last) return;
+  const int n = *last - *first + 1, per = (n + int(gridDim.y) - 1) / int(gridDim.y);
+  const int lo = *first + int(blockIdx.y) * per;
+  *first = lo;
+  *last = min(lo + per - 1, *last);
+}
+__device__ __forceinline__ void store_or_add(double* dst, double v) {
+  if (gridDim.y == 1) *dst = v;
+  else atomicAdd(dst, v);
+}
+
 // resident [C_PAD channels][64 rows] tile -> dst[c][kRPitch], optionally scaled
 template <int C_PAD>
 __device__ __forceinline__ void load_resident_tile(double* dst, const double* __restrict__ src, int channels, int64_t n,
@@ -356,6 +372,7 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdPara
   const double* vg = p.v + b * p.v_d * int64_t(p.nk);
   int kt_first, kt_last;
   fa_k_tile_range(rule, q0, q_hi, kTile, &kt_first, &kt_last);
+  split_range(&kt_first, &kt_last);   // small grids: the streamed range is shared out over gridDim.y CTAs
   auto next_live = [&](int kt) {
     while (kt <= kt_last && fa_classify(rule, q0, q_hi, kt * kTile, min(kt * kTile + kTile, p.nk) - 1) == FA_TILE_SKIP) ++kt;
     return kt;
@@ -451,7 +468,7 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdPara
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int ch = ct * 8 + 2 * t + e;
-          if (ch < p.d) dqg[int64_t(ch) * p.nq + row[mt]] = dq[mt][ct][e] * scale;
+          if (ch < p.d) store_or_add(dqg + int64_t(ch) * p.nq + row[mt], dq[mt][ct][e] * scale);
         }
     }
 }
@@ -489,6 +506,7 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdPa
   const double* dog = p.d_o + b * p.v_d * int64_t(p.nq);
   int qt_first, qt_last;
   fa_q_tile_range(rule, k0, k_hi, kTile, &qt_first, &qt_last);
+  split_range(&qt_first, &qt_last);
   auto next_live = [&](int qt) {
     while (qt <= qt_last && fa_classify(rule, qt * kTile, min(qt * kTile + kTile, p.nq) - 1, k0, k_hi) == FA_TILE_SKIP) ++qt;
     return qt;
@@ -606,14 +624,14 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdPa
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int ch = ct * 8 + 2 * t + e;
-          if (ch < p.d) dkg[int64_t(ch) * p.nk + row[mt]] = dk[mt][ct][e] * scale;
+          if (ch < p.d) store_or_add(dkg + int64_t(ch) * p.nk + row[mt], dk[mt][ct][e] * scale);
         }
 #pragma unroll
       for (int ct = 0; ct < VP / 8; ++ct)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int ch = ct * 8 + 2 * t + e;
-          if (ch < p.v_d) dvg[int64_t(ch) * p.nk + row[mt]] = dv[mt][ct][e];
+          if (ch < p.v_d) store_or_add(dvg + int64_t(ch) * p.nk + row[mt], dv[mt][ct][e]);
         }
     }
 }
@@ -639,13 +657,20 @@ static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  auto splits_for = [](int64_t ctas, int64_t streamed_tiles) {   // 1 unless the grid leaves SMs idle
+    int n = 1;
+    while (ctas * n < 148 && n < 4 && streamed_tiles / (2 * n) >= 4) n *= 2;
+    return n;
+  };
   {
     auto kern = bwd_dq_kernel<DP, VP, MT>;
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
     p.n_tiles = (p.nq + kRows - 1) / kRows;
+    const int ns = splits_for(p.batch * p.n_tiles, (p.nk + kTile - 1) / kTile);
+    if (ns > 1 && (e = cudaMemsetAsync(p.d_q, 0, size_t(p.batch) * p.d * p.nq * 8, stream)) != cudaSuccess) return e;
     ScopedKernel timed("bwd_dq_f64_dmma", stream);
-    kern<<<unsigned(p.batch * p.n_tiles), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
@@ -653,8 +678,13 @@ static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
     p.n_tiles = (p.nk + kRows - 1) / kRows;
+    const int ns = splits_for(p.batch * p.n_tiles, (p.nq + kTile - 1) / kTile);
+    if (ns > 1) {
+      if ((e = cudaMemsetAsync(p.d_k, 0, size_t(p.batch) * p.d * p.nk * 8, stream)) != cudaSuccess) return e;
+      if ((e = cudaMemsetAsync(p.d_v, 0, size_t(p.batch) * p.v_d * p.nk * 8, stream)) != cudaSuccess) return e;
+    }
     ScopedKernel timed("bwd_dkdv_f64_dmma", stream);
-    kern<<<unsigned(p.batch * p.n_tiles), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     return cudaGetLastError();
   }
 }
