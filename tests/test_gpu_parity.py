@@ -132,9 +132,10 @@ def test_reference_matrix_random_shapes(dims, attn, sync_mode, dtype):
                 w = int(rng.integers(1, max(2, big // 4)))
                 s = int(rng.integers(1, 4)) if cfg["strided"] else 0
             c = cfg["is_causal"]
-        # fp16: the reference's own shape distribution (channels 8..32, arbitrary even lengths) runs on the tensor cores
+        # the reference's own shape distribution (channels 8..32, arbitrary lengths) runs on the tensor cores in all
+        # three precisions: tcgen05 for fp16 and fp32 (3xTF32 / three bf16 pieces), DMMA for fp64
         _check(dtype, dims, cfg["rule"], sync_mode, w, s, c, batch, d, d, qs, ks, seed + run,
-               expect_path=2 if dtype == np.float16 else None)
+               expect_path={np.float16: 2, np.float32: 3, np.float64: 4}[dtype])
 
 
 @pytest.mark.parametrize("case", [
@@ -155,6 +156,24 @@ def test_fp16_any_channels_any_lengths_on_the_tensor_cores(case):
     dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
     _check(np.float16, dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=zlib.crc32(repr(case).encode()) % 1000,
            expect_path=2)
+
+
+@pytest.mark.parametrize("case", [
+    (1, "causal", "scale_end", 1, 0, False, (2, 1, 2), 24, 9, (77,), (131,)),        # (32, 16) kernel, odd lengths
+    (1, "full", "none_front", 1, 0, False, (3,), 8, 8, (300,), (258,)),
+    (1, "causal", "none_front", 1, 0, False, (2,), 32, 32, (1023,), (1023,)),
+    (1, "local", "scale_front", 16, 0, True, (2,), 48, 40, (130,), (515,)),          # 32 < channels < 64
+    (1, "full", "scale_end", 1, 0, False, (1,), 17, 64, (250,), (1000,)),            # v_d forces the (64, 64) kernel
+    (2, "local", "none_front", 3, 0, True, (2,), 17, 31, (13, 9), (13, 9)),
+    (1, "full", "none_front", 1, 0, False, (1,), 1, 1, (1,), (1,)),
+    (1, "local", "none_front", 2, 0, False, (2,), 16, 16, (200,), (40,)),             # rows with no keys
+], ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-d{c[7]}x{c[8]}-q{'x'.join(map(str, c[9]))}-k{'x'.join(map(str, c[10]))}")
+def test_fp32_any_channels_any_lengths_on_the_tensor_cores(case):
+    """fp32: the split pass writes its pieces in the kernel's shape (zero-padded channels, padded lengths), the kernels
+    store only the tensors' own channels - channel counts up to 64 and any length stay on tcgen05."""
+    dims, rule, mode, w, s, c, batch, d, vd, qs, ks = case
+    _check(np.float32, dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=zlib.crc32(repr(case).encode()) % 1000,
+           expect_path=3)
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
@@ -458,8 +477,8 @@ def test_fp64_tensor_core_kernels_match_oracle(case):
 
 def test_fp32_tensors_that_are_only_4_byte_aligned():
     """A contiguous fp32 tensor whose base is offset by one float (a view into a larger buffer) is only 4-byte aligned:
-    the 3xTF32 forward reads Q, K, V with 16-byte vector loads, so the dispatch must decline it (generic kernels) instead
-    of faulting with a misaligned address, and the result must still match the oracle."""
+    the vector-load split pass and the TMA store of O need 16 bytes, so the launcher takes its scalar split pass and a
+    padded O (copied out afterwards) instead of faulting with a misaligned address; the tensor-core path stays on."""
     rng = np.random.default_rng(8)
     Q, K, V, dO = da.random_inputs(rng, np.float32, (2,), 64, 64, (256,), (320,))
     ref = da.attention(Q, K, V, 1, "full", "none_front", dO=dO)
@@ -473,7 +492,7 @@ def test_fp32_tensors_that_are_only_4_byte_aligned():
     tq, tk, tv = (off_by_one(x).requires_grad_(True) for x in (Q, K, V))
     O = fa.full_1d(tq, tk, tv, "none_front")
     torch.cuda.synchronize()
-    assert _capi.lib.fa_last_path() == 1, "misaligned fp32 inputs must not take the vector-load tensor-core path"
+    assert _capi.lib.fa_last_path() == 3
     assert max_abs_err(O.detach().cpu().numpy(), ref["O"]) <= 1e-5
     dQ, dK, dV = torch.autograd.grad(O, (tq, tk, tv), torch.from_numpy(dO).cuda())
     for name, g in (("dQ", dQ), ("dK", dK), ("dV", dV)):

@@ -152,14 +152,15 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
   if (p->dtype == FA_F16) s = fa::sm100_f16_workspace_bytes(a, is_backward != 0);
   if (p->dtype == FA_F32 && is_backward && fa::g_path_override != 1) {
     fa::LaunchArgs probe = a;
-    probe.workspace = nullptr;
+    probe.workspace = reinterpret_cast<void*>(uintptr_t(256));   // a probe: only shape / size rules are evaluated
     probe.workspace_bytes = ~size_t(0);
     if (fa::sm100_f32_backward_supports(probe)) s = fa::sm100_f32_backward_workspace_bytes(a);
   }
   if (p->dtype == FA_F32 && !is_backward) {
     // hi / lo TF32 copies of Q, K, V for the 3xTF32 forward (only when that kernel can take the shape)
     fa::LaunchArgs probe = a;
-    probe.o = probe.workspace = nullptr;
+    probe.o = nullptr;
+    probe.workspace = reinterpret_cast<void*>(uintptr_t(256));
     probe.workspace_bytes = ~size_t(0);
     if (fa::g_path_override != 1 && fa::sm100_f32_forward_supports(probe)) s = fa::sm100_f32_forward_workspace_bytes(a);
   }

@@ -58,6 +58,8 @@ struct alignas(64) BwdF32Params {
   float* lse2_refined;  // written by the dQ kernel, read by the dK/dV kernel (see bwd_dq_f32_kernel)
   float *d_q, *d_k, *d_v;
   int32_t nq, nk, n_blocks, batch;
+  int32_t d, v_d;        // the tensors' own channel counts (<= the kernel's D, VD; the pieces are zero-padded up to those)
+  int32_t stat_pitch;    // floats per batch element in lse2 / dsum / lse2_refined (nq rounded up to 4: 16-byte rows)
   int32_t renormalise;   // 0 when the call sees only a shard of the keys (ring): sum_k P != 1 by construction there
   float scale, scale_log2;
 };
@@ -67,27 +69,34 @@ struct PrepJob {
   const float *o, *d_o, *l, *m;
   float *lse2, *dsum, *lse2_refined;
   int64_t batch;
-  int32_t v_d, nq;
+  int32_t v_d, nq, sp;
 };
 __device__ __forceinline__ void bwd_prep_f32(const float* __restrict__ o, const float* __restrict__ d_o,
                                              const float* __restrict__ l, const float* __restrict__ m,
                                              float* __restrict__ lse2, float* __restrict__ dsum,
-                                             float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq) {
-  const int64_t total = batch * nq;
-  // the padding behind the arrays is read by the 64-wide bulk copies of the last, ragged query tile: keep it finite
+                                             float* __restrict__ lse2_refined, int64_t batch, int32_t v_d, int32_t nq,
+                                             int32_t sp) {
+  const int64_t total = batch * sp;
+  // the padding behind the arrays (and behind each batch element's row when nq is not a multiple of 4) is read by the
+  // 64-wide bulk copies of the last, ragged query tile: keep it finite
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kXStatPad) {
     lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
     lse2_refined[total + threadIdx.x] = __int_as_float(0x7f800000);
     dsum[total + threadIdx.x] = 0.f;
   }
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t b = i / nq, r = i - b * nq;
+    const int64_t b = i / sp, r = i - b * sp;
+    if (r >= nq) {
+      lse2[i] = lse2_refined[i] = __int_as_float(0x7f800000);
+      dsum[i] = 0.f;
+      continue;
+    }
     const float* op = o + b * v_d * int64_t(nq) + r;
     const float* dp = d_o + b * v_d * int64_t(nq) + r;
     float acc = 0.f;
     for (int c = 0; c < v_d; ++c) acc = fmaf(op[int64_t(c) * nq], dp[int64_t(c) * nq], acc);
     dsum[i] = acc;
-    const float lv = l[i], mv = m[i];
+    const float lv = l[b * nq + r], mv = m[b * nq + r];
     lse2[i] = (lv > 0.f && !is_sentinel<float>(mv)) ? (mv + logf(lv)) * kXLog2e : __int_as_float(0x7f800000);
   }
 }
@@ -298,8 +307,8 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
     const int qi = q0 + r;
     const bool q_valid = qi < p.nq;
     const FaPos qpos = fa_pos(rule, rule.q, min(qi, p.nq - 1));
-    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.nq + qi] : __int_as_float(0x7f800000);
-    const float dsum = q_valid ? p.dsum[int64_t(b) * p.nq + qi] : 0.f;
+    const float lse2 = q_valid ? p.lse2[int64_t(b) * p.stat_pitch + qi] : __int_as_float(0x7f800000);
+    const float dsum = q_valid ? p.dsum[int64_t(b) * p.stat_pitch + qi] : 0.f;
     const float scale_log2 = p.scale_log2;
     // The forward's l, m come from a 3xTF32 S (about 2^-21 relative), this kernel's S from three bf16 pieces (2^-24):
     // P = exp2(S c - LSE2) then misses sum_k P = 1 by a common factor per row of a few 1e-6, which is the whole error
@@ -351,10 +360,10 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       ++j;
     }
     // epilogue: dQ = scale * acc, fp32, straight to global (lanes = consecutive queries -> coalesced per channel)
-    float* out = p.d_q + int64_t(b) * D * p.nq + qi;
+    float* out = p.d_q + int64_t(b) * p.d * p.nq + qi;
     const float out_scale = !p.renormalise ? p.scale : (row_sum > 0.f ? p.scale / row_sum : 0.f);
     if (q_valid)
-      p.lse2_refined[int64_t(b) * p.nq + qi] =
+      p.lse2_refined[int64_t(b) * p.stat_pitch + qi] =
           !p.renormalise ? lse2 : (row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000));
     if (j > 0) {
       mbar_wait(bar_final, 0);
@@ -368,11 +377,11 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
         if (q_valid) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c * 32 + e < D) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
+            if (c * 32 + e < p.d) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
         }
       }
     } else if (q_valid) {
-      for (int c = 0; c < D; ++c) out[int64_t(c) * p.nq] = 0.f;
+      for (int c = 0; c < p.d; ++c) out[int64_t(c) * p.nq] = 0.f;
     }
   }
   tc_fence_before();
@@ -482,7 +491,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
             tma_load_2d(ring + s * Cfg::kStageBytes + 3 * Cfg::kStrD + j * Cfg::kStrV, &p.map_do[j],
                         bar_full + 8 * s, qt * kXN, b * VD);
           }
-          const int64_t off = int64_t(b) * p.nq + qt * kXN;
+          const int64_t off = int64_t(b) * p.stat_pitch + qt * kXN;
           bulk_load_1d_x(stat_smem + s * Cfg::kStatBytes, p.lse2_refined + off, kXN * 4, bar_full + 8 * s);
           bulk_load_1d_x(stat_smem + s * Cfg::kStatBytes + kXN * 4, p.dsum + off, kXN * 4, bar_full + 8 * s);
           ++t;
@@ -590,8 +599,8 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
       ++t;
     }
     // epilogue: dV, dK = scale * acc in fp32, straight to global (lanes = consecutive keys -> coalesced per channel)
-    float* out_v = p.d_v + int64_t(b) * VD * p.nk + ki;
-    float* out_k = p.d_k + int64_t(b) * D * p.nk + ki;
+    float* out_v = p.d_v + int64_t(b) * p.v_d * p.nk + ki;
+    float* out_k = p.d_k + int64_t(b) * p.d * p.nk + ki;
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         if (k_valid) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c * 32 + e < VD) out_v[int64_t(c * 32 + e) * p.nk] = o[e] + oc[e];
+            if (c * 32 + e < p.v_d) out_v[int64_t(c * 32 + e) * p.nk] = o[e] + oc[e];
         }
       }
 #pragma unroll
@@ -616,12 +625,12 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         if (k_valid) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c * 32 + e < D) out_k[int64_t(c * 32 + e) * p.nk] = (o[e] + oc[e]) * p.scale;
+            if (c * 32 + e < p.d) out_k[int64_t(c * 32 + e) * p.nk] = (o[e] + oc[e]) * p.scale;
         }
       }
     } else if (k_valid) {
-      for (int c = 0; c < VD; ++c) out_v[int64_t(c) * p.nk] = 0.f;
-      for (int c = 0; c < D; ++c) out_k[int64_t(c) * p.nk] = 0.f;
+      for (int c = 0; c < p.v_d; ++c) out_v[int64_t(c) * p.nk] = 0.f;
+      for (int c = 0; c < p.d; ++c) out_k[int64_t(c) * p.nk] = 0.f;
     }
   }
   tc_fence_before();
@@ -635,16 +644,23 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
 // ---- host side -------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+static int64_t pad8x(int64_t n) { return (n + 7) & ~int64_t(7); }
+static int64_t pad4x(int64_t n) { return (n + 3) & ~int64_t(3); }
 struct F32BwdWorkspace {
-  size_t stats, q, dout, k, v, total;   // byte sizes: statistics, one bf16 piece of Q, dO, K, V
+  size_t stats, q, dout, k, v, total;   // byte sizes: statistics, one bf16 piece of Q, dO, K, V (kernel shape, padded)
+  int64_t nqp, nkp, sp;
 };
+// d, v_d here are the KERNEL's channel counts
 static F32BwdWorkspace f32_bwd_layout(int64_t batch, int64_t nq, int64_t nk, int d, int v_d) {
   F32BwdWorkspace w;
-  w.stats = align256(size_t(3) * (batch * nq + kXStatPad) * sizeof(float));
-  w.q = align256(size_t(batch) * d * nq * 2);
-  w.dout = align256(size_t(batch) * v_d * nq * 2);
-  w.k = align256(size_t(batch) * d * nk * 2);
-  w.v = align256(size_t(batch) * v_d * nk * 2);
+  w.nqp = pad8x(nq);
+  w.nkp = pad8x(nk);
+  w.sp = pad4x(nq);
+  w.stats = align256(size_t(3) * (batch * w.sp + kXStatPad) * sizeof(float));
+  w.q = align256(size_t(batch) * d * w.nqp * 2);
+  w.dout = align256(size_t(batch) * v_d * w.nqp * 2);
+  w.k = align256(size_t(batch) * d * w.nkp * 2);
+  w.v = align256(size_t(batch) * v_d * w.nkp * 2);
   w.total = w.stats + 3 * (w.q + w.dout + w.k + w.v);
   return w;
 }
@@ -652,20 +668,31 @@ static F32BwdWorkspace f32_bwd_layout(int64_t batch, int64_t nq, int64_t nk, int
 struct SplitJobs {
   const float* src[4];
   __nv_bfloat16* dst[4][3];
-  int64_t n[4];
+  int64_t batch;
+  int32_t c_src[4], c_dst[4], s_src[4], s_dst[4];   // [batch][c_src][s_src] -> [batch][c_dst][s_dst], zero-padded
 };
-// one launch for the four operands and the row statistics: blockIdx.y selects the tensor, y == 4 the statistics pass
+// one launch for the four operands and the row statistics: blockIdx.y selects the tensor, y == 4 the statistics pass.
+// The pieces are written in the KERNEL's shape (channels padded to its D / VD, lengths to a multiple of 8), so any
+// channel count up to 64 and any length run on the tensor cores.
 __global__ void split_bf16x3_all(const SplitJobs jobs, const PrepJob prep) {
   const int t = blockIdx.y;
   if (t == 4) {
     bwd_prep_f32(prep.o, prep.d_o, prep.l, prep.m, prep.lse2, prep.dsum, prep.lse2_refined, prep.batch, prep.v_d,
-                 prep.nq);
+                 prep.nq, prep.sp);
     return;
   }
   const float* __restrict__ x = jobs.src[t];
-  const int64_t n = jobs.n[t];
+  const int64_t cd = jobs.c_dst[t], sd = jobs.s_dst[t], cs = jobs.c_src[t], ss = jobs.s_src[t];
+  const int64_t n = jobs.batch * cd * sd;
+  const bool same = cd == cs && sd == ss;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-    const float v = x[i];
+    float v;
+    if (same) {
+      v = x[i];
+    } else {
+      const int64_t px = i % sd, bc = i / sd, c = bc % cd, b = bc / cd;
+      v = (c < cs && px < ss) ? x[(b * cs + c) * ss + px] : 0.f;
+    }
     const __nv_bfloat16 a = __float2bfloat16_rn(v);
     const float r1 = v - __bfloat162float(a);
     const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
@@ -682,8 +709,8 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   const F32BwdWorkspace w = f32_bwd_layout(a.batch, nq, nk, D, VD);
   char* ws = reinterpret_cast<char*>(a.workspace);
   float* lse2 = reinterpret_cast<float*>(ws);
-  float* dsum = lse2 + (a.batch * int64_t(nq) + kXStatPad);
-  float* lse2_refined = dsum + (a.batch * int64_t(nq) + kXStatPad);
+  float* dsum = lse2 + (a.batch * w.sp + kXStatPad);
+  float* lse2_refined = dsum + (a.batch * w.sp + kXStatPad);
   char* pieces = ws + w.stats;
   __nv_bfloat16 *qp[3], *dop[3], *kp[3], *vp[3];
   for (int j = 0; j < 3; ++j) {
@@ -694,10 +721,10 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   }
   BwdF32Params p;
   for (int j = 0; j < 3; ++j)
-    if (!make_map_2d(&p.map_q[j], qp[j], a.batch * D, nq, 64, D, true) ||
-        !make_map_2d(&p.map_do[j], dop[j], a.batch * VD, nq, 64, VD, true) ||
-        !make_map_2d(&p.map_k[j], kp[j], a.batch * D, nk, 64, D, true) ||
-        !make_map_2d(&p.map_v[j], vp[j], a.batch * VD, nk, 64, VD, true))
+    if (!make_map_2d(&p.map_q[j], qp[j], a.batch * D, w.nqp, 64, D, true) ||
+        !make_map_2d(&p.map_do[j], dop[j], a.batch * VD, w.nqp, 64, VD, true) ||
+        !make_map_2d(&p.map_k[j], kp[j], a.batch * D, w.nkp, 64, D, true) ||
+        !make_map_2d(&p.map_v[j], vp[j], a.batch * VD, w.nkp, 64, VD, true))
       return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.lse2 = lse2;
@@ -709,26 +736,33 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   p.nq = nq;
   p.nk = nk;
   p.batch = int32_t(a.batch);
+  p.d = a.d;
+  p.v_d = a.v_d;
+  p.stat_pitch = int32_t(w.sp);
   p.renormalise = a.partial_keys ? 0 : 1;
-  p.scale = 1.f / sqrtf(float(D));
+  p.scale = 1.f / sqrtf(float(a.d));
   p.scale_log2 = p.scale * kXLog2e;
   cudaError_t e;
   {
     SplitJobs jobs;
     const float* src[4] = {(const float*)a.q, (const float*)a.d_o, (const float*)a.k, (const float*)a.v};
     __nv_bfloat16** dst[4] = {qp, dop, kp, vp};
-    const int64_t n[4] = {a.batch * int64_t(D) * nq, a.batch * int64_t(VD) * nq, a.batch * int64_t(D) * nk,
-                          a.batch * int64_t(VD) * nk};
+    const int cs[4] = {a.d, a.v_d, a.d, a.v_d}, cd[4] = {D, VD, D, VD};
+    const int64_t ss[4] = {nq, nq, nk, nk}, sd[4] = {w.nqp, w.nqp, w.nkp, w.nkp};
+    jobs.batch = a.batch;
     int64_t nmax = 0;
     for (int t = 0; t < 4; ++t) {
       jobs.src[t] = src[t];
-      jobs.n[t] = n[t];
+      jobs.c_src[t] = cs[t];
+      jobs.c_dst[t] = cd[t];
+      jobs.s_src[t] = int32_t(ss[t]);
+      jobs.s_dst[t] = int32_t(sd[t]);
       for (int j = 0; j < 3; ++j) jobs.dst[t][j] = dst[t][j];
-      nmax = std::max(nmax, n[t]);
+      nmax = std::max<int64_t>(nmax, a.batch * cd[t] * sd[t]);
     }
     const int blocks = int(std::min<int64_t>((nmax + 255) / 256, 148 * 8));
     const PrepJob prep{(const float*)a.o, (const float*)a.d_o, (const float*)a.l, (const float*)a.m, lse2, dsum,
-                       lse2_refined, a.batch, VD, nq};
+                       lse2_refined, a.batch, a.v_d, nq, int32_t(w.sp)};
     ScopedKernel timed("split_bf16x3+prep", stream);
     split_bf16x3_all<<<dim3(blocks, 5), 256, 0, stream>>>(jobs, prep);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -757,19 +791,25 @@ cudaError_t launch_bwd_f32(const LaunchArgs& a, cudaStream_t stream) {
 
 static bool aligned16x(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static bool f32_bwd_shape(const LaunchArgs& a) {
-  return (a.d == 64 && a.v_d == 64) || (a.d == 32 && a.v_d == 32) || (a.d == 32 && a.v_d == 16);
+// the instantiation that holds the problem's channel counts with the least padding (same choice as the forward)
+static void f32_bwd_pick(const LaunchArgs& a, int* D, int* VD) {
+  if (a.d <= 32 && a.v_d <= 16) { *D = 32; *VD = 16; }
+  else if (a.d <= 32 && a.v_d <= 32) { *D = 32; *VD = 32; }
+  else { *D = 64; *VD = 64; }
 }
 
 size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a) {
-  return sm100::f32_bwd_layout(a.batch, a.rule.q.total, a.rule.k.total, a.d, a.v_d).total;
+  int D, VD;
+  f32_bwd_pick(a, &D, &VD);
+  return sm100::f32_bwd_layout(a.batch, a.rule.q.total, a.rule.k.total, D, VD).total;
 }
 
+// Any channel counts up to 64 and any lengths: the split pass writes the bf16 pieces in the kernel's shape (zero-padded
+// channels, lengths padded to 8), the kernels store only the tensors' own channels.
 bool sm100_f32_backward_supports(const LaunchArgs& a) {
   if (a.dtype != 1 || a.accumulate) return false;
-  if (!f32_bwd_shape(a)) return false;   // the head dims of BASELINE configs C4 (64/64) and C1 (32/16), and 32/32
+  if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
-  if (nq % 8 || nk % 8) return false;   // TMA row pitch of the bf16 pieces
   if (a.workspace && !aligned16x(a.workspace)) return false;
   if (a.batch * 64 > 0x7fffffffLL) return false;
   if (((nq + 127) / 128) * a.batch > 0x7fffffffLL || ((nk + 127) / 128) * a.batch > 0x7fffffffLL) return false;
@@ -779,8 +819,10 @@ bool sm100_f32_backward_supports(const LaunchArgs& a) {
 }
 
 cudaError_t sm100_f32_backward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 64) return sm100::launch_bwd_f32<64, 64>(a, stream);
-  if (a.v_d == 32) return sm100::launch_bwd_f32<32, 32>(a, stream);
+  int D, VD;
+  f32_bwd_pick(a, &D, &VD);
+  if (D == 64) return sm100::launch_bwd_f32<64, 64>(a, stream);
+  if (VD == 32) return sm100::launch_bwd_f32<32, 32>(a, stream);
   return sm100::launch_bwd_f32<32, 16>(a, stream);
 }
 

@@ -77,6 +77,28 @@ __global__ void split_tf32_kernel(const SplitTf32Jobs jobs) {
   }
 }
 
+// the same split for tensors that do not have the kernel's shape: [batch][c_src][s_src] -> [batch][c_dst][s_dst], channels
+// and positions past the source zero-filled (any channel count up to the kernel's, any length, any alignment)
+struct SplitTf32PadJobs {
+  const float* src[3];
+  float* hi[3];
+  float* lo[3];
+  int64_t batch;
+  int32_t c_src[3], c_dst[3], s_src[3], s_dst[3];
+};
+__global__ void split_tf32_pad_kernel(const SplitTf32PadJobs jobs) {
+  const int t = blockIdx.y;
+  const int64_t cd = jobs.c_dst[t], sd = jobs.s_dst[t], cs = jobs.c_src[t], ss = jobs.s_src[t];
+  const int64_t n = jobs.batch * cd * sd;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t x = i % sd, bc = i / sd, c = bc % cd, b = bc / cd;
+    const float v = (c < cs && x < ss) ? jobs.src[t][(b * cs + c) * ss + x] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    jobs.hi[t][i] = h;
+    jobs.lo[t][i] = v - h;
+  }
+}
+
 template <int D, int VD>
 struct F32Cfg {
   static constexpr int kCh = D > VD ? D : VD;
@@ -420,23 +442,51 @@ static bool make_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+static int64_t pad4(int64_t n) { return (n + 3) & ~int64_t(3); }
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Workspace of the fp32 forward: hi / lo TF32 copies of Q, K, V in the KERNEL's shape [batch][D or VD][length padded to 4]
+// and, unless the tensors already have that shape (and 16-byte alignment), a padded O that is copied out afterwards.
+struct F32FwdLayout {
+  bool exact;
+  int64_t nqp, nkp;
+  size_t q, k, v, o, total;   // byte sizes of one Q / K / V piece and of the padded O
+};
+static F32FwdLayout f32_fwd_layout(const LaunchArgs& a, int D, int VD) {
+  F32FwdLayout w;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  w.nqp = pad4(nq);
+  w.nkp = pad4(nk);
+  w.exact = a.d == D && a.v_d == VD && w.nqp == nq && w.nkp == nk && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.o);
+  w.q = align256(size_t(a.batch) * D * w.nqp * 4);
+  w.k = align256(size_t(a.batch) * D * w.nkp * 4);
+  w.v = align256(size_t(a.batch) * VD * w.nkp * 4);
+  w.o = align256(size_t(a.batch) * VD * w.nqp * 4);
+  // sized without looking at the pointers: the padded O is reserved whenever the shape alone does not rule it out
+  const bool shape_exact = a.d == D && a.v_d == VD && w.nqp == nq && w.nkp == nk;
+  (void)shape_exact;
+  w.total = 2 * (w.q + w.k + w.v) + w.o;
+  return w;
+}
+
 template <int D, int VD>
 cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   using Cfg = F32Cfg<D, VD>;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
-  const size_t nqe = size_t(a.batch) * D * nq, nke = size_t(a.batch) * D * nk, nve = size_t(a.batch) * VD * nk;
+  const F32FwdLayout w = f32_fwd_layout(a, D, VD);
   char* ws = reinterpret_cast<char*>(a.workspace);
   float* qh = reinterpret_cast<float*>(ws);
-  float* ql = reinterpret_cast<float*>(ws + align256(nqe * 4));
-  float* kh = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4));
-  float* kl = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + align256(nke * 4));
-  float* vh = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + 2 * align256(nke * 4));
-  float* vl = reinterpret_cast<float*>(ws + 2 * align256(nqe * 4) + 2 * align256(nke * 4) + align256(nve * 4));
+  float* ql = reinterpret_cast<float*>(ws + w.q);
+  float* kh = reinterpret_cast<float*>(ws + 2 * w.q);
+  float* kl = reinterpret_cast<float*>(ws + 2 * w.q + w.k);
+  float* vh = reinterpret_cast<float*>(ws + 2 * w.q + 2 * w.k);
+  float* vl = reinterpret_cast<float*>(ws + 2 * w.q + 2 * w.k + w.v);
+  float* opad = reinterpret_cast<float*>(ws + 2 * (w.q + w.k + w.v));
   const float* src[3] = {(const float*)a.q, (const float*)a.k, (const float*)a.v};
   float* hi[3] = {qh, kh, vh};
   float* lo[3] = {ql, kl, vl};
-  const size_t cnt[3] = {nqe, nke, nve};
-  {
+  if (w.exact) {
+    const size_t cnt[3] = {size_t(a.batch) * D * nq, size_t(a.batch) * D * nk, size_t(a.batch) * VD * nk};
     SplitTf32Jobs jobs;
     size_t most = 0;
     for (int t = 0; t < 3; ++t) {
@@ -451,12 +501,36 @@ cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
     split_tf32_kernel<<<dim3(blocks, 3), 256, 0, stream>>>(jobs);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+  } else {
+    SplitTf32PadJobs jobs;
+    jobs.batch = a.batch;
+    const int cs[3] = {a.d, a.d, a.v_d}, cd[3] = {D, D, VD};
+    const int64_t ss[3] = {nq, nk, nk}, sd[3] = {w.nqp, w.nkp, w.nkp};
+    int64_t most = 0;
+    for (int t = 0; t < 3; ++t) {
+      jobs.src[t] = src[t];
+      jobs.hi[t] = hi[t];
+      jobs.lo[t] = lo[t];
+      jobs.c_src[t] = cs[t];
+      jobs.c_dst[t] = cd[t];
+      jobs.s_src[t] = int32_t(ss[t]);
+      jobs.s_dst[t] = int32_t(sd[t]);
+      most = std::max<int64_t>(most, a.batch * cd[t] * sd[t]);
+    }
+    const int blocks = int(std::min<int64_t>((most + 255) / 256, 148 * 8));
+    ScopedKernel timed("split_tf32_pad", stream);
+    split_tf32_pad_kernel<<<dim3(blocks, 3), 256, 0, stream>>>(jobs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
   }
   F32FwdParams p;
-  if (!make_map_f32(&p.map_q_hi, qh, a.batch * D, nq, D, 2) || !make_map_f32(&p.map_q_lo, ql, a.batch * D, nq, D, 2) ||
-      !make_map_f32(&p.map_k_hi, kh, a.batch * D, nk, D, 2) || !make_map_f32(&p.map_k_lo, kl, a.batch * D, nk, D, 2) ||
-      !make_map_f32(&p.map_v_hi, vh, a.batch * VD, nk, VD, 1) ||
-      !make_map_f32(&p.map_v_lo, vl, a.batch * VD, nk, VD, 1) || !make_map_f32(&p.map_o, a.o, a.batch * VD, nq, VD, 0))
+  float* o_dst = w.exact ? (float*)a.o : opad;
+  const int64_t o_pitch = w.exact ? nq : w.nqp;
+  if (!make_map_f32(&p.map_q_hi, qh, a.batch * D, w.nqp, D, 2) || !make_map_f32(&p.map_q_lo, ql, a.batch * D, w.nqp, D, 2) ||
+      !make_map_f32(&p.map_k_hi, kh, a.batch * D, w.nkp, D, 2) || !make_map_f32(&p.map_k_lo, kl, a.batch * D, w.nkp, D, 2) ||
+      !make_map_f32(&p.map_v_hi, vh, a.batch * VD, w.nkp, VD, 1) ||
+      !make_map_f32(&p.map_v_lo, vl, a.batch * VD, w.nkp, VD, 1) ||
+      !make_map_f32(&p.map_o, o_dst, a.batch * VD, o_pitch, VD, 0))
     return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.l = (float*)a.l;
@@ -465,42 +539,53 @@ cudaError_t launch_fwd_f32(const LaunchArgs& a, cudaStream_t stream) {
   p.nk = nk;
   p.n_qtiles = (nq + kF32BlockM - 1) / kF32BlockM;
   p.batch = int32_t(a.batch);
-  p.scale_log2 = kF32Log2e / sqrtf(float(D));
+  p.scale_log2 = kF32Log2e / sqrtf(float(a.d));
   auto kern = fwd_f32_kernel<D, VD>;
   cudaError_t e = plan::ensure_smem(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  ScopedKernel timed("fwd_f32_3xtf32_sm100", stream);
-  kern<<<unsigned(int64_t(p.n_qtiles) * p.batch), kF32Threads, Cfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  {
+    ScopedKernel timed("fwd_f32_3xtf32_sm100", stream);
+    kern<<<unsigned(int64_t(p.n_qtiles) * p.batch), kF32Threads, Cfg::kSmemBytes, stream>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (!w.exact) return pack_channels_f32(opad, (float*)a.o, a.batch, a.v_d, nq, VD, w.nqp, a.v_d, nq, stream);
+  return cudaSuccess;
+}
+
+// the instantiation that holds the problem's channel counts with the least padding
+static void f32_pick(const LaunchArgs& a, int* D, int* VD) {
+  if (a.d <= 32 && a.v_d <= 16) { *D = 32; *VD = 16; }
+  else if (a.d <= 32 && a.v_d <= 32) { *D = 32; *VD = 32; }
+  else { *D = 64; *VD = 64; }
 }
 
 }  // namespace sm100
 
 size_t sm100_f32_forward_workspace_bytes(const LaunchArgs& a) {
-  const size_t nq = a.rule.q.total, nk = a.rule.k.total;
-  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
-  return 2 * al(size_t(a.batch) * a.d * nq * 4) + 2 * al(size_t(a.batch) * a.d * nk * 4) +
-         2 * al(size_t(a.batch) * a.v_d * nk * 4);
+  int D, VD;
+  sm100::f32_pick(a, &D, &VD);
+  return sm100::f32_fwd_layout(a, D, VD).total;
 }
 
+// Any channel counts up to 64 and any lengths / alignments: the split pass writes its hi / lo copies in the kernel's
+// shape (zero-padded), so the reference's fp32 test shapes (channels 8..32, arbitrary lengths) run on the tensor cores.
 bool sm100_f32_forward_supports(const LaunchArgs& a) {
   if (a.dtype != 1 || a.accumulate) return false;
-  const bool shape_ok = (a.d == 64 && a.v_d == 64) || (a.d == 32 && a.v_d == 32) || (a.d == 32 && a.v_d == 16);
-  if (!shape_ok) return false;
+  if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
-  if (nq % 4 || nk % 4) return false;  // TMA: row pitch must be a multiple of 16 bytes
   if (nk > int64_t(sm100::kF32BlockN) * 32 * sm100::kMaxTileWords) return false;
-  if ((reinterpret_cast<uintptr_t>(a.o) & 15) || (reinterpret_cast<uintptr_t>(a.workspace) & 255)) return false;
-  // split_tf32_kernel reads the caller's Q, K, V with 16-byte vector loads
-  if ((reinterpret_cast<uintptr_t>(a.q) & 15) || (reinterpret_cast<uintptr_t>(a.k) & 15) || (reinterpret_cast<uintptr_t>(a.v) & 15)) return false;
+  if (!a.workspace || (reinterpret_cast<uintptr_t>(a.workspace) & 255)) return false;
   if (a.workspace_bytes < sm100_f32_forward_workspace_bytes(a)) return false;
-  if (((nq + 127) / 128) * a.batch > 0x7fffffffLL) return false;
+  if (((nq + 127) / 128) * a.batch > 0x7fffffffLL || a.batch * 64 > 0x7fffffffLL) return false;
+  if (sm100::pad4(nq) > 0x7fffffffLL || sm100::pad4(nk) > 0x7fffffffLL) return false;
   return true;
 }
 
 cudaError_t sm100_f32_forward(const LaunchArgs& a, cudaStream_t stream) {
-  if (a.d == 64) return sm100::launch_fwd_f32<64, 64>(a, stream);
-  if (a.v_d == 32) return sm100::launch_fwd_f32<32, 32>(a, stream);
+  int D, VD;
+  sm100::f32_pick(a, &D, &VD);
+  if (D == 64) return sm100::launch_fwd_f32<64, 64>(a, stream);
+  if (VD == 32) return sm100::launch_fwd_f32<32, 32>(a, stream);
   return sm100::launch_fwd_f32<32, 16>(a, stream);
 }
 

@@ -68,6 +68,9 @@ cudaError_t layout_transpose(int dtype, const void* x, void* y, int64_t B, int64
 cudaError_t pack_rows(int elt_bytes, const void* src, void* dst, int64_t rows, int64_t len, int64_t src_pitch,
                       int64_t dst_pitch, cudaStream_t stream);
 
+cudaError_t pack_channels_f32(const float* src, float* dst, int64_t batch, int64_t ch, int64_t len, int64_t src_ch,
+                              int64_t src_pitch, int64_t dst_ch, int64_t dst_pitch, cudaStream_t stream);
+
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);
 bool sm100_f16_backward_supports(const LaunchArgs& a);

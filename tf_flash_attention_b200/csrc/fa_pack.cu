@@ -24,6 +24,20 @@ __global__ void pack_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
   }
 }
 
+// [batch][src_ch][src_pitch] -> [batch][dst_ch][dst_pitch], copying the first `ch` channels and `len` positions of each
+template <typename T>
+__global__ void pack_channels_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t batch, int64_t ch,
+                                     int64_t len, int64_t src_ch, int64_t src_pitch, int64_t dst_ch, int64_t dst_pitch) {
+  const int64_t rows = batch * ch;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    const int64_t b = r / ch, c = r - b * ch;
+    const T* s = src + (b * src_ch + c) * src_pitch;
+    T* d = dst + (b * dst_ch + c) * dst_pitch;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x)
+      d[i] = s[i];
+  }
+}
+
 template <typename T>
 cudaError_t launch_pack(const void* src, void* dst, int64_t rows, int64_t len, int64_t src_pitch, int64_t dst_pitch,
                         cudaStream_t stream) {
@@ -38,6 +52,18 @@ cudaError_t launch_pack(const void* src, void* dst, int64_t rows, int64_t len, i
 }
 
 }  // namespace
+
+cudaError_t pack_channels_f32(const float* src, float* dst, int64_t batch, int64_t ch, int64_t len, int64_t src_ch,
+                              int64_t src_pitch, int64_t dst_ch, int64_t dst_pitch, cudaStream_t stream) {
+  if (batch <= 0 || ch <= 0 || len <= 0) return cudaSuccess;
+  const int threads = 256;
+  const unsigned gx = unsigned(std::min<int64_t>((len + threads - 1) / threads, 64));
+  const unsigned gy = unsigned(std::min<int64_t>(batch * ch, 148 * 32));
+  ScopedKernel timed("pack_channels", stream);
+  pack_channels_kernel<float><<<dim3(gx, gy), threads, 0, stream>>>(src, dst, batch, ch, len, src_ch, src_pitch, dst_ch,
+                                                                     dst_pitch);
+  return cudaGetLastError();
+}
 
 cudaError_t pack_rows(int elt_bytes, const void* src, void* dst, int64_t rows, int64_t len, int64_t src_pitch,
                       int64_t dst_pitch, cudaStream_t stream) {
