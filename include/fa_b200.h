@@ -39,6 +39,14 @@ enum { FA_RULE_FULL = 0, FA_RULE_CAUSAL = 1, FA_RULE_LOCAL = 2 };
 /* sync mode (reference: sync_methods.cc:113-117) */
 enum { FA_SYNC_NONE_FRONT = 0, FA_SYNC_SCALE_FRONT = 1, FA_SYNC_SCALE_END = 2 };
 
+/* tensor layout of q, k, v, o (and d_o, d_q, d_k, d_v). The reference's ops are channel-first only and expect an
+ * einsum either side (README.md:40); channel-last is read and written directly through 4-D TMA descriptors by the
+ * fp16 tensor-core kernels, which removes those transposes. l, m are [batch, q] in both layouts. */
+enum {
+  FA_LAYOUT_CHANNEL_FIRST = 0, /* [batch..., channels, sequence...]                          */
+  FA_LAYOUT_CHANNEL_LAST = 1   /* [outer, sequence..., heads, channels], batch = outer*heads */
+};
+
 /* status codes; 0 = ok. Each FA_EINVAL_* mirrors one reference check. */
 enum {
   FA_OK = 0,
@@ -56,6 +64,7 @@ enum {
   FA_EINVAL_CHANNEL = -11,     /* fa_check_*_shapes: channel mismatch                       */
   FA_EINVAL_BATCH = -12,       /* fa_check_*_shapes: batch shapes differ                    */
   FA_EINVAL_SEQ_SHAPE = -13,   /* fa_check_*_shapes: sequence shapes differ                 */
+  FA_EINVAL_LAYOUT = -14,      /* layout / heads invalid, or channel-last asked of a path that cannot read it */
   FA_ECUDA = -100,             /* a CUDA call failed; fa_last_cuda_error() has the code     */
   FA_ENODEVICE = -101          /* no sm_100 device is current                               */
 };
@@ -70,7 +79,7 @@ typedef struct fa_problem_t {
   int32_t sync_mode;        /* FA_SYNC_*                                                     */
   int32_t d;                /* channels of Q and K                                           */
   int32_t v_d;              /* channels of V and O                                           */
-  int32_t reserved0;
+  int32_t layout;           /* FA_LAYOUT_*; 0 (channel-first) is the reference's layout      */
   int64_t batch;            /* product of all batch axes (heads included)                    */
   int32_t q_shape[2];       /* TF axis order (outer, inner); 1-D uses q_shape[0]             */
   int32_t k_shape[2];
@@ -85,7 +94,7 @@ typedef struct fa_problem_t {
   /* 1 = `o`,`l`,`m` already hold a partial result of the same rows (from earlier
    * K/V shards) and this call merges into them online; 0 = overwrite.              */
   int32_t accumulate;
-  int32_t reserved1;
+  int32_t heads;            /* FA_LAYOUT_CHANNEL_LAST only: innermost batch axis (>= 1)      */
 } fa_problem_t;
 
 /* ---- the hot path ------------------------------------------------------------- */

@@ -176,14 +176,50 @@ def test_backward_shape_validation():
 
 def test_python_api_surface_matches_reference():
     import inspect
-    sig = {n: list(inspect.signature(getattr(fa, n)).parameters) for n in
-           ("full_1d", "causal_1d", "local_1d", "full_2d", "causal_2d", "local_2d")}
+    names = ("full_1d", "causal_1d", "local_1d", "full_2d", "causal_2d", "local_2d")
+    # the reference's positional surface; `layout` is this package's one addition and is keyword-only
+    sig = {n: [k for k, v in inspect.signature(getattr(fa, n)).parameters.items() if v.kind != v.KEYWORD_ONLY]
+           for n in names}
+    for n in names:
+        extra = [k for k, v in inspect.signature(getattr(fa, n)).parameters.items() if v.kind == v.KEYWORD_ONLY]
+        assert extra == ["layout"] and inspect.signature(getattr(fa, n)).parameters["layout"].default == "channel_first"
     assert sig["full_1d"] == sig["full_2d"] == ["Q", "K", "V", "sync_mode", "returning_l_m"]
     assert sig["causal_1d"] == sig["causal_2d"] == ["Q", "K", "V", "sync_mode", "returning_l_m"]
     assert sig["local_1d"] == sig["local_2d"] == ["Q", "K", "V", "window_size", "log2_stride_size", "is_causal",
                                                   "sync_mode", "returning_l_m"]
     assert inspect.signature(fa.full_1d).parameters["sync_mode"].default == "none_front"
     assert inspect.signature(fa.causal_1d).parameters["sync_mode"].default is inspect.Parameter.empty
+
+
+def test_channel_last_problem_validation():
+    """fa_problem_t.layout / heads (include/fa_b200.h): validated on the host before any launch; a dtype no kernel
+    reads channel-last answers FA_EINVAL_LAYOUT so the caller can run the adapter (fa_layout_transpose) instead."""
+    import ctypes as C
+    p = _capi.make_problem(_capi.FA_F16, 1, "causal", "none_front", (2, 3, 64, 128), (2, 3, 64, 128), (2, 3, 64, 128))
+    assert p.layout == _capi.FA_LAYOUT_CHANNEL_FIRST and p.heads == 0
+    one = C.c_void_p(256)
+    call = lambda: _capi.lib.fa_forward(C.byref(p), one, one, one, one, one, one, None, 0, None)  # noqa: E731
+    p.layout = 2
+    assert call() == _capi.FA_EINVAL_LAYOUT
+    p.layout, p.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 0
+    assert call() == _capi.FA_EINVAL_LAYOUT
+    p.heads = 4                                      # 6 batch elements are not a multiple of 4 heads
+    assert call() == _capi.FA_EINVAL_LAYOUT
+    assert "channel-last" in _capi.lib.fa_strerror(_capi.FA_EINVAL_LAYOUT).decode()
+    p32 = _capi.make_problem(_capi.FA_F32, 1, "causal", "none_front", (2, 3, 64, 128), (2, 3, 64, 128), (2, 3, 64, 128))
+    p32.layout, p32.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 3
+    ws = _capi.lib.fa_workspace_bytes(C.byref(p32), 0)
+    assert _capi.lib.fa_forward(C.byref(p32), one, one, one, one, one, one, one, ws, None) == _capi.FA_EINVAL_LAYOUT
+    # python side: shapes are outer + sequence + (heads, channels)
+    from tf_flash_attention_b200.flash_attention import _cf_shape
+    assert _cf_shape((2, 100, 3, 64), 1) == (2, 3, 64, 100)
+    assert _cf_shape((5, 2, 10, 12, 3, 64), 2) == (5, 2, 3, 64, 10, 12)
+    with pytest.raises(_capi.InvalidArgumentError):
+        fa.full_1d(np.zeros((1, 8, 2, 8), np.float16), np.zeros((1, 8, 2, 8), np.float16),
+                   np.zeros((1, 8, 2, 8), np.float16), layout="channel_last")     # host arrays: channel-first only
+    with pytest.raises(_capi.InvalidArgumentError):
+        fa.full_1d(np.zeros((1, 8, 8), np.float16), np.zeros((1, 8, 8), np.float16), np.zeros((1, 8, 8), np.float16),
+                   layout="rows")
 
 
 def test_layout_adapter_argument_checks():

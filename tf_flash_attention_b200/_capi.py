@@ -29,7 +29,9 @@ FA_EINVAL_RANK = -10
 FA_EINVAL_CHANNEL = -11
 FA_EINVAL_BATCH = -12
 FA_EINVAL_SEQ_SHAPE = -13
+FA_EINVAL_LAYOUT = -14
 FA_ECUDA = -100
+FA_LAYOUT_CHANNEL_FIRST, FA_LAYOUT_CHANNEL_LAST = 0, 1
 FA_ENODEVICE = -101
 
 PATH_NAMES = {0: "none", 1: "generic_simt", 2: "tcgen05_f16", 3: "tcgen05_f32_split", 4: "dmma_f64"}
@@ -40,12 +42,12 @@ class Problem(C.Structure):
     _fields_ = [
         ("dtype", C.c_int32), ("seq_dims", C.c_int32), ("rule", C.c_int32),
         ("window_size", C.c_int32), ("log2_stride_size", C.c_int32), ("is_causal", C.c_int32),
-        ("sync_mode", C.c_int32), ("d", C.c_int32), ("v_d", C.c_int32), ("reserved0", C.c_int32),
+        ("sync_mode", C.c_int32), ("d", C.c_int32), ("v_d", C.c_int32), ("layout", C.c_int32),
         ("batch", C.c_int64),
         ("q_shape", C.c_int32 * 2), ("k_shape", C.c_int32 * 2),
         ("q_index_base", C.c_int32), ("k_index_base", C.c_int32),
         ("q_full_len", C.c_int32), ("k_full_len", C.c_int32),
-        ("accumulate", C.c_int32), ("reserved1", C.c_int32),
+        ("accumulate", C.c_int32), ("heads", C.c_int32),
     ]
 
 

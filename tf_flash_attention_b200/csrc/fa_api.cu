@@ -75,6 +75,10 @@ int fill_args(const fa_problem_t* p, fa::LaunchArgs* a) {
   a->v_d = p->v_d;
   a->batch = p->batch;
   a->accumulate = p->accumulate;
+  if (p->layout != FA_LAYOUT_CHANNEL_FIRST && p->layout != FA_LAYOUT_CHANNEL_LAST) return FA_EINVAL_LAYOUT;
+  if (p->layout == FA_LAYOUT_CHANNEL_LAST && (p->heads < 1 || p->batch % p->heads)) return FA_EINVAL_LAYOUT;
+  a->layout = p->layout;
+  a->heads = p->layout == FA_LAYOUT_CHANNEL_LAST ? p->heads : 0;
   a->grad_split = fa::g_grad_precision;
   // a key shard of a longer sequence (K/V ring): rows do not see all of their keys in this call
   a->partial_keys = (p->k_index_base != 0 || (p->k_full_len != 0 && p->k_full_len != a->rule.k.total)) ? 1 : 0;
@@ -105,6 +109,9 @@ const char* fa_strerror(int s) {
     case FA_EINVAL_CHANNEL: return "The channel dimensions should be equal";
     case FA_EINVAL_BATCH: return "The batch shape of all inputs should be equal";
     case FA_EINVAL_SEQ_SHAPE: return "The sequence shapes are inconsistent";
+    case FA_EINVAL_LAYOUT:
+      return "channel-last operands are read directly only by the fp16 tensor-core kernels (channels multiples of 8 up "
+             "to 128, 16-byte-aligned tensors, heads >= 1 dividing batch); use fa_layout_transpose otherwise";
     case FA_ECUDA: return "CUDA error (see fa_last_cuda_error)";
     case FA_ENODEVICE: return "no sm_100 CUDA device is current";
     default: return "unknown status";
@@ -191,6 +198,7 @@ int fa_forward(const fa_problem_t* p, const void* q, const void* k, const void* 
     fa::g_last_path = 4;
     e = fa::f64_dmma_forward(a, st);
   } else {
+    if (a.layout != 0) return FA_EINVAL_LAYOUT;
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;
     e = fa::generic_forward(a, st);
@@ -224,6 +232,7 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
     fa::g_last_path = 4;
     e = fa::f64_dmma_backward(a, st);
   } else {
+    if (a.layout != 0) return FA_EINVAL_LAYOUT;
     if (!fa::generic_supports(a)) return FA_EINVAL_SHAPE;
     fa::g_last_path = 1;
     e = fa::generic_backward(a, st);
@@ -267,6 +276,7 @@ int fa_partial_merge(const fa_problem_t* p, const void* o_part, const void* l_pa
   fa::LaunchArgs a{};
   int rc = fill_args(p, &a);
   if (rc) return rc;
+  if (a.layout != 0) return FA_EINVAL_LAYOUT;
   if (p->batch == 0) return FA_OK;
   if (!o_part || !l_part || !m_part || !o_acc || !l_acc || !m_acc) return FA_EINVAL_NULL;
   cudaError_t e = fa::partial_merge(a, o_part, l_part, m_part, o_acc, l_acc, m_acc, first, (cudaStream_t)stream);
@@ -278,6 +288,7 @@ int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_
   fa::LaunchArgs a{};
   int rc = fill_args(p, &a);
   if (rc) return rc;
+  if (a.layout != 0) return FA_EINVAL_LAYOUT;
   if (p->batch == 0) return FA_OK;
   if (!o_acc || !l_acc || !m_acc || !o || !l || !m) return FA_EINVAL_NULL;
   cudaError_t e = fa::partial_finalize(a, o_acc, l_acc, m_acc, o, l, m, (cudaStream_t)stream);

@@ -2061,6 +2061,7 @@ static bool aligned16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) &
 
 bool sm100_f16_backward_supports(const LaunchArgs& a) {
   if (a.dtype != 0) return false;
+  if (a.layout != 0) return false;
   if (a.d < 1 || a.v_d < 1 || a.d > 128 || a.v_d > 128) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   const sm100::BwdLayout w = sm100::bwd_layout(a);

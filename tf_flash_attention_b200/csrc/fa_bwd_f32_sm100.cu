@@ -807,7 +807,7 @@ size_t sm100_f32_backward_workspace_bytes(const LaunchArgs& a) {
 // Any channel counts up to 64 and any lengths: the split pass writes the bf16 pieces in the kernel's shape (zero-padded
 // channels, lengths padded to 8), the kernels store only the tensors' own channels.
 bool sm100_f32_backward_supports(const LaunchArgs& a) {
-  if (a.dtype != 1 || a.accumulate) return false;
+  if (a.dtype != 1 || a.accumulate || a.layout != 0) return false;
   if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   if (a.workspace && !aligned16x(a.workspace)) return false;

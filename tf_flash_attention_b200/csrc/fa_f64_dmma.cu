@@ -692,14 +692,14 @@ static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
 }  // namespace f64
 
 bool f64_dmma_forward_supports(const LaunchArgs& a) {
-  if (a.dtype != 2 || a.accumulate) return false;
+  if (a.dtype != 2 || a.accumulate || a.layout != 0) return false;
   if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   const int64_t tiles = (int64_t(a.rule.q.total) + f64::kRows - 1) / f64::kRows;
   return tiles * a.batch <= 0x7fffffffLL;
 }
 
 bool f64_dmma_backward_supports(const LaunchArgs& a) {
-  if (a.dtype != 2) return false;
+  if (a.dtype != 2 || a.layout != 0) return false;
   if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   if (!a.workspace || a.workspace_bytes < size_t(2) * size_t(a.batch) * size_t(a.rule.q.total) * 8) return false;
   const int64_t tq = (int64_t(a.rule.q.total) + f64::kRows - 1) / f64::kRows;

@@ -40,6 +40,7 @@ struct alignas(64) FwdParams {
   __half* m;
   int32_t nq, nk, n_qpairs;
   int32_t batch;
+  int32_t heads;   // channel-last tensors: batch element = outer * heads + head
   float scale_log2;
 };
 
@@ -84,7 +85,11 @@ struct FwdCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;  // + alignment slack
 };
 
-template <int D, int VD, int BN, int MINB>
+// CL = the tensors are channel-last, [outer][sequence][heads][channels] (4-D tensor maps, one box = 64 channels of R
+// positions of one head): the same tiles with positions and channels swapped, so every shared-memory operand flips
+// between MN-major and K-major (sm100_ptx.cuh tile_desc) and O is staged row-major. Products, accumulation order and
+// results are identical to the channel-first kernel's.
+template <int D, int VD, int BN, int MINB, bool CL>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_constant__ FwdParams p) {
   using Cfg = FwdCfg<D, VD, BN>;
   constexpr int kBlockN = BN;
@@ -110,6 +115,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
   // CTAs of one batch element are adjacent (its K/V stay L2-resident while ~5 heads are in
   // flight); inside a head the heavy (late) query rows go first
   const int b = int(blockIdx.x / p.n_qpairs);
+  const int head = CL ? b % p.heads : 0, outer = CL ? b / p.heads : b;
+  (void)head; (void)outer;
   const int pair = p.n_qpairs - 1 - int(blockIdx.x % p.n_qpairs);
   const int q0 = pair * (kQTiles * kBlockM);
   const int q_hi = min(q0 + kQTiles * kBlockM, p.nq) - 1;
@@ -164,9 +171,15 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
       if (elect_one()) {
         for (int i = 0; i < kQTiles; ++i) {
           mbar_arrive_expect_tx(bar_q_full + 8 * i, kBlockM * D * 2);
-          for (int h = 0; h < 2; ++h)
-            tma_load_bc(q_smem + i * Cfg::kQTileBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
-                        q0 + i * kBlockM + h * 64, b);
+          if constexpr (CL) {
+            for (int c = 0; c < D / 64; ++c)
+              tma_load_cl(q_smem + i * Cfg::kQTileBytes + c * (kBlockM * 128), &p.map_q, bar_q_full + 8 * i, c * 64,
+                          head, q0 + i * kBlockM, outer);
+          } else {
+            for (int h = 0; h < 2; ++h)
+              tma_load_bc(q_smem + i * Cfg::kQTileBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
+                          q0 + i * kBlockM + h * 64, b);
+          }
         }
         int t = 0;
         TileIter it;
@@ -177,18 +190,30 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
             const int s = t % kStages, u = t / kStages;
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * D * 2);
-            for (int h = 0; h < kBlockN / 64; ++h)
-              tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
-                          kt * kBlockN + h * 64, b);
+            if constexpr (CL) {
+              for (int c = 0; c < D / 64; ++c)
+                tma_load_cl(kv_smem + s * Cfg::kStageBytes + c * (kBlockN * 128), &p.map_k, bar_kv_full + 8 * s, c * 64,
+                            head, kt * kBlockN, outer);
+            } else {
+              for (int h = 0; h < kBlockN / 64; ++h)
+                tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (D * 128), &p.map_k, bar_kv_full + 8 * s,
+                            kt * kBlockN + h * 64, b);
+            }
             ++t;
           }
           {
             const int s = t % kStages, u = t / kStages;
             mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
             mbar_arrive_expect_tx(bar_kv_full + 8 * s, kBlockN * VD * 2);
-            for (int h = 0; h < kBlockN / 64; ++h)
-              tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
-                          kt * kBlockN + h * 64, b);
+            if constexpr (CL) {
+              for (int c = 0; c < VD / 64; ++c)
+                tma_load_cl(kv_smem + s * Cfg::kStageBytes + c * (kBlockN * 128), &p.map_v, bar_kv_full + 8 * s, c * 64,
+                            head, kt * kBlockN, outer);
+            } else {
+              for (int h = 0; h < kBlockN / 64; ++h)
+                tma_load_bc(kv_smem + s * Cfg::kStageBytes + h * (VD * 128), &p.map_v, bar_kv_full + 8 * s,
+                            kt * kBlockN + h * 64, b);
+            }
             ++t;
           }
         }
@@ -199,16 +224,16 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         TileIter it;
         it.init(sched, 2, kt_first, kt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_qk = idesc_f16(kBlockM, kBlockN, true, true);
-        constexpr uint32_t idesc_pv = idesc_f16(kBlockM, VD, false, false);
+        constexpr uint32_t idesc_qk = idesc_f16(kBlockM, kBlockN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_pv = idesc_f16(kBlockM, VD, false, tile_mn_major<CL>(false));
         auto issue_qk = [&](int i, int stage) {
           const uint32_t a0 = q_smem + i * Cfg::kQTileBytes;
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
-            // MN-major SW128: 16 channels = two 1024-byte atoms; LBO = next 64 rows (next TMA box)
-            const uint64_t da = smem_desc_sw128(a0 + ks * 2048, D * 128, 1024);
-            const uint64_t db = smem_desc_sw128(b0 + ks * 2048, D * 128, 1024);
+            // channel-first: MN-major SW128, 16 channels = two 1024-byte atoms, LBO = next 64 rows (next TMA box)
+            const uint64_t da = tile_desc<CL>(a0, ks, kBlockM, D, true);
+            const uint64_t db = tile_desc<CL>(b0, ks, kBlockN, D, true);
             mma_ss(tmem_base + i * kBlockN, da, db, idesc_qk, ks > 0);
           }
         };
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = half * Cfg::kSplitKs; ks < (half ? kBlockN / 16 : Cfg::kSplitKs); ++ks) {
-            const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
+            const uint64_t db = tile_desc<CL>(b0, ks, kBlockN, VD, false);
             mma_ts(tmem_base + Cfg::kColO + i * VD, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
                    (accumulate || ks > 0) ? 1u : 0u);
           }
@@ -226,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
           const uint32_t b0 = kv_smem + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < kBlockN / 16; ++ks) {
-            // K-major SW128: 16 keys = 32 bytes inside the 128-byte row; second box after 64 keys
-            const uint64_t db = smem_desc_sw128(b0 + (ks / 4) * (VD * 128) + (ks % 4) * 32, 16, 1024);
+            // channel-first: K-major SW128, 16 keys = 32 bytes inside the 128-byte row; second box after 64 keys
+            const uint64_t db = tile_desc<CL>(b0, ks, kBlockN, VD, false);
             mma_ts(tmem_base + Cfg::kColO + i * VD, tmem_base + i * kBlockN + ks * 8, db, idesc_pv,
                    (accumulate || ks > 0) ? 1u : 0u);
           }
@@ -428,14 +453,32 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
         float o[32];
         tmem_ld32f(t_o + c * 32, o);
         tmem_wait_ld();
+        if constexpr (CL) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(l_sum > 0.f ? o[e] * inv : 0.f);
+          for (int e = 0; e < 32; e += 8) {
+            uint4 w;
+            w.x = pack_half2(o[e] * inv, o[e + 1] * inv);       // inv = 0 for rows without keys
+            w.y = pack_half2(o[e + 2] * inv, o[e + 3] * inv);
+            w.z = pack_half2(o[e + 4] * inv, o[e + 5] * inv);
+            w.w = pack_half2(o[e + 6] * inv, o[e + 7] * inv);
+            *reinterpret_cast<uint4*>(stage_gen + cl_chunk_offset(r, c * 32 + e, kBlockM)) = w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(l_sum > 0.f ? o[e] * inv : 0.f);
+        }
       }
     } else {
       // no key tile survives for this CTA: wait for Q to land before reusing its buffer
       mbar_wait(bar_q_full + 8 * i, 0);
+      if constexpr (CL) {
+#pragma unroll 4
+        for (int c = 0; c < VD; c += 8)
+          *reinterpret_cast<uint4*>(stage_gen + cl_chunk_offset(r, c, kBlockM)) = make_uint4(0, 0, 0, 0);
+      } else {
 #pragma unroll 8
-      for (int c = 0; c < VD; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+        for (int c = 0; c < VD; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+      }
     }
     if (q_valid) {
       const int64_t idx = int64_t(b) * p.nq + qi;
@@ -451,9 +494,14 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_kernel(const __grid_consta
     fence_proxy_async_smem();
     named_bar_sync(1 + i, kBlockM);
     if (r == 0 && tile_valid) {
-      for (int h = 0; h < 2; ++h)
-        if (tq0 + h * 64 < p.nq)
-          tma_store_bc(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b);
+      if constexpr (CL) {
+        for (int c = 0; c < VD / 64; ++c)
+          tma_store_cl(&p.map_o, q_smem + i * Cfg::kQTileBytes + c * (kBlockM * 128), c * 64, head, tq0, outer);
+      } else {
+        for (int h = 0; h < 2; ++h)
+          if (tq0 + h * 64 < p.nq)
+            tma_store_bc(&p.map_o, q_smem + i * Cfg::kQTileBytes + h * (VD * 128), tq0 + h * 64, b);
+      }
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -490,18 +538,41 @@ bool make_map_3d(CUtensorMap* map, const void* base, int64_t batch, int64_t chan
                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-template <int D, int VD, int BN, int MINB>
+// 4-D view [outer][sequence][heads][channels] of a channel-last fp16 tensor: the box is 64 channels x box_rows positions
+// of one head (one 128-byte-row slab of a tile); channels past `channels` and positions past `seq` are zero-filled on
+// loads and clipped on stores.
+bool make_map_cl(CUtensorMap* map, const void* base, int64_t outer, int64_t heads, int64_t channels, int64_t seq,
+                 int box_rows) {
+  const uint64_t gdim[4] = {uint64_t(channels), uint64_t(heads), uint64_t(seq), uint64_t(outer)};
+  const uint64_t gstride[3] = {uint64_t(channels) * 2, uint64_t(channels) * 2 * uint64_t(heads),
+                               uint64_t(channels) * 2 * uint64_t(heads) * uint64_t(seq)};
+  const uint32_t box[4] = {64u, 1u, uint32_t(box_rows), 1u};
+  return plan::tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D, int VD, int BN, int MINB, bool CL>
 cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   using Cfg = FwdCfg<D, VD, BN>;
   FwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
   // D, VD are the kernel's padded channel counts (a.d <= D, a.v_d <= VD)
-  const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
-  if (!make_map_3d(&p.map_q, a.q, a.batch, a.d, nq, qp, D, true) ||
-      !make_map_3d(&p.map_k, a.k, a.batch, a.d, nk, kp, D, true) ||
-      !make_map_3d(&p.map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) ||
-      !make_map_3d(&p.map_o, a.o, a.batch, a.v_d, nq, qp, VD, false))
-    return cudaErrorInvalidValue;
+  if constexpr (CL) {
+    const int64_t heads = a.heads > 0 ? a.heads : 1, outer = a.batch / heads;
+    if (!make_map_cl(&p.map_q, a.q, outer, heads, a.d, nq, kBlockM) ||
+        !make_map_cl(&p.map_k, a.k, outer, heads, a.d, nk, BN) ||
+        !make_map_cl(&p.map_v, a.v, outer, heads, a.v_d, nk, BN) ||
+        !make_map_cl(&p.map_o, a.o, outer, heads, a.v_d, nq, kBlockM))
+      return cudaErrorInvalidValue;
+    p.heads = int32_t(heads);
+  } else {
+    const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
+    if (!make_map_3d(&p.map_q, a.q, a.batch, a.d, nq, qp, D, true) ||
+        !make_map_3d(&p.map_k, a.k, a.batch, a.d, nk, kp, D, true) ||
+        !make_map_3d(&p.map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) ||
+        !make_map_3d(&p.map_o, a.o, a.batch, a.v_d, nq, qp, VD, false))
+      return cudaErrorInvalidValue;
+    p.heads = 1;
+  }
   p.rule = a.rule;
   p.l = (float*)a.l;
   p.m = (__half*)a.m;
@@ -510,10 +581,11 @@ cudaError_t launch_fwd(const LaunchArgs& a, cudaStream_t stream) {
   p.n_qpairs = (nq + kQTiles * kBlockM - 1) / (kQTiles * kBlockM);
   p.batch = int32_t(a.batch);
   p.scale_log2 = kLog2e / sqrtf(float(a.d));
-  auto kern = fwd_kernel<D, VD, BN, MINB>;
+  auto kern = fwd_kernel<D, VD, BN, MINB, CL>;
   cudaError_t e = plan::ensure_smem(kern, Cfg::kSmemBytes);
   if (e != cudaSuccess) return e;
-  ScopedKernel timed(BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64", stream);
+  ScopedKernel timed(CL ? (BN == 128 ? "fwd_f16_sm100_cl" : "fwd_f16_sm100_n64_cl")
+                        : (BN == 128 ? "fwd_f16_sm100" : "fwd_f16_sm100_n64"), stream);
   kern<<<unsigned(int64_t(p.n_qpairs) * p.batch), kThreads, Cfg::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
@@ -535,6 +607,7 @@ struct FwdPack {
 static FwdPack fwd_pack_layout(const LaunchArgs& a) {
   FwdPack w{};
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (a.layout == 1) return w;   // channel-last: the sequence is an outer dimension of the tensor maps, any length
   w.q = (nq % 8) != 0;
   w.k = (nk % 8) != 0;
   size_t off = 0;
@@ -559,6 +632,13 @@ bool sm100_f16_forward_supports(const LaunchArgs& a) {
   if (a.d < 1 || a.v_d < 1 || a.d > 128 || a.v_d > 128) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   const FwdPack w = fwd_pack_layout(a);
+  if (a.layout == 1) {
+    // channel-last: the strides between heads / positions are channels * 2 and heads * channels * 2 bytes
+    if (a.heads < 1 || a.batch % a.heads) return false;
+    if (a.d % 8 || a.v_d % 8) return false;
+  } else if (a.layout != 0) {
+    return false;
+  }
   // TMA: base addresses and row pitches must be multiples of 16 bytes; a side whose length is not a multiple of 8 is
   // copied into the workspace, a misaligned base with an aligned length is left to the generic kernels
   if (!w.q && (!aligned16(a.q) || !aligned16(a.o))) return false;
@@ -583,15 +663,19 @@ size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward) {
 // head_dim <= 64: the 64-key / two-CTAs-per-SM configuration is faster on every workload measured (S1 1.01 -> 0.67 ms,
 // S2 3.95 -> 2.01 ms, C3 0.84 -> 0.51 ms, C4 0.86 -> 0.73 ms; profiles/r1_short_sequences.md); override 5 keeps the
 // 128-key / one-CTA configuration reachable for A/B runs.
-static cudaError_t forward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+template <bool CL>
+static cudaError_t forward_dispatch_layout(const LaunchArgs& a, cudaStream_t stream) {
   const bool d_small = a.d <= 64, v_small = a.v_d <= 64;
-  if (!d_small && !v_small) return sm100::launch_fwd<128, 128, 128, 1>(a, stream);
+  if (!d_small && !v_small) return sm100::launch_fwd<128, 128, 128, 1, CL>(a, stream);
   if (d_small && v_small) {
-    if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2>(a, stream);
-    return sm100::launch_fwd<64, 64, 128, 1>(a, stream);
+    if (a.variant != 5) return sm100::launch_fwd<64, 64, 64, 2, CL>(a, stream);
+    return sm100::launch_fwd<64, 64, 128, 1, CL>(a, stream);
   }
-  if (!d_small) return sm100::launch_fwd<128, 64, 128, 1>(a, stream);
-  return sm100::launch_fwd<64, 128, 128, 1>(a, stream);
+  if (!d_small) return sm100::launch_fwd<128, 64, 128, 1, CL>(a, stream);
+  return sm100::launch_fwd<64, 128, 128, 1, CL>(a, stream);
+}
+static cudaError_t forward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+  return a.layout == 1 ? forward_dispatch_layout<true>(a, stream) : forward_dispatch_layout<false>(a, stream);
 }
 
 cudaError_t sm100_f16_forward(const LaunchArgs& a0, cudaStream_t stream) {

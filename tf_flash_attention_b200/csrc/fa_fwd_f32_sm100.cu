@@ -570,7 +570,7 @@ size_t sm100_f32_forward_workspace_bytes(const LaunchArgs& a) {
 // Any channel counts up to 64 and any lengths / alignments: the split pass writes its hi / lo copies in the kernel's
 // shape (zero-padded), so the reference's fp32 test shapes (channels 8..32, arbitrary lengths) run on the tensor cores.
 bool sm100_f32_forward_supports(const LaunchArgs& a) {
-  if (a.dtype != 1 || a.accumulate) return false;
+  if (a.dtype != 1 || a.accumulate || a.layout != 0) return false;
   if (a.d < 1 || a.v_d < 1 || a.d > 64 || a.v_d > 64) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   if (nk > int64_t(sm100::kF32BlockN) * 32 * sm100::kMaxTileWords) return false;

@@ -578,7 +578,7 @@ cudaError_t backward_t(const LaunchArgs& a, cudaStream_t stream) {
 
 }  // namespace generic
 
-bool generic_supports(const LaunchArgs& a) { return a.d <= 256 && a.v_d <= 256; }
+bool generic_supports(const LaunchArgs& a) { return a.layout == 0 && a.d <= 256 && a.v_d <= 256; }
 
 size_t generic_workspace_bytes(int dtype, int64_t batch, int64_t nq, bool backward) {
   if (!backward) return 0;

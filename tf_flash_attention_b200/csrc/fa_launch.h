@@ -29,6 +29,9 @@ struct LaunchArgs {
   // dV); 0 = dense (the sequence length). Set by the pitch-padding pack pass (fa_pack.cu) for lengths that are not
   // multiples of 8 halves, which TMA cannot address directly (row pitch must be a multiple of 16 bytes).
   int64_t q_pitch, k_pitch;
+  // 0 = channel-first [batch][channels][sequence] (the reference's layout); 1 = channel-last
+  // [outer][sequence][heads][channels] with batch = outer * heads (fp16 tcgen05 kernels only; l, m stay [batch][q])
+  int32_t layout, heads;
   int32_t grad_split;  // fp16 backward: dS handed to the tensor cores as hi + lo fp16 pairs (fa_set_grad_precision)
   int32_t variant;  // fa_set_path_override value (0 auto; 4 = fp16 backward as two kernels; 5 / 6 = forward tile configuration)
 };

@@ -15,8 +15,8 @@ namespace plan {
 namespace {
 
 struct MapKey {
-  uint64_t base, gdim[3], gstride[2];
-  uint32_t box[3], dtype, rank, swizzle;
+  uint64_t base, gdim[4], gstride[3];
+  uint32_t box[4], dtype, rank, swizzle, pad;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -56,7 +56,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encoder() {
 
 bool tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* gdim,
                 const uint64_t* gstride_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
-  if (rank < 1 || rank > 3) return false;
+  if (rank < 1 || rank > 4) return false;
   MapKey k;
   memset(&k, 0, sizeof(k));
   k.base = reinterpret_cast<uint64_t>(base);
@@ -79,8 +79,8 @@ bool tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const voi
   }
   auto enc = encoder();
   if (!enc) return false;
-  cuuint64_t gd[3], gs[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     gd[i] = gdim[i];
     bx[i] = box[i];

@@ -13,7 +13,7 @@
 namespace fa {
 namespace plan {
 
-// rank <= 3; gstride_bytes has rank - 1 entries (strides of dims 1..rank-1)
+// rank <= 4; gstride_bytes has rank - 1 entries (strides of dims 1..rank-1)
 bool tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* gdim,
                 const uint64_t* gstride_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 

@@ -96,6 +96,22 @@ __device__ __forceinline__ void tma_store_bc(const void* map, uint32_t smem_src,
                "r"(smem_src), "r"(x), "r"(0), "r"(b)
                : "memory");
 }
+// 4-D tile copies of channel-last tensors [outer][sequence][heads][channels]: coordinates (channel, head, position,
+// outer); the box is 64 channels x R positions of one head, i.e. one 128-byte-row slab of a tile in shared memory.
+__device__ __forceinline__ void tma_load_cl(uint32_t smem_dst, const void* map, uint32_t bar, int32_t c, int32_t h,
+                                            int32_t s, int32_t b) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(h), "r"(s), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_cl(const void* map, uint32_t smem_src, int32_t c, int32_t h, int32_t s,
+                                             int32_t b) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c), "r"(h), "r"(s), "r"(b)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // shared-memory source of every committed bulk store has been read (enough before the CTA reuses the tile or exits;
 // the global writes complete on their own before the grid does)
@@ -240,6 +256,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= uint64_t(1) << 46;
   d |= uint64_t(2) << 61;
   return d;
+}
+// Operand descriptor of one K = 16 step over a 2-byte tile of R sequence positions x C channels (128-byte swizzle).
+// Channel-first tensors land as boxes of 64 positions ([C rows][128 B], the next 64 positions C * 128 bytes further);
+// channel-last tensors as slabs of 64 channels ([R rows][128 B], the next 64 channels R * 128 bytes further) - the
+// same picture with positions and channels swapped. `over_channels`: the contraction runs over the channels (Q K^T,
+// dO V^T), else over the positions (P V, dS K, ...). The operand is K-major exactly when the contraction runs along
+// the 128-byte rows; tile_mn_major() is the matching instruction-descriptor bit.
+template <bool CL>
+__host__ __device__ constexpr bool tile_mn_major(bool over_channels) {
+  return CL ? !over_channels : over_channels;
+}
+template <bool CL>
+__device__ __forceinline__ uint64_t tile_desc(uint32_t base, int ks, int R, int C, bool over_channels) {
+  const uint32_t block = uint32_t(CL ? R : C) * 128u;   // bytes of one 64-wide box / slab
+  if (tile_mn_major<CL>(over_channels)) return smem_desc_sw128(base + ks * 2048, block, 1024);
+  return smem_desc_sw128(base + (ks >> 2) * block + (ks & 3) * 32, 16, 1024);
+}
+// byte offset of 8 consecutive channels [c, c + 8) of position r inside a channel-last staging tile (slabs of
+// 64 channels, R rows of 128 bytes, 16-byte chunks XOR-swizzled with the row as TMA's 128-byte swizzle expects)
+__device__ __forceinline__ uint32_t cl_chunk_offset(int r, int c, int R) {
+  return uint32_t(c >> 6) * uint32_t(R) * 128u + uint32_t(r) * 128u + uint32_t((((c & 63) >> 3) ^ (r & 7)) << 4);
 }
 // MN-major 32-bit (TF32) operands must use the "128-byte swizzle with 32-byte atoms" layout (descriptor
 // layout type 1; TMA swizzle CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the swizzle atom is 4 rows of 128 bytes.

@@ -58,19 +58,67 @@ def _dtype_code(x):
     return _NP_DTYPES[dt]
 
 
-def _problem(seq_dims, rule, Q, K, V, sync_mode, window_size=1, log2_stride_size=0, is_causal=False):
+LAYOUTS = ('channel_first', 'channel_last')
+
+
+def _cf_shape(shape, seq_dims):
+    """channel-last outer + seq + (heads, channels) -> the channel-first shape outer + (heads, channels) + seq"""
+    shape = tuple(shape)
+    if len(shape) < seq_dims + 2:
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_RANK, "channel-last tensors are outer + sequence + (heads, channels)")
+    n = len(shape)
+    return shape[: n - seq_dims - 2] + shape[n - 2:] + shape[n - seq_dims - 2: n - 2]
+
+
+def _problem(seq_dims, rule, Q, K, V, sync_mode, window_size=1, log2_stride_size=0, is_causal=False,
+             layout='channel_first'):
     code = _dtype_code(Q)
     if _dtype_code(K) != code or _dtype_code(V) != code:
         raise _capi.InvalidArgumentError(-2, "Q, K and V must have the same dtype")
-    return _capi.make_problem(code, seq_dims, rule, sync_mode, tuple(Q.shape), tuple(K.shape), tuple(V.shape),
-                              window_size, log2_stride_size, is_causal)
+    if layout not in LAYOUTS:
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_LAYOUT, f"layout must be one of {LAYOUTS}")
+    shapes = [tuple(x.shape) for x in (Q, K, V)]
+    if layout == 'channel_last':
+        shapes = [_cf_shape(sh, seq_dims) for sh in shapes]
+    p = _capi.make_problem(code, seq_dims, rule, sync_mode, shapes[0], shapes[1], shapes[2],
+                           window_size, log2_stride_size, is_causal)
+    if layout == 'channel_last':
+        p.layout = _capi.FA_LAYOUT_CHANNEL_LAST
+        p.heads = int(Q.shape[-2])
+    return p
 
 
 def _out_shapes(p, Q, V):
     sd = p.seq_dims
     qs = tuple(Q.shape)
+    if p.layout == _capi.FA_LAYOUT_CHANNEL_LAST:   # O: outer + seq + (heads, v_d); l, m: outer + (heads,) + seq
+        outer, seq = qs[: len(qs) - sd - 2], qs[len(qs) - sd - 2: len(qs) - 2]
+        return outer + seq + (qs[-2], p.v_d), outer + (qs[-2],) + seq
     batch, seq = qs[: len(qs) - sd - 1], qs[len(qs) - sd:]
     return batch + (p.v_d,) + seq, batch + seq
+
+
+def _cl_to_cf(x, seq_dims):
+    """channel-last tensor of any outer rank / 1-D or 2-D sequence -> channel-first, through the adapter kernel"""
+    sh = tuple(x.shape)
+    n = len(sh)
+    outer, seq = sh[: n - seq_dims - 2], sh[n - seq_dims - 2: n - 2]
+    y = from_channel_last(x.reshape((int(np.prod(outer, dtype=np.int64)), int(np.prod(seq, dtype=np.int64))) + sh[-2:]))
+    return y.reshape(outer + sh[-2:] + seq)
+
+
+def _cf_to_cl(x, seq_dims):
+    sh = tuple(x.shape)
+    n = len(sh)
+    outer, hc, seq = sh[: n - seq_dims - 2], sh[n - seq_dims - 2: n - seq_dims], sh[n - seq_dims:]
+    y = to_channel_last(x.reshape((int(np.prod(outer, dtype=np.int64)),) + hc + (int(np.prod(seq, dtype=np.int64)),)))
+    return y.reshape(outer + seq + hc)
+
+
+def _channel_first_problem(p):
+    q = _capi.Problem.from_buffer_copy(p)
+    q.layout, q.heads = _capi.FA_LAYOUT_CHANNEL_FIRST, 0
+    return q
 
 
 # ------------------------------------------------------------------------------------ #
@@ -108,13 +156,21 @@ def _forward_device(p, Q, K, V, out=None):
         rc = _capi.lib.fa_forward(C.byref(p), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
                                   l.data_ptr(), m.data_ptr(), ws.data_ptr() if ws is not None else None,
                                   ws_bytes, stream)
+    if rc == _capi.FA_EINVAL_LAYOUT and p.layout == _capi.FA_LAYOUT_CHANNEL_LAST and out is None:
+        # no kernel reads this dtype / shape channel-last: the adapter pass either side of the channel-first op
+        sd = p.seq_dims
+        Oc, l, m = _forward_device(_channel_first_problem(p), *(_cl_to_cf(t, sd) for t in (Q, K, V)))
+        return _cf_to_cl(Oc, sd), l, m
     _capi.check(rc, "fa_forward")
     return O, l, m
 
 
 def _backward_device(p, Q, K, V, O, l, m, dO):
     Q, K, V, O, l, m, dO = (t.contiguous() for t in (Q, K, V, O, l, m, dO))
-    _capi.check_backward_shapes(p, [tuple(t.shape) for t in (Q, K, V, O, l, m, dO)])
+    shapes = [tuple(t.shape) for t in (Q, K, V, O, l, m, dO)]
+    if p.layout == _capi.FA_LAYOUT_CHANNEL_LAST:
+        shapes = [sh if i in (4, 5) else _cf_shape(sh, p.seq_dims) for i, sh in enumerate(shapes)]
+    _capi.check_backward_shapes(p, shapes)
     dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
     with torch.cuda.device(Q.device):
         ws, ws_bytes = _workspace(_capi.lib.fa_workspace_bytes(C.byref(p), 1), Q.device)
@@ -122,6 +178,10 @@ def _backward_device(p, Q, K, V, O, l, m, dO):
         rc = _capi.lib.fa_backward(C.byref(p), Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(),
                                    l.data_ptr(), m.data_ptr(), dO.data_ptr(), dQ.data_ptr(), dK.data_ptr(),
                                    dV.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+    if rc == _capi.FA_EINVAL_LAYOUT and p.layout == _capi.FA_LAYOUT_CHANNEL_LAST:
+        sd = p.seq_dims
+        Qc, Kc, Vc, Oc, dOc = (_cl_to_cf(t, sd) for t in (Q, K, V, O, dO))
+        return tuple(_cf_to_cl(g, sd) for g in _backward_device(_channel_first_problem(p), Qc, Kc, Vc, Oc, l, m, dOc))
     _capi.check(rc, "fa_backward")
     return dQ, dK, dV
 
@@ -192,6 +252,8 @@ def backward_host(p, Q, K, V, O, l, m, dO):
 
 
 def _attend(p, Q, K, V, returning_l_m):
+    if p.layout != _capi.FA_LAYOUT_CHANNEL_FIRST and not _is_torch(Q):
+        raise _capi.InvalidArgumentError(_capi.FA_EINVAL_LAYOUT, "channel-last operands are torch CUDA tensors")
     if _is_torch(Q):
         if torch.is_grad_enabled() and (Q.requires_grad or K.requires_grad or V.requires_grad):
             results = _AttentionFn.apply(Q, K, V, p)
@@ -205,43 +267,49 @@ def _attend(p, Q, K, V, returning_l_m):
 # ------------------------------------------------------------------------------------ #
 # public API — same names, argument order and defaults as the reference
 # ------------------------------------------------------------------------------------ #
-def full_1d(Q, K, V, sync_mode='none_front', returning_l_m=False):
+# `layout` (keyword only, not in the reference): 'channel_last' takes Q, K, V as outer + sequence + (heads, channels) -
+# what a projection produces - and returns O the same way (l, m: outer + (heads,) + sequence). The fp16 tensor-core
+# kernels read and write that layout directly through their TMA descriptors; other dtypes /
+# shapes go through the adapter kernel either side of the channel-first op.
+def full_1d(Q, K, V, sync_mode='none_front', returning_l_m=False, *, layout='channel_first'):
     '''Full attention (no masking) on 1d sequences. Reference: flash_attention.py:80-119.'''
-    return _attend(_problem(1, 'full', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+    return _attend(_problem(1, 'full', Q, K, V, sync_mode, layout=layout), Q, K, V, returning_l_m)
 
 
-def causal_1d(Q, K, V, sync_mode, returning_l_m=False):
+def causal_1d(Q, K, V, sync_mode, returning_l_m=False, *, layout='channel_first'):
     '''Causal attention on 1d sequences. Reference: flash_attention.py:122-160.'''
-    return _attend(_problem(1, 'causal', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+    return _attend(_problem(1, 'causal', Q, K, V, sync_mode, layout=layout), Q, K, V, returning_l_m)
 
 
-def local_1d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False):
+def local_1d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False, *,
+             layout='channel_first'):
     '''Local attention on 1d sequences; window length 2*window_size-1, stride 2**log2_stride_size.
     Reference: flash_attention.py:163-216.'''
-    return _attend(_problem(1, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal),
+    return _attend(_problem(1, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal, layout),
                    Q, K, V, returning_l_m)
 
 
-def full_2d(Q, K, V, sync_mode='none_front', returning_l_m=False):
+def full_2d(Q, K, V, sync_mode='none_front', returning_l_m=False, *, layout='channel_first'):
     '''Full attention on 2d sequences. Reference: flash_attention.py:219-263.'''
-    return _attend(_problem(2, 'full', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+    return _attend(_problem(2, 'full', Q, K, V, sync_mode, layout=layout), Q, K, V, returning_l_m)
 
 
-def causal_2d(Q, K, V, sync_mode, returning_l_m=False):
+def causal_2d(Q, K, V, sync_mode, returning_l_m=False, *, layout='channel_first'):
     '''Causal attention on 2d sequences (row-major order). Reference: flash_attention.py:266-309.'''
-    return _attend(_problem(2, 'causal', Q, K, V, sync_mode), Q, K, V, returning_l_m)
+    return _attend(_problem(2, 'causal', Q, K, V, sync_mode, layout=layout), Q, K, V, returning_l_m)
 
 
-def local_2d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False):
+def local_2d(Q, K, V, window_size, log2_stride_size, is_causal, sync_mode, returning_l_m=False, *,
+             layout='channel_first'):
     '''Local attention on 2d sequences. Reference: flash_attention.py:312-370.'''
-    return _attend(_problem(2, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal),
+    return _attend(_problem(2, 'local', Q, K, V, sync_mode, window_size, log2_stride_size, is_causal, layout),
                    Q, K, V, returning_l_m)
 
 
 # backward ops, callable directly like the reference's `_fa_kernel.*_attention_backward{1,2}d[_float16]`
 def attention_backward(seq_dims, rule, Q, K, V, O, l, m, dO, sync_mode, window_size=1, log2_stride_size=0,
-                       is_causal=False):
-    p = _problem(seq_dims, rule, Q, K, V, sync_mode, window_size, log2_stride_size, is_causal)
+                       is_causal=False, *, layout='channel_first'):
+    p = _problem(seq_dims, rule, Q, K, V, sync_mode, window_size, log2_stride_size, is_causal, layout)
     if _is_torch(Q):
         return _backward_device(p, Q, K, V, O, l, m, dO)
     return backward_host(p, Q, K, V, O, l, m, dO)
