@@ -76,6 +76,61 @@ def test_forward_channel_last_is_bit_identical_and_direct(case):
     assert torch.equal(ll, l) and torch.equal(ml.view(torch.int16), m.view(torch.int16))
 
 
+BWD_CASES = CASES + [
+    (1, "causal", "none_front", 1, 0, False, (1,), 2, 128, 128, (640,), (640,)),     # fused dQ/dK/dV kernel, 5 key blocks
+    (1, "full", "scale_end", 1, 0, False, (2,), 2, 128, 128, (200,), (1000,)),       # fused, ragged, cross lengths
+    (1, "causal", "none_front", 1, 0, False, (1,), 3, 64, 64, (96,), (96,)),         # precise (split-operand) kernels
+    (1, "local", "none_front", 4, 0, True, (1,), 2, 128, 128, (300,), (300,)),       # precise, head_dim 128 two-kernel
+    (1, "causal", "scale_end", 1, 0, False, (1,), 2, 32, 32, (1000,), (88,)),        # precise: many queries per key
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: f"{c[0]}d-{c[1]}-{c[2]}-h{c[7]}-d{c[8]}x{c[9]}-q{'x'.join(map(str, c[10]))}-k{'x'.join(map(str, c[11]))}")
+def test_backward_channel_last_matches_channel_first_and_is_direct(case):
+    """Same kernels, same products: dK / dV and the two-kernel dQ differ from the channel-first results at most by the
+    summation order of D = rowsum(dO o O) in the statistics pass (last-bit fp32 differences before one fp16 rounding),
+    the fused kernel's dQ additionally by the order of its reduce-adds (run-dependent in both layouts)."""
+    dims, rule, mode, w, s, c = case[:6]
+    Q, K, V, dO = _inputs(case)
+    Q.requires_grad_(True), K.requires_grad_(True), V.requires_grad_(True)
+    O, l, m = _call(dims, rule, Q, K, V, mode, w, s, c)
+    grads = torch.autograd.grad(O, (Q, K, V), dO)
+    Ql, Kl, Vl = (_cl(x.detach(), dims).requires_grad_(True) for x in (Q, K, V))
+    Ol, ll, ml = _call(dims, rule, Ql, Kl, Vl, mode, w, s, c, layout="channel_last")
+    dOl = _cl(dO, dims)
+    torch.cuda.synchronize()
+    _capi.lib.fa_launch_count(1)
+    gl = torch.autograd.grad(Ol, (Ql, Kl, Vl), dOl)
+    torch.cuda.synchronize()
+    launches = _capi.lib.fa_launch_count(1)
+    assert launches <= 4, f"{launches} launches: the channel-last backward must not go through adapter / pack passes"
+    assert _capi.lib.fa_last_path() == 2
+    for name, a, b in zip(("dQ", "dK", "dV"), gl, grads):
+        assert a.shape == _cl(b, dims).shape
+        a, b = _cf(a, dims).float(), b.float()
+        err = ((a - b).abs() / b.abs().clamp(min=1.0)).max().item()
+        assert err <= 1.5e-3, f"{name}: {err}"
+        if a.numel() >= 4096:   # most elements round to the same fp16 value
+            assert (a == b).float().mean().item() >= 0.9, name
+
+
+def test_backward_channel_last_against_the_oracle():
+    """One case checked against the oracle itself (not only against the channel-first kernels)."""
+    from oracle import dense_attention as da
+    rng = np.random.default_rng(5)
+    Q, K, V, dO = da.random_inputs(rng, np.float16, (2, 3), 64, 64, (200,), (264,))
+    ref = da.attention(Q, K, V, 1, "causal", "none_front", dO=dO)
+    tq, tk, tv, tdo = (_cl(torch.from_numpy(x).cuda(), 1) for x in (Q, K, V, dO))
+    tq.requires_grad_(True), tk.requires_grad_(True), tv.requires_grad_(True)
+    O = fa.causal_1d(tq, tk, tv, "none_front", layout="channel_last")
+    grads = torch.autograd.grad(O, (tq, tk, tv), tdo)
+    assert np.max(np.abs(_cf(O.detach(), 1).cpu().numpy().astype(np.float64) - ref["O"])) <= 2e-3
+    for name, g in zip(("dQ", "dK", "dV"), grads):
+        got = _cf(g, 1).cpu().numpy().astype(np.float64)
+        err = np.max(np.abs(got - ref[name]) / np.maximum(1.0, np.abs(ref[name])))
+        assert err <= 2e-3, f"{name}: {err}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_other_dtypes_take_the_adapter(dtype):
     case = (1, "causal", "none_front", 1, 0, False, (2,), 3, 32, 32, (130,), (130,))

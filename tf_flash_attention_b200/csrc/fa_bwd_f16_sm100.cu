@@ -33,6 +33,8 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
                  bool swizzle128);  // fa_fwd_f16_sm100.cu
 bool make_map_3d(CUtensorMap* map, const void* base, int64_t batch, int64_t channels, int64_t seq, int64_t pitch,
                  int box_rows, bool swizzle128);  // fa_fwd_f16_sm100.cu
+bool make_map_cl(CUtensorMap* map, const void* base, int64_t outer, int64_t heads, int64_t channels, int64_t seq,
+                 int box_rows);  // fa_fwd_f16_sm100.cu
 
 // Workspace of the fp16 backward: [LSE2, D (+ pad)] [fp32 dQ scratch of the fused head_dim-128 kernel] [pitch-padded
 // copies of the q-length / k-length tensors when their length is not a multiple of 8 (fa_pack.cu)].
@@ -67,6 +69,7 @@ struct alignas(64) BwdParams {
   const float* lse2;   // [batch*nq + pad]  (m + log l) * log2(e), +inf on empty rows
   const float* dsum;   // [batch*nq + pad]  rowsum(dO o O)
   int32_t nq, nk, n_blocks, batch;
+  int32_t heads;       // channel-last tensors: batch element = outer * heads + head
   int32_t stat_pitch;  // floats per batch element in lse2 / dsum: nq rounded up to 4 (16-byte rows for the bulk copies)
   int32_t exact_d;     // split-operand dQ kernel: replace D = rowsum(dO o O) (O is fp16-rounded) by rowsum(P o dP)
   float* dsum_out;     // where that kernel leaves the exact D for the dK/dV kernel launched behind it (== dsum)
@@ -146,6 +149,57 @@ __global__ void bwd_prep_f16_any(const __half* __restrict__ o, const __half* __r
   }
 }
 
+// channel-last O / dO ([outer][q][heads][v_d], v_d a multiple of 8): a group of G lanes (the power of two >= v_d / 8)
+// reads one row's channels as 16-byte chunks and reduces with shuffles; one thread per (outer, q, head) row would touch
+// 16 bytes of every 2 * v_d-byte row per instruction
+template <int G>
+__global__ void bwd_prep_f16_cl(const __half* __restrict__ o, const __half* __restrict__ d_o,
+                                const float* __restrict__ l, const __half* __restrict__ m, float* __restrict__ lse2,
+                                float* __restrict__ dsum, int64_t outer, int32_t heads, int32_t v_d, int32_t nq,
+                                int32_t sp) {
+  const int64_t batch = outer * heads, total = batch * sp;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < kStatPad) {
+    lse2[total + threadIdx.x] = __int_as_float(0x7f800000);
+    dsum[total + threadIdx.x] = 0.f;
+  }
+  // the padding behind each batch element's row (nq not a multiple of 4)
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < batch * (sp - nq);
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t b = i / (sp - nq), r = nq + i % (sp - nq);
+    lse2[b * sp + r] = __int_as_float(0x7f800000);
+    dsum[b * sp + r] = 0.f;
+  }
+  const int g = threadIdx.x % G;
+  const int64_t rows = outer * nq * heads;
+  for (int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) / G; row < rows;
+       row += int64_t(gridDim.x) * blockDim.x / G) {
+    float acc = 0.f;
+    if (g * 8 < v_d) {
+      const uint4 x = *reinterpret_cast<const uint4*>(o + row * v_d + g * 8);
+      const uint4 y = *reinterpret_cast<const uint4*>(d_o + row * v_d + g * 8);
+      const __half2* xh = reinterpret_cast<const __half2*>(&x);
+      const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(xh[e]), c = __half22float2(yh[e]);
+        acc = fmaf(a.x, c.x, acc);
+        acc = fmaf(a.y, c.y, acc);
+      }
+    }
+#pragma unroll
+    for (int w = G / 2; w > 0; w >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, w, G);
+    if (g == 0) {
+      const int64_t h = row % heads, oq = row / heads, q = oq % nq, ob = oq / nq;
+      const int64_t b = ob * heads + h;
+      dsum[b * sp + q] = acc;
+      const float lv = l[b * nq + q];
+      const __half mv = m[b * nq + q];
+      lse2[b * sp + q] = (lv > 0.f && !is_sentinel<__half>(mv)) ? (__half2float(mv) + logf(lv)) * kLog2eB
+                                                                 : __int_as_float(0x7f800000);
+    }
+  }
+}
+
 // =================================================================================================
 // dQ kernel
 // =================================================================================================
@@ -164,7 +218,7 @@ struct DqCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD, bool SPLIT>
+template <int D, int VD, bool SPLIT, bool CL>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DqCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -191,6 +245,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
   const int b = int(blockIdx.x / p.n_blocks);                     // head-major: K/V stay in L2
+  const BatchCoord bc = batch_coord<CL>(b, p.heads);
   const int pair = p.n_blocks - 1 - int(blockIdx.x % p.n_blocks);  // heavy (late) rows first
   const int q0 = pair * (2 * kBM);
   const int q_hi = min(q0 + 2 * kBM, p.nq) - 1;
@@ -242,12 +297,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       if (elect_one()) {
         for (int i = 0; i < 2; ++i) {
           mbar_arrive_expect_tx(bar_q_full + 8 * i, Cfg::kQBytes + Cfg::kDoBytes);
-          for (int h = 0; h < 2; ++h) {
-            tma_load_bc(q_smem + i * Cfg::kQBytes + h * (D * 128), &p.map_q, bar_q_full + 8 * i,
-                        q0 + i * kBM + h * 64, b);
-            tma_load_bc(do_smem + i * Cfg::kDoBytes + h * (VD * 128), &p.map_do, bar_q_full + 8 * i,
-                        q0 + i * kBM + h * 64, b);
-          }
+          tile_load<CL>(q_smem + i * Cfg::kQBytes, &p.map_q, bar_q_full + 8 * i, q0 + i * kBM, kBM, D, bc);
+          tile_load<CL>(do_smem + i * Cfg::kDoBytes, &p.map_do, bar_q_full + 8 * i, q0 + i * kBM, kBM, VD, bc);
         }
         int t = 0;
         TileIter it;
@@ -257,8 +308,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
-          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b);
-          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b);
+          tile_load<CL>(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, kBN, D, bc);
+          tile_load<CL>(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, kBN, VD, bc);
           ++t;
         }
       }
@@ -267,37 +318,37 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
         TileIter it;
         it.init(sched, 2, kt_first, kt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, true, true);
-        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, false);
+        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, tile_mn_major<CL>(false));
         auto issue_s_dp = [&](int i, int stage) {
           const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + Cfg::kKBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tmem_base + i * kBN, smem_desc_sw128(q_smem + i * Cfg::kQBytes + ks * 2048, D * 128, 1024),
-                   smem_desc_sw128(k_s + ks * 2048, D * 128, 1024), idesc_s, ks > 0);
+            mma_ss(tmem_base + i * kBN, tile_desc<CL>(q_smem + i * Cfg::kQBytes, ks, kBM, D, true),
+                   tile_desc<CL>(k_s, ks, kBN, D, true), idesc_s, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
             mma_ss(tmem_base + 128 + i * kBN,
-                   smem_desc_sw128(do_smem + i * Cfg::kDoBytes + ks * 2048, VD * 128, 1024),
-                   smem_desc_sw128(v_s + ks * 2048, VD * 128, 1024), idesc_s, ks > 0);
+                   tile_desc<CL>(do_smem + i * Cfg::kDoBytes, ks, kBM, VD, true),
+                   tile_desc<CL>(v_s, ks, kBN, VD, true), idesc_s, ks > 0);
         };
         auto issue_dq = [&](int i, int stage, bool accumulate) {
           const uint32_t k_s = ring + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + ks * 8,
-                   smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // dS lo halves: the 32 columns behind the packed hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 256 + i * 128, tmem_base + i * kBN + 32 + ks * 8,
-                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+                     tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, 1u);
           }
           if constexpr (kExact) {   // A2_i += P K: P (fp16) in the dP columns, A2 in the upper half of the dQ_i columns
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 256 + i * 128 + 64, tmem_base + 128 + i * kBN + ks * 8,
-                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+                     tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           }
         };
         if (n > 0) {
@@ -408,7 +459,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
       ++j;
     }
     // epilogue: dQ = scale * acc -> fp16 -> smem [D][64] x2 -> TMA store
-    __half* stage_h = reinterpret_cast<__half*>(smem_gen + i * Cfg::kQBytes) + (r >> 6) * (D * 64) + (r & 63);
+    uint8_t* stage_gen = smem_gen + i * Cfg::kQBytes;
     if (j > 0) {
       mbar_wait(bar_final + 8 * i, 0);
       tc_fence_after();
@@ -431,20 +482,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dq_kernel(const __grid_con
 #pragma unroll
           for (int e = 0; e < 32; ++e) o[e] = fmaf(-delta, o2[e], o[e]);
         }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
+        stage_row32<CL>(stage_gen, r, c * 32, kBM, D, o, p.scale);
       }
     } else {
       mbar_wait(bar_q_full + 8 * i, 0);
-#pragma unroll 8
-      for (int c = 0; c < D; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+      stage_row_zero<CL>(stage_gen, r, 0, D, kBM, D);
     }
     fence_proxy_async_smem();
     named_bar_sync(1 + i, kBM);
     if (r == 0 && tile_valid) {
-      for (int h = 0; h < 2; ++h)
-        if (tq0 + h * 64 < p.nq)
-          tma_store_bc(&p.map_dq, q_smem + i * Cfg::kQBytes + h * (D * 128), tq0 + h * 64, b);
+      tile_store<CL>(&p.map_dq, q_smem + i * Cfg::kQBytes, tq0, kBM, D, p.nq, bc);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -476,7 +523,7 @@ struct DqSmallCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD, bool SPLIT>
+template <int D, int VD, bool SPLIT, bool CL>
 __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DqSmallCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -500,6 +547,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
   const int b = int(blockIdx.x / p.n_blocks);                     // head-major: K/V stay in L2
+  const BatchCoord bc = batch_coord<CL>(b, p.heads);
   const int pair = p.n_blocks - 1 - int(blockIdx.x % p.n_blocks);  // heavy (late) rows first
   const int q0 = pair * kBM;
   const int q_hi = min(q0 + kBM, p.nq) - 1;
@@ -556,10 +604,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
     if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_q_full, Cfg::kQBytes + Cfg::kDoBytes);
-        for (int h = 0; h < 2; ++h) {
-          tma_load_bc(q_smem + h * (D * 128), &p.map_q, bar_q_full, q0 + h * 64, b);
-          tma_load_bc(do_smem + h * (VD * 128), &p.map_do, bar_q_full, q0 + h * 64, b);
-        }
+        tile_load<CL>(q_smem, &p.map_q, bar_q_full, q0, kBM, D, bc);
+        tile_load<CL>(do_smem, &p.map_do, bar_q_full, q0, kBM, VD, bc);
         int t = 0;
         TileIter it;
         it.init(sched, 1, kt_first, kt_last);
@@ -568,8 +614,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_kv_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_kv_full + 8 * s, Cfg::kStageBytes);
-          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, b);
-          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, b);
+          tile_load<CL>(ring + s * Cfg::kStageBytes, &p.map_k, bar_kv_full + 8 * s, kt * kBN, kBN, D, bc);
+          tile_load<CL>(ring + s * Cfg::kStageBytes + Cfg::kKBytes, &p.map_v, bar_kv_full + 8 * s, kt * kBN, kBN, VD, bc);
           ++t;
         }
       }
@@ -578,18 +624,18 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
         TileIter it;
         it.init(sched, 1, kt_first, kt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, true, true);
-        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, false);
+        constexpr uint32_t idesc_s = idesc_f16(kBM, kBN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_dq = idesc_f16(kBM, D, false, tile_mn_major<CL>(false));
         auto issue_s_dp = [&](int stage) {
           const uint32_t k_s = ring + stage * Cfg::kStageBytes, v_s = k_s + Cfg::kKBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tmem_base, smem_desc_sw128(q_smem + ks * 2048, D * 128, 1024),
-                   smem_desc_sw128(k_s + ks * 2048, D * 128, 1024), idesc_s, ks > 0);
+            mma_ss(tmem_base, tile_desc<CL>(q_smem, ks, kBM, D, true),
+                   tile_desc<CL>(k_s, ks, kBN, D, true), idesc_s, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
-            mma_ss(tmem_base + 64, smem_desc_sw128(do_smem + ks * 2048, VD * 128, 1024),
-                   smem_desc_sw128(v_s + ks * 2048, VD * 128, 1024), idesc_s, ks > 0);
+            mma_ss(tmem_base + 64, tile_desc<CL>(do_smem, ks, kBM, VD, true),
+                   tile_desc<CL>(v_s, ks, kBN, VD, true), idesc_s, ks > 0);
         };
         auto issue_dq = [&](int stage, bool accumulate) {
           const uint32_t k_s = ring + stage * Cfg::kStageBytes;
@@ -597,16 +643,16 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
-                   smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // the lo halves sit 16 columns behind their hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
-                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, 1u);
+                     tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, 1u);
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)   // A2 += P K (P in the dP columns)
               mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
-                     smem_desc_sw128(k_s + ks * 32, 16, 1024), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
+                     tile_desc<CL>(k_s, ks, kBN, D, false), idesc_dq, (accumulate || ks > 0) ? 1u : 0u);
           }
         };
         if (n > 0) {
@@ -701,7 +747,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
       ++j;
     }
     // epilogue: dQ = scale * acc -> fp16 -> smem [D][64] x2 -> TMA store; warpgroup x handles channels [32x, 32x+32)
-    __half* stage_h = reinterpret_cast<__half*>(smem_gen) + (r >> 6) * (D * 64) + (r & 63);
+    uint8_t* stage_gen = smem_gen;
     if (j > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -728,20 +774,16 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dq_small_kernel(const __gr
 #pragma unroll
           for (int e = 0; e < 32; ++e) o[e] = fmaf(-delta, o2[e], o[e]);
         }
-#pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * p.scale);
+        stage_row32<CL>(stage_gen, r, c * 32, kBM, D, o, p.scale);
       }
     } else {
       mbar_wait(bar_q_full, 0);
-      for (int c = x * 32; c < D; c += 64)
-#pragma unroll 8
-        for (int e = 0; e < 32; ++e) stage_h[(c + e) * 64] = __float2half_rn(0.f);
+      for (int c = x * 32; c < D; c += 64) stage_row_zero<CL>(stage_gen, r, c, c + 32, kBM, D);
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 2 * kBM);
     if (threadIdx.x == 0) {
-      for (int h = 0; h < 2; ++h)
-        if (q0 + h * 64 < p.nq) tma_store_bc(&p.map_dq, q_smem + h * (D * 128), q0 + h * 64, b);
+      tile_store<CL>(&p.map_dq, q_smem, q0, kBM, D, p.nq, bc);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -782,7 +824,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
                : "memory");
 }
 
-template <int D, int VD, bool SPLIT>
+template <int D, int VD, bool SPLIT, bool CL>
 __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DkvCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -808,6 +850,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
   const int b = int(blockIdx.x / p.n_blocks);     // head-major: Q/dO stay in L2
+  const BatchCoord bc = batch_coord<CL>(b, p.heads);
   const int kblk = int(blockIdx.x % p.n_blocks);  // early key tiles are the heavy ones under causal
   const int k0 = kblk * kBM;
   const int k_hi = min(k0 + kBM, p.nk) - 1;
@@ -859,10 +902,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
     if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
-        for (int h = 0; h < 2; ++h) {
-          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
-          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
-        }
+        tile_load<CL>(k_smem, &p.map_k, bar_kv_res, k0, kBM, D, bc);
+        tile_load<CL>(v_smem, &p.map_v, bar_kv_res, k0, kBM, VD, bc);
         int t = 0;
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
@@ -871,8 +912,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
-          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          tile_load<CL>(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, kBN, D, bc);
+          tile_load<CL>(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, kBN, VD, bc);
           const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
@@ -884,41 +925,41 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
-        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
-        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, tile_mn_major<CL>(false));
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, tile_mn_major<CL>(false));
         auto issue_st_dpt = [&](int x, int stage) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
-                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base + x * kBN, tile_desc<CL>(k_smem, ks, kBM, D, true),
+                   tile_desc<CL>(q_s, ks, kBN, D, true), idesc_st, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
-            mma_ss(tmem_base + 128 + x * kBN, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
-                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base + 128 + x * kBN, tile_desc<CL>(v_smem, ks, kBM, VD, true),
+                   tile_desc<CL>(do_s, ks, kBN, VD, true), idesc_st, ks > 0);
         };
         auto issue_dv_dk = [&](int x, int stage, bool accumulate) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+            mma_ts(tmem_base + 256, tmem_base + x * kBN + ks * 8, tile_desc<CL>(do_s, ks, kBN, VD, false),
                    idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // P^T lo halves: the 32 columns behind the packed hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
-              mma_ts(tmem_base + 256, tmem_base + x * kBN + 32 + ks * 8, smem_desc_sw128(do_s + ks * 32, 16, 1024),
+              mma_ts(tmem_base + 256, tmem_base + x * kBN + 32 + ks * 8, tile_desc<CL>(do_s, ks, kBN, VD, false),
                      idesc_dv, 1u);
           }
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
-            mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + ks * 8, smem_desc_sw128(q_s + ks * 32, 16, 1024),
+            mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + ks * 8, tile_desc<CL>(q_s, ks, kBN, D, false),
                    idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // dS^T lo halves: the 32 columns behind the packed hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 384, tmem_base + 128 + x * kBN + 32 + ks * 8,
-                     smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, 1u);
+                     tile_desc<CL>(q_s, ks, kBN, D, false), idesc_dk, 1u);
           }
         };
         if (n > 0) {
@@ -1034,7 +1075,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
     const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 256 : 384);
     const float out_scale = x == 0 ? 1.f : p.scale;
     uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
-    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -1042,23 +1082,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) bwd_dkdv_kernel(const __grid_c
         float o[32];
         tmem_ld32f(t_acc + c * 32, o);
         tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+        stage_row32<CL>(stage_gen, r, c * 32, kBM, CH, o, out_scale);
       }
     } else {
       mbar_wait(bar_kv_res, 0);
-      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+      stage_row_zero<CL>(stage_gen, r, 0, CH, kBM, CH);
     }
     fence_proxy_async_smem();
     named_bar_sync(1 + x, kBM);
     if (r == 0) {
-      for (int h = 0; h < 2; ++h)
-        if (k0 + h * 64 < p.nk) {
-          if (x == 0)
-            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
-          else
-            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
-        }
+      if (x == 0)
+        tile_store<CL>(&p.map_dv, v_smem, k0, kBM, VD, p.nk, bc);
+      else
+        tile_store<CL>(&p.map_dk, k_smem, k0, kBM, D, p.nk, bc);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -1092,7 +1128,7 @@ struct DkvSmallCfg {
   static constexpr int kSmemBytes = kSchedOffset + int(sizeof(TileSchedule)) + 1024;
 };
 
-template <int D, int VD, bool SPLIT>
+template <int D, int VD, bool SPLIT, bool CL>
 __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __grid_constant__ BwdParams p) {
   using Cfg = DkvSmallCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -1118,6 +1154,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
   const int b = int(blockIdx.x / p.n_blocks);     // head-major: Q/dO stay in L2
+  const BatchCoord bc = batch_coord<CL>(b, p.heads);
   const int kblk = int(blockIdx.x % p.n_blocks);  // early key tiles are the heavy ones under causal
   const int k0 = kblk * kBM;
   const int k_hi = min(k0 + kBM, p.nk) - 1;
@@ -1171,10 +1208,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
     if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
-        for (int h = 0; h < 2; ++h) {
-          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
-          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
-        }
+        tile_load<CL>(k_smem, &p.map_k, bar_kv_res, k0, kBM, D, bc);
+        tile_load<CL>(v_smem, &p.map_v, bar_kv_res, k0, kBM, VD, bc);
         int t = 0;
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
@@ -1183,8 +1218,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
-          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          tile_load<CL>(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, kBN, D, bc);
+          tile_load<CL>(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, kBN, VD, bc);
           const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
@@ -1196,19 +1231,19 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
-        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
-        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, tile_mn_major<CL>(false));
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, tile_mn_major<CL>(false));
         auto issue_st_dpt = [&](int stage) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tmem_base, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
-                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base, tile_desc<CL>(k_smem, ks, kBM, D, true),
+                   tile_desc<CL>(q_s, ks, kBN, D, true), idesc_st, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
-            mma_ss(tmem_base + 64, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
-                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base + 64, tile_desc<CL>(v_smem, ks, kBM, VD, true),
+                   tile_desc<CL>(do_s, ks, kBN, VD, true), idesc_st, ks > 0);
         };
         auto issue_dv_dk = [&](int stage, bool accumulate) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes, do_s = q_s + Cfg::kQBytes;
@@ -1216,22 +1251,22 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8,
-                   smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(do_s, ks, kBN, VD, false), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // P^T lo halves, 16 columns behind the hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 128, tmem_base + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
-                     smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, 1u);
+                     tile_desc<CL>(do_s, ks, kBN, VD, false), idesc_dv, 1u);
           }
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8,
-                   smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(q_s, ks, kBN, D, false), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
           if constexpr (SPLIT) {   // dS^T lo halves, 16 columns behind the hi halves
 #pragma unroll
             for (int ks = 0; ks < kBN / 16; ++ks)
               mma_ts(tmem_base + 192, tmem_base + 64 + (ks >> 1) * 32 + (ks & 1) * 8 + 16,
-                     smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, 1u);
+                     tile_desc<CL>(q_s, ks, kBN, D, false), idesc_dk, 1u);
           }
         };
         if (n > 0) {
@@ -1348,7 +1383,6 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
     const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 128 : 192);
     const float out_scale = x == 0 ? 1.f : p.scale;
     uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
-    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -1356,23 +1390,19 @@ __global__ void __launch_bounds__(kBwdThreads, 2) bwd_dkdv_small_kernel(const __
         float o[32];
         tmem_ld32f(t_acc + c * 32, o);
         tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+        stage_row32<CL>(stage_gen, r, c * 32, kBM, CH, o, out_scale);
       }
     } else {
       mbar_wait(bar_kv_res, 0);
-      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+      stage_row_zero<CL>(stage_gen, r, 0, CH, kBM, CH);
     }
     fence_proxy_async_smem();
     named_bar_sync(1 + x, kBM);
     if (r == 0) {
-      for (int h = 0; h < 2; ++h)
-        if (k0 + h * 64 < p.nk) {
-          if (x == 0)
-            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
-          else
-            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
-        }
+      if (x == 0)
+        tile_store<CL>(&p.map_dv, v_smem, k0, kBM, VD, p.nk, bc);
+      else
+        tile_store<CL>(&p.map_dk, k_smem, k0, kBM, D, p.nk, bc);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -1467,7 +1497,7 @@ struct alignas(64) FusedParams {
   CUtensorMap map_dq_acc;   // fp32 [batch*D, nq], box 32 x D, 128B swizzle
 };
 
-template <int D, int VD>
+template <int D, int VD, bool CL>
 __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __grid_constant__ FusedParams fp) {
   using Cfg = FusedCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -1499,6 +1529,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
   const int warp = threadIdx.x >> 5;
   const FaRule& rule = p.rule;
   const int b = int(blockIdx.x / p.n_blocks);
+  const BatchCoord bc = batch_coord<CL>(b, p.heads);
   const int kblk = int(blockIdx.x % p.n_blocks);
   const int k0 = kblk * kBM;
   const int k_hi = min(k0 + kBM, p.nk) - 1;
@@ -1605,10 +1636,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
     if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kKBytes + Cfg::kVBytes);
-        for (int h = 0; h < 2; ++h) {
-          tma_load_bc(k_smem + h * (D * 128), &p.map_k, bar_kv_res, k0 + h * 64, b);
-          tma_load_bc(v_smem + h * (VD * 128), &p.map_v, bar_kv_res, k0 + h * 64, b);
-        }
+        tile_load<CL>(k_smem, &p.map_k, bar_kv_res, k0, kBM, D, bc);
+        tile_load<CL>(v_smem, &p.map_v, bar_kv_res, k0, kBM, VD, bc);
         int t = 0;
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
@@ -1617,8 +1646,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
           const int s = t % kStages, u = t / kStages;
           mbar_wait(bar_empty + 8 * s, (u & 1) ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes + Cfg::kStatBytes);
-          tma_load_bc(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, b);
-          tma_load_bc(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, b);
+          tile_load<CL>(ring + s * Cfg::kStageBytes, &p.map_q, bar_full + 8 * s, qt * kBN, kBN, D, bc);
+          tile_load<CL>(ring + s * Cfg::kStageBytes + Cfg::kQBytes, &p.map_do, bar_full + 8 * s, qt * kBN, kBN, VD, bc);
           const int64_t off = int64_t(b) * p.stat_pitch + qt * kBN;
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes, p.lse2 + off, kBN * 4, bar_full + 8 * s);
           bulk_load_1d(stat_smem + s * Cfg::kStatBytes + kBN * 4, p.dsum + off, kBN * 4, bar_full + 8 * s);
@@ -1631,29 +1660,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
         const int n = it.count();
-        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, true, true);
-        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, false);
-        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, false);
-        constexpr uint32_t idesc_dq = idesc_f16(D, kBN, false, true);
+        constexpr uint32_t idesc_st = idesc_f16(kBM, kBN, tile_mn_major<CL>(true), tile_mn_major<CL>(true));
+        constexpr uint32_t idesc_dv = idesc_f16(kBM, VD, false, tile_mn_major<CL>(false));
+        constexpr uint32_t idesc_dk = idesc_f16(kBM, D, false, tile_mn_major<CL>(false));
+        constexpr uint32_t idesc_dq = idesc_f16(D, kBN, tile_mn_major<CL>(false), true);
         auto issue_st = [&](int x, int stage) {
           const uint32_t q_s = ring + stage * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks)
-            mma_ss(tmem_base + x * kBN, smem_desc_sw128(k_smem + ks * 2048, D * 128, 1024),
-                   smem_desc_sw128(q_s + ks * 2048, D * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base + x * kBN, tile_desc<CL>(k_smem, ks, kBM, D, true),
+                   tile_desc<CL>(q_s, ks, kBN, D, true), idesc_st, ks > 0);
         };
         auto issue_dpt = [&](int x, int stage) {
           const uint32_t do_s = ring + stage * Cfg::kStageBytes + Cfg::kQBytes;
 #pragma unroll
           for (int ks = 0; ks < VD / 16; ++ks)
-            mma_ss(tmem_base + 128 + x * kBN, smem_desc_sw128(v_smem + ks * 2048, VD * 128, 1024),
-                   smem_desc_sw128(do_s + ks * 2048, VD * 128, 1024), idesc_st, ks > 0);
+            mma_ss(tmem_base + 128 + x * kBN, tile_desc<CL>(v_smem, ks, kBM, VD, true),
+                   tile_desc<CL>(do_s, ks, kBN, VD, true), idesc_st, ks > 0);
         };
         auto issue_dq = [&](int x) {
 #pragma unroll
           for (int ks = 0; ks < kBM / 16; ++ks)
             mma_ss(tmem_base + 128 + x * kBN,
-                   smem_desc_sw128(k_smem + (ks >> 2) * (D * 128) + (ks & 3) * 32, 16, 1024),
+                   tile_desc<CL>(k_smem, ks, kBM, D, false),
                    smem_desc_sw128(ds_smem + x * Cfg::kDsBytes + ks * 2048, 16, 1024), idesc_dq, ks > 0);
         };
         auto issue_dv_dk = [&](int x, int stage, bool accumulate) {
@@ -1661,11 +1690,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 256, tmem_base + x * kBN + (ks >> 1) * 32 + (ks & 1) * 8,
-                   smem_desc_sw128(do_s + ks * 32, 16, 1024), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(do_s, ks, kBN, VD, false), idesc_dv, (accumulate || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < kBN / 16; ++ks)
             mma_ts(tmem_base + 384, tmem_base + x * kBN + (ks >> 1) * 32 + 16 + (ks & 1) * 8,
-                   smem_desc_sw128(q_s + ks * 32, 16, 1024), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
+                   tile_desc<CL>(q_s, ks, kBN, D, false), idesc_dk, (accumulate || ks > 0) ? 1u : 0u);
         };
         if (n > 0) {
           mbar_wait(bar_kv_res, 0);
@@ -1813,7 +1842,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
     const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 256 : 384);
     const float out_scale = x == 0 ? 1.f : p.scale;
     uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
-    __half* stage_h = reinterpret_cast<__half*>(stage_gen) + (r >> 6) * (CH * 64) + (r & 63);
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
@@ -1821,23 +1849,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         float o[32];
         tmem_ld32f(t_acc + c * 32, o);
         tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) stage_h[(c * 32 + e) * 64] = __float2half_rn(o[e] * out_scale);
+        stage_row32<CL>(stage_gen, r, c * 32, kBM, CH, o, out_scale);
       }
     } else {
       mbar_wait(bar_kv_res, 0);
-      for (int c = 0; c < CH; ++c) stage_h[c * 64] = __float2half_rn(0.f);
+      stage_row_zero<CL>(stage_gen, r, 0, CH, kBM, CH);
     }
     fence_proxy_async_smem();
     named_bar_sync(1 + x, kBM);
     if (r == 0) {
-      for (int h = 0; h < 2; ++h)
-        if (k0 + h * 64 < p.nk) {
-          if (x == 0)
-            tma_store_bc(&p.map_dv, v_smem + h * (VD * 128), k0 + h * 64, b);
-          else
-            tma_store_bc(&p.map_dk, k_smem + h * (D * 128), k0 + h * 64, b);
-        }
+      if (x == 0)
+        tile_store<CL>(&p.map_dv, v_smem, k0, kBM, VD, p.nk, bc);
+      else
+        tile_store<CL>(&p.map_dk, k_smem, k0, kBM, D, p.nk, bc);
       tma_store_commit();
       tma_store_wait_read();
     }
@@ -1860,6 +1884,32 @@ __global__ void bwd_dq_convert(const float4* __restrict__ acc, uint4* __restrict
     o.z = pack_half2(c.x * scale, c.y * scale);
     o.w = pack_half2(c.z * scale, c.w * scale);
     dq[i] = o;
+  }
+}
+
+// channel-last dQ: the fused kernel's scratch stays [batch * 128][pitch] fp32 (its drain is layout-independent); this
+// pass scales, rounds and transposes 64 positions x 128 channels per block through shared memory into
+// [outer][q][heads][128] fp16
+__global__ void __launch_bounds__(256) bwd_dq_convert_cl(const float* __restrict__ acc, __half* __restrict__ dq,
+                                                         int32_t nq, int64_t pitch, int32_t heads, float scale) {
+  constexpr int kPitch = 130;   // halves per staged position row: 4-byte aligned rows, 2-way bank conflicts at most
+  __shared__ __half tile[64 * kPitch];
+  const int b = blockIdx.y, q0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = q0 + 2 * lane;
+  for (int d = warp; d < 128; d += 8) {
+    float2 v = make_float2(0.f, 0.f);
+    if (q < pitch) v = *reinterpret_cast<const float2*>(acc + (int64_t(b) * 128 + d) * pitch + q);   // pitch is even
+    tile[(2 * lane) * kPitch + d] = __float2half_rn(v.x * scale);
+    tile[(2 * lane + 1) * kPitch + d] = __float2half_rn(v.y * scale);
+  }
+  __syncthreads();
+  const int64_t ob = b / heads, h = b % heads;
+  for (int r = warp; r < 64 && q0 + r < nq; r += 8) {
+    __half2* dst = reinterpret_cast<__half2*>(dq + ((ob * nq + q0 + r) * heads + h) * 128);
+    const __half2* src = reinterpret_cast<const __half2*>(tile + r * kPitch);
+    dst[lane] = src[lane];
+    dst[lane + 32] = src[lane + 32];
   }
 }
 
@@ -1889,12 +1939,39 @@ static bool precise_auto(const FaRule& r) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-// D, VD: the kernels' padded channel counts (a.d <= D, a.v_d <= VD; the 3-D tensor maps zero-fill / clip the rest)
-template <int D, int VD>
+// Tensor maps of one kernel. Channel-first boxes are 64 positions x the kernel's channels for every kernel; a
+// channel-last box is 64 channels x the tile's rows, which differ per kernel: rq rows for the q-length tensors
+// (Q, dO, dQ), rk for the k-length ones.
+template <int D, int VD, bool CL>
+static bool bwd_maps(BwdParams* p, const LaunchArgs& a, int rq, int rk) {
+  const int nq = a.rule.q.total, nk = a.rule.k.total;
+  if constexpr (CL) {
+    const int64_t heads = a.heads, outer = a.batch / heads;
+    return make_map_cl(&p->map_q, a.q, outer, heads, a.d, nq, rq) && make_map_cl(&p->map_k, a.k, outer, heads, a.d, nk, rk) &&
+           make_map_cl(&p->map_v, a.v, outer, heads, a.v_d, nk, rk) &&
+           make_map_cl(&p->map_do, a.d_o, outer, heads, a.v_d, nq, rq) &&
+           make_map_cl(&p->map_dq, a.d_q, outer, heads, a.d, nq, rq) &&
+           make_map_cl(&p->map_dk, a.d_k, outer, heads, a.d, nk, rk) &&
+           make_map_cl(&p->map_dv, a.d_v, outer, heads, a.v_d, nk, rk);
+  } else {
+    const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
+    return make_map_3d(&p->map_q, a.q, a.batch, a.d, nq, qp, D, true) &&
+           make_map_3d(&p->map_k, a.k, a.batch, a.d, nk, kp, D, true) &&
+           make_map_3d(&p->map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) &&
+           make_map_3d(&p->map_do, a.d_o, a.batch, a.v_d, nq, qp, VD, true) &&
+           make_map_3d(&p->map_dq, a.d_q, a.batch, a.d, nq, qp, D, false) &&
+           make_map_3d(&p->map_dk, a.d_k, a.batch, a.d, nk, kp, D, false) &&
+           make_map_3d(&p->map_dv, a.d_v, a.batch, a.v_d, nk, kp, VD, false);
+  }
+}
+
+// D, VD: the kernels' padded channel counts (a.d <= D, a.v_d <= VD; the tensor maps zero-fill / clip the rest)
+template <int D, int VD, bool CL>
 cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   BwdParams p;
   const int nq = a.rule.q.total, nk = a.rule.k.total;
-  const int64_t qp = a.q_pitch ? a.q_pitch : nq, kp = a.k_pitch ? a.k_pitch : nk;
+  // row pitch of the fused kernel's fp32 dQ scratch (and, channel-first, of the dQ tensor the convert pass writes)
+  const int64_t qp = CL ? ((int64_t(nq) + 7) & ~int64_t(7)) : (a.q_pitch ? a.q_pitch : nq);
   // fa_set_grad_precision: 1 = dS as hi + lo fp16 pairs everywhere (head_dim 128 then runs the two-kernel backward),
   // 2 = never, 0 = automatic: on for every path but the fused head_dim-128 kernel, whose TMEM has no room for the lo
   // halves and whose shapes (long rows, small P) measure inside the 2e-3 bar without them
@@ -1903,20 +1980,13 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   float* lse2 = reinterpret_cast<float*>(a.workspace);
   const int64_t sp = stat_pitch_of(nq);
   float* dsum = lse2 + (a.batch * sp + kStatPad);
-  if (!make_map_3d(&p.map_q, a.q, a.batch, a.d, nq, qp, D, true) ||
-      !make_map_3d(&p.map_k, a.k, a.batch, a.d, nk, kp, D, true) ||
-      !make_map_3d(&p.map_v, a.v, a.batch, a.v_d, nk, kp, VD, true) ||
-      !make_map_3d(&p.map_do, a.d_o, a.batch, a.v_d, nq, qp, VD, true) ||
-      !make_map_3d(&p.map_dq, a.d_q, a.batch, a.d, nq, qp, D, false) ||
-      !make_map_3d(&p.map_dk, a.d_k, a.batch, a.d, nk, kp, D, false) ||
-      !make_map_3d(&p.map_dv, a.d_v, a.batch, a.v_d, nk, kp, VD, false))
-    return cudaErrorInvalidValue;
   p.rule = a.rule;
   p.lse2 = lse2;
   p.dsum = dsum;
   p.nq = nq;
   p.nk = nk;
   p.batch = int32_t(a.batch);
+  p.heads = CL ? a.heads : 1;
   p.stat_pitch = int32_t(sp);
   // the exact row sum needs every key of a row in this call (a ring block sees a key shard only)
   p.exact_d = (split && !a.partial_keys) ? 1 : 0;
@@ -1926,8 +1996,23 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   {
     // statistics from the caller's own (dense) O and dO
     const int64_t total = a.batch * sp;
-    ScopedKernel timed("bwd_prep_f16", stream);
-    if (nq % 2 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.prep_d_o) & 3) == 0) {
+    ScopedKernel timed(CL ? "bwd_prep_f16_cl" : "bwd_prep_f16", stream);
+    if constexpr (CL) {
+      const int64_t outer = a.batch / a.heads;
+      const int chunks = a.v_d / 8;
+      const int64_t rows = outer * nq * int64_t(a.heads);
+      auto go = [&](auto kern, int G) {
+        const int blocks = int(std::min<int64_t>((rows * G + 255) / 256, 148 * 16));
+        kern<<<std::max(blocks, 1), 256, 0, stream>>>((const __half*)a.o, (const __half*)a.prep_d_o, (const float*)a.l,
+                                                     (const __half*)a.m, lse2, dsum, outer, a.heads, a.v_d, nq, int32_t(sp));
+      };
+      if (chunks <= 1) go(bwd_prep_f16_cl<1>, 1);
+      else if (chunks <= 2) go(bwd_prep_f16_cl<2>, 2);
+      else if (chunks <= 4) go(bwd_prep_f16_cl<4>, 4);
+      else if (chunks <= 8) go(bwd_prep_f16_cl<8>, 8);
+      else go(bwd_prep_f16_cl<16>, 16);
+    } else if (nq % 2 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 3) == 0 &&
+               (reinterpret_cast<uintptr_t>(a.prep_d_o) & 3) == 0) {
       const int blocks = int(std::min<int64_t>((total / 2 + 255) / 256, 148 * 16));
       bwd_prep_f16<<<blocks, 256, 0, stream>>>((const __half*)a.o, (const __half*)a.prep_d_o, (const float*)a.l,
                                                (const __half*)a.m, lse2, dsum, a.batch, a.v_d, nq, int32_t(sp));
@@ -1943,6 +2028,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     if (a.variant != 4 && !split && fused_shape) {
       // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics, with the row pitch of the dQ tensor the convert pass
       // writes (the padded pitch when the q side is packed; the columns past nq only ever receive zeros)
+      if (!bwd_maps<D, VD, CL>(&p, a, kBN, kBM)) return cudaErrorInvalidValue;
       float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + bwd_layout(a).off_acc);
       const size_t acc_bytes = size_t(a.batch) * D * qp * sizeof(float);
       FusedParams fp;
@@ -1954,17 +2040,22 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
       }
       {
-        auto kern = bwd_fused_kernel<D, VD>;
+        auto kern = bwd_fused_kernel<D, VD, CL>;
         cudaError_t e =
             plan::ensure_smem(kern, FusedCfg<D, VD>::kSmemBytes);
         if (e != cudaSuccess) return e;
         fp.base.n_blocks = (nk + kBM - 1) / kBM;
-        ScopedKernel timed("bwd_fused_f16_sm100", stream);
+        ScopedKernel timed(CL ? "bwd_fused_f16_sm100_cl" : "bwd_fused_f16_sm100", stream);
         kern<<<unsigned(int64_t(fp.base.n_blocks) * p.batch), kFusedThreads, FusedCfg<D, VD>::kSmemBytes, stream>>>(fp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
       }
-      {
+      if constexpr (CL) {
+        ScopedKernel timed("bwd_dq_convert_cl", stream);
+        bwd_dq_convert_cl<<<dim3(unsigned((nq + 63) / 64), unsigned(a.batch)), 256, 0, stream>>>(
+            acc, reinterpret_cast<__half*>(a.d_q), nq, qp, a.heads, p.scale);
+        return cudaGetLastError();
+      } else {
         const int64_t n8 = a.batch * int64_t(D) * qp / 8;
         const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 148 * 16));
         ScopedKernel timed("bwd_dq_convert", stream);
@@ -1974,15 +2065,16 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       }
     }
   }
+  if (!bwd_maps<D, VD, CL>(&p, a, kBM, kBN)) return cudaErrorInvalidValue;   // dQ kernels: resident queries
   bool dq_done = false;
   if constexpr (D == 64 && VD == 64) {
     if (a.variant != 4) {
-      auto kern = split ? bwd_dq_small_kernel<D, VD, true> : bwd_dq_small_kernel<D, VD, false>;
+      auto kern = split ? bwd_dq_small_kernel<D, VD, true, CL> : bwd_dq_small_kernel<D, VD, false, CL>;
       cudaError_t e =
           plan::ensure_smem(kern, DqSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
       p.n_blocks = (nq + kBM - 1) / kBM;
-      ScopedKernel timed("bwd_dq_f16_sm100_2cta", stream);
+      ScopedKernel timed(CL ? "bwd_dq_f16_sm100_2cta_cl" : "bwd_dq_f16_sm100_2cta", stream);
       kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DqSmallCfg<D, VD>::kSmemBytes, stream>>>(p);
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
@@ -1990,34 +2082,35 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
     }
   }
   if (!dq_done) {
-    auto kern = split ? bwd_dq_kernel<D, VD, true> : bwd_dq_kernel<D, VD, false>;
+    auto kern = split ? bwd_dq_kernel<D, VD, true, CL> : bwd_dq_kernel<D, VD, false, CL>;
     cudaError_t e = plan::ensure_smem(kern, DqCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nq + 2 * kBM - 1) / (2 * kBM);
-    ScopedKernel timed("bwd_dq_f16_sm100", stream);
+    ScopedKernel timed(CL ? "bwd_dq_f16_sm100_cl" : "bwd_dq_f16_sm100", stream);
     kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DqCfg<D, VD>::kSmemBytes, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  if (CL && !bwd_maps<D, VD, CL>(&p, a, kBN, kBM)) return cudaErrorInvalidValue;   // dK/dV kernels: resident keys
   if constexpr (D == 64 && VD == 64) {
     if (a.variant != 4) {
-      auto kern = split ? bwd_dkdv_small_kernel<D, VD, true> : bwd_dkdv_small_kernel<D, VD, false>;
+      auto kern = split ? bwd_dkdv_small_kernel<D, VD, true, CL> : bwd_dkdv_small_kernel<D, VD, false, CL>;
       cudaError_t e =
           plan::ensure_smem(kern, DkvSmallCfg<D, VD>::kSmemBytes);
       if (e != cudaSuccess) return e;
       p.n_blocks = (nk + kBM - 1) / kBM;
-      ScopedKernel timed("bwd_dkdv_f16_sm100_2cta", stream);
+      ScopedKernel timed(CL ? "bwd_dkdv_f16_sm100_2cta_cl" : "bwd_dkdv_f16_sm100_2cta", stream);
       kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DkvSmallCfg<D, VD>::kSmemBytes, stream>>>(p);
       return cudaGetLastError();
     }
   }
   {
-    auto kern = split ? bwd_dkdv_kernel<D, VD, true> : bwd_dkdv_kernel<D, VD, false>;
+    auto kern = split ? bwd_dkdv_kernel<D, VD, true, CL> : bwd_dkdv_kernel<D, VD, false, CL>;
     cudaError_t e =
         plan::ensure_smem(kern, DkvCfg<D, VD>::kSmemBytes);
     if (e != cudaSuccess) return e;
     p.n_blocks = (nk + kBM - 1) / kBM;
-    ScopedKernel timed("bwd_dkdv_f16_sm100", stream);
+    ScopedKernel timed(CL ? "bwd_dkdv_f16_sm100_cl" : "bwd_dkdv_f16_sm100", stream);
     kern<<<unsigned(int64_t(p.n_blocks) * p.batch), kBwdThreads, DkvCfg<D, VD>::kSmemBytes, stream>>>(p);
     return cudaGetLastError();
   }
@@ -2033,8 +2126,9 @@ static size_t al256b(size_t v) { return (v + 255) & ~size_t(255); }
 BwdLayout bwd_layout(const LaunchArgs& a) {
   BwdLayout w{};
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
-  w.pack_q = (nq % 8) != 0;
-  w.pack_k = (nk % 8) != 0;
+  // channel-last: the sequence is an outer dimension of the tensor maps - no pitch constraint, nothing to pack
+  w.pack_q = a.layout == 0 && (nq % 8) != 0;
+  w.pack_k = a.layout == 0 && (nk % 8) != 0;
   const int64_t qp = pad8b(nq), kp = pad8b(nk);
   size_t off = stats_bytes(a.batch, nq);
   auto take = [&off](size_t n) { size_t o = off; off += al256b(n); return o; };
@@ -2061,7 +2155,13 @@ static bool aligned16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) &
 
 bool sm100_f16_backward_supports(const LaunchArgs& a) {
   if (a.dtype != 0) return false;
-  if (a.layout != 0) return false;
+  if (a.layout == 1) {
+    if (a.heads < 1 || a.batch % a.heads) return false;
+    if (a.d % 8 || a.v_d % 8) return false;   // strides of the 4-D tensor maps are multiples of 16 bytes
+    if (!aligned16b(a.o)) return false;        // the statistics pass reads O, dO in 16-byte chunks
+  } else if (a.layout != 0) {
+    return false;
+  }
   if (a.d < 1 || a.v_d < 1 || a.d > 128 || a.v_d > 128) return false;
   const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
   const sm100::BwdLayout w = sm100::bwd_layout(a);
@@ -2078,12 +2178,16 @@ bool sm100_f16_backward_supports(const LaunchArgs& a) {
 
 size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) { return sm100::bwd_layout(a).total; }
 
-static cudaError_t backward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+template <bool CL>
+static cudaError_t backward_dispatch_layout(const LaunchArgs& a, cudaStream_t stream) {
   const bool d_small = a.d <= 64, v_small = a.v_d <= 64;
-  if (!d_small && !v_small) return sm100::launch_bwd<128, 128>(a, stream);
-  if (d_small && v_small) return sm100::launch_bwd<64, 64>(a, stream);
-  if (!d_small) return sm100::launch_bwd<128, 64>(a, stream);
-  return sm100::launch_bwd<64, 128>(a, stream);
+  if (!d_small && !v_small) return sm100::launch_bwd<128, 128, CL>(a, stream);
+  if (d_small && v_small) return sm100::launch_bwd<64, 64, CL>(a, stream);
+  if (!d_small) return sm100::launch_bwd<128, 64, CL>(a, stream);
+  return sm100::launch_bwd<64, 128, CL>(a, stream);
+}
+static cudaError_t backward_dispatch(const LaunchArgs& a, cudaStream_t stream) {
+  return a.layout == 1 ? backward_dispatch_layout<true>(a, stream) : backward_dispatch_layout<false>(a, stream);
 }
 
 cudaError_t sm100_f16_backward(const LaunchArgs& a0, cudaStream_t stream) {

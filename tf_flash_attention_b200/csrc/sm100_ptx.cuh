@@ -370,5 +370,72 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+
+// ---- tiles of channel-first / channel-last tensors (the CL switch of the fp16 kernels) -------------------------------
+// which batch element a CTA works on: channel-first tensors index it directly, channel-last ones by (outer, head)
+struct BatchCoord {
+  int b, head, outer;
+};
+template <bool CL>
+__device__ __forceinline__ BatchCoord batch_coord(int b, int heads) {
+  BatchCoord c;
+  c.b = b;
+  c.head = CL ? b % heads : 0;
+  c.outer = CL ? b / heads : b;
+  return c;
+}
+// TMA load of a tile of R positions (a multiple of 64) x C channels (64 or 128) starting at position pos0
+template <bool CL>
+__device__ __forceinline__ void tile_load(uint32_t dst, const void* map, uint32_t bar, int pos0, int R, int C,
+                                          const BatchCoord& bc) {
+  if constexpr (CL) {
+    for (int c = 0; c < C / 64; ++c) tma_load_cl(dst + c * (R * 128), map, bar, c * 64, bc.head, pos0, bc.outer);
+  } else {
+    for (int h = 0; h < R / 64; ++h) tma_load_bc(dst + h * (C * 128), map, bar, pos0 + h * 64, bc.b);
+  }
+}
+// TMA store of a staged tile (stage_row32 layout); n = the tensor's sequence length
+template <bool CL>
+__device__ __forceinline__ void tile_store(const void* map, uint32_t src, int pos0, int R, int C, int n,
+                                           const BatchCoord& bc) {
+  if constexpr (CL) {
+    for (int c = 0; c < C / 64; ++c) tma_store_cl(map, src + c * (R * 128), c * 64, bc.head, pos0, bc.outer);
+  } else {
+    for (int h = 0; h < R / 64; ++h)
+      if (pos0 + h * 64 < n) tma_store_bc(map, src + h * (C * 128), pos0 + h * 64, bc.b);
+  }
+}
+// One thread owns row r of an output tile and stages channels [c0, c0 + 32) = v[0..32) * scale as fp16.
+// channel-first: [C][64] per 64 positions, unswizzled (lanes = consecutive positions: conflict-free 2-byte stores);
+// channel-last: slabs of 64 channels, rows of 128 bytes with TMA's 128-byte swizzle (16-byte stores, conflict-free)
+template <bool CL>
+__device__ __forceinline__ void stage_row32(uint8_t* tile, int r, int c0, int R, int C, const float* v, float scale) {
+  if constexpr (CL) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 8) {
+      uint4 w;
+      w.x = pack_half2(v[e] * scale, v[e + 1] * scale);
+      w.y = pack_half2(v[e + 2] * scale, v[e + 3] * scale);
+      w.z = pack_half2(v[e + 4] * scale, v[e + 5] * scale);
+      w.w = pack_half2(v[e + 6] * scale, v[e + 7] * scale);
+      *reinterpret_cast<uint4*>(tile + cl_chunk_offset(r, c0 + e, R)) = w;
+    }
+  } else {
+    __half* h = reinterpret_cast<__half*>(tile) + (r >> 6) * (C * 64) + (r & 63);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) h[(c0 + e) * 64] = __float2half_rn(v[e] * scale);
+  }
+}
+template <bool CL>
+__device__ __forceinline__ void stage_row_zero(uint8_t* tile, int r, int c_begin, int c_end, int R, int C) {
+  if constexpr (CL) {
+    for (int c = c_begin; c < c_end; c += 8)
+      *reinterpret_cast<uint4*>(tile + cl_chunk_offset(r, c, R)) = make_uint4(0, 0, 0, 0);
+  } else {
+    __half* h = reinterpret_cast<__half*>(tile) + (r >> 6) * (C * 64) + (r & 63);
+    for (int c = c_begin; c < c_end; ++c) h[c * 64] = __float2half_rn(0.f);
+  }
+}
+
 }  // namespace ptx
 }  // namespace fa
