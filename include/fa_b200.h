@@ -283,6 +283,31 @@ int fa_ring_recv_wait(fa_ring_t* ring, int32_t slot, void* stream);
 int fa_ring_recv_release(fa_ring_t* ring, int32_t slot, void* stream);
 int fa_ring_destroy(fa_ring_t* ring);
 
+/* ---- K/V ring driver: causal_1d forward / backward of one sequence sharded zig-zag over the ring's ranks (rank r of G
+ * holds chunks r and 2G-1-r of 2G chunks of `chunk` positions), as one call per rank on one stream. All tensors are
+ * chunk-major: q2, k2, dq2, dk2 [2, batch, d, chunk]; v2, o2, do2, dv2 [2, batch, v_d, chunk]; l2, m2 [2, batch, chunk]
+ * (index 0 = chunk r, 1 = chunk 2G-1-r). Per ring step: one fa_forward / fa_backward launch over both local query
+ * chunks (step 0: both diagonal blocks as one causal launch plus Q_hi x K_lo; later steps: two full blocks), results
+ * folded with fa_partial_merge / fa_grad_accumulate, the K/V shard of the step travelling to rank+1 on the copy
+ * engines while it is being used; in the backward the fp32 dK / dV accumulators travel one hop behind their shard
+ * through `acc_ring` and are home after G hops. Every rank makes the same call; nothing synchronises with the host.
+ *   kv_ring : slots >= fa_ring_causal_slot_bytes(.., 0), >= 2 slots; NULL = a single rank (world 1)
+ *   acc_ring: backward only, slots >= fa_ring_causal_slot_bytes(.., 1)
+ *   arena   : device scratch, 256-byte aligned, >= fa_ring_causal_arena_bytes(.., world, backward)
+ * Gradients are made with the FINAL o2, l2, m2 that fa_ring_causal_forward returned. The Python mirror of the same
+ * schedule (ring.py: ring_forward_causal / ring_backward_causal) is what the gloo tests pin against the oracle.    */
+size_t fa_ring_causal_arena_bytes(int32_t dtype, int64_t batch, int32_t d, int32_t v_d, int32_t chunk, int32_t world,
+                                  int32_t backward);
+size_t fa_ring_causal_slot_bytes(int32_t dtype, int64_t batch, int32_t d, int32_t v_d, int32_t chunk,
+                                 int32_t accumulators);
+int fa_ring_causal_forward(fa_ring_t* kv_ring, int32_t dtype, int64_t batch, int32_t d, int32_t v_d, int32_t chunk,
+                           const void* q2, const void* k2, const void* v2, void* o2, void* l2, void* m2, void* arena,
+                           size_t arena_bytes, void* stream);
+int fa_ring_causal_backward(fa_ring_t* kv_ring, fa_ring_t* acc_ring, int32_t dtype, int64_t batch, int32_t d,
+                            int32_t v_d, int32_t chunk, const void* q2, const void* k2, const void* v2, const void* o2,
+                            const void* l2, const void* m2, const void* do2, void* dq2, void* dk2, void* dv2,
+                            void* arena, size_t arena_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -191,6 +191,34 @@ def test_python_api_surface_matches_reference():
     assert inspect.signature(fa.causal_1d).parameters["sync_mode"].default is inspect.Parameter.empty
 
 
+def test_ring_driver_argument_checks():
+    """fa_ring_causal_forward / _backward / arena sizes (include/fa_b200.h): validated before anything is queued."""
+    lib = _capi.lib
+    one = 256
+    assert lib.fa_ring_causal_arena_bytes(9, 4, 64, 64, 128, 1, 0) == 0
+    assert lib.fa_ring_causal_arena_bytes(_capi.FA_F16, 0, 64, 64, 128, 1, 0) == 0
+    fwd1 = lib.fa_ring_causal_arena_bytes(_capi.FA_F16, 4, 64, 64, 128, 1, 0)
+    fwd2 = lib.fa_ring_causal_arena_bytes(_capi.FA_F16, 4, 64, 64, 128, 2, 0)
+    acc = 2 * 4 * 128 * (64 + 2) * 4                 # fp32 O, l, m accumulators of both local chunks
+    part = 2 * 4 * 128 * (64 * 2 + 4 + 2)            # the step's own O, l, m
+    assert fwd1 >= acc + part
+    assert fwd2 >= fwd1 + 3 * 2 * 4 * 64 * 128 * 2   # + [Q_hi; Q_hi], [K_lo; K_lo], [V_lo; V_lo]
+    bwd2 = lib.fa_ring_causal_arena_bytes(_capi.FA_F16, 4, 64, 64, 128, 2, 1)
+    assert bwd2 >= 3 * 2 * 4 * 64 * 128 * 4 + 3 * 2 * 4 * 64 * 128 * 2
+    assert lib.fa_ring_causal_slot_bytes(_capi.FA_F16, 4, 64, 32, 128, 0) == 2 * 4 * 128 * (64 + 32) * 2
+    assert lib.fa_ring_causal_slot_bytes(_capi.FA_F16, 4, 64, 32, 128, 1) == 2 * 4 * 128 * (64 + 32) * 4
+    f = lambda dtype=_capi.FA_F16, q=one, arena=one, nbytes=fwd1: lib.fa_ring_causal_forward(  # noqa: E731
+        None, dtype, 4, 64, 64, 128, q, one, one, one, one, one, arena, nbytes, None)
+    assert f(dtype=5) == _capi.FA_EINVAL_DTYPE
+    assert f(q=None) == _capi.FA_EINVAL_NULL
+    assert f(arena=None) == _capi.FA_EINVAL_NULL
+    assert f(nbytes=fwd1 - 1) == _capi.FA_EINVAL_WORKSPACE
+    assert f(arena=one + 16) == _capi.FA_EINVAL_WORKSPACE          # arena must be 256-byte aligned
+    b = lib.fa_ring_causal_backward(None, None, _capi.FA_F16, 4, 64, 64, 128, one, one, one, one, one, one, one, one, one,
+                                    None, one, 1 << 30, None)
+    assert b == _capi.FA_EINVAL_NULL
+
+
 def test_channel_last_problem_validation():
     """fa_problem_t.layout / heads (include/fa_b200.h): validated on the host before any launch; a dtype no kernel
     reads channel-last answers FA_EINVAL_LAYOUT so the caller can run the adapter (fa_layout_transpose) instead."""

@@ -13,9 +13,17 @@ torch = pytest.importorskip("torch")
 from tf_flash_attention_b200 import _capi, ring  # noqa: E402
 
 
+@pytest.fixture(params=["native", "python"])
+def driver(request, monkeypatch):
+    """Both drivers of the same schedule: fa_ring_causal_forward / _backward (csrc/fa_ring.cu, the default) and the
+    Python loops of ring.py."""
+    monkeypatch.setenv("FA_RING_DRIVER", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("dtype,d,seq,tol", [(np.float16, 128, 2048, 2e-3), (np.float16, 64, 512, 2e-3),
                                               (np.float32, 32, 384, 1e-5), (np.float64, 16, 256, 1e-12)])
-def test_single_rank_ring_equals_plain_causal(dtype, d, seq, tol):
+def test_single_rank_ring_equals_plain_causal(dtype, d, seq, tol, driver):
     rng = np.random.default_rng(3)
     Q, K, V, _ = da.random_inputs(rng, dtype, (2, 2), d, d, (seq,), (seq,))
     ref = da.attention(Q, K, V, 1, "causal", "none_front")
@@ -30,7 +38,7 @@ def test_single_rank_ring_equals_plain_causal(dtype, d, seq, tol):
 @pytest.mark.parametrize("dtype,d,seq,tol", [(np.float16, 128, 2048, 2e-3), (np.float16, 64, 512, 2e-3),
                                               (np.float16, 64, 256, 2e-3),   # 128-key chunks: the precise kernels, on key shards
                                               (np.float32, 32, 384, 1e-5), (np.float64, 16, 256, 1e-12)])
-def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol):
+def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol, driver):
     """ring_backward: blocks computed by fa_backward with global index bases and the final (O, l, m), summed with
     fa_grad_accumulate / fa_grad_finalize. fp16 bar: the plain 2e-3 * max(1, |ref|)."""
     rng = np.random.default_rng(4)
@@ -56,7 +64,9 @@ def test_two_rank_ring_over_the_peer_copy_data_plane():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "ring_check.py")],
-                       capture_output=True, text=True, timeout=600, cwd=root)
-    assert r.returncode == 0 and "RING_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    for drv in ("native", "python"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533",
+                            os.path.join(root, "tools", "ring_check.py")],
+                           capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, FA_RING_DRIVER=drv))
+        assert r.returncode == 0 and "RING_CHECK PASS" in r.stdout, drv + r.stdout[-2000:] + r.stderr[-2000:]

@@ -116,6 +116,11 @@ def _load():
         "fa_ring_recv_wait": (C.c_int, [vp, i32, vp]),
         "fa_ring_recv_release": (C.c_int, [vp, i32, vp]),
         "fa_ring_destroy": (C.c_int, [vp]),
+        "fa_ring_causal_arena_bytes": (sz, [i32, i64, i32, i32, i32, i32, i32]),
+        "fa_ring_causal_slot_bytes": (sz, [i32, i64, i32, i32, i32, i32]),
+        "fa_ring_causal_forward": (C.c_int, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "fa_ring_causal_backward": (C.c_int, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                              vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -580,6 +580,81 @@ def ring_backward(backend, layout, rank, q_chunks, kv_chunks, o_chunks, l_chunks
     return d_q, d_kv
 
 
+class _Template:
+    """Shape / dtype / device of a tensor that travels through a PeerRing slot (no storage of its own)."""
+
+    def __init__(self, shape, dtype, device, element_size):
+        self.shape, self.dtype, self.device, self._es = tuple(shape), dtype, device, element_size
+
+    def numel(self):
+        n = 1
+        for s in self.shape:
+            n *= int(s)
+        return n
+
+    def element_size(self):
+        return self._es
+
+
+_native_arena = {}
+
+
+def _native_driver(backend):
+    """The native ring driver (csrc/fa_ring.cu: fa_ring_causal_forward / _backward) runs the schedule unless
+    FA_RING_DRIVER=python (this module's loops, which the gloo tests pin against the oracle) or the shards are asked to
+    move over NCCL (FA_RING_TRANSPORT=nccl)."""
+    import os
+    return (isinstance(backend, DeviceBackend) and os.environ.get("FA_RING_DRIVER", "native") == "native"
+            and os.environ.get("FA_RING_TRANSPORT", "peer") != "nccl")
+
+
+def _native_setup(backend, rank, world, q2, k2, v2, dist, group, backward):
+    t = backend.torch
+    kv = acc = None
+    if world > 1:
+        kv = PeerRing.get("kv", t, dist, group, rank, world, [k2, v2])
+        if backward:
+            es = 8 if backend.acc_dtype == t.float64 else 4
+            acc = PeerRing.get("acc", t, dist, group, rank, world,
+                               [_Template(k2.shape, backend.acc_dtype, k2.device, es),
+                                _Template(v2.shape, backend.acc_dtype, v2.device, es)])
+    batch = 1
+    for n in q2.shape[1:-2]:
+        batch *= int(n)
+    d, v_d, c = int(q2.shape[-2]), int(v2.shape[-2]), int(q2.shape[-1])
+    need = _capi.lib.fa_ring_causal_arena_bytes(backend.p.dtype, batch, d, v_d, c, world, int(backward))
+    key = (q2.device, int(backward))
+    arena = _native_arena.get(key)
+    if arena is None or arena.numel() < need:
+        arena = t.empty(max(need, 256), dtype=t.uint8, device=q2.device)
+        _native_arena[key] = arena
+    return kv, acc, (backend.p.dtype, batch, d, v_d, c), arena
+
+
+def ring_forward_causal_native(backend, layout, rank, q2, k2, v2, dist=None, group=None):
+    """ring_forward_causal as ONE C-ABI call (fa_ring_causal_forward): same arguments, same result."""
+    kv, _, dims, arena = _native_setup(backend, rank, layout.world, q2, k2, v2, dist, group, False)
+    o, l, m = backend.new_out_like(q2, v2)
+    _capi.check(_capi.lib.fa_ring_causal_forward(kv.handle if kv else None, *dims, q2.data_ptr(), k2.data_ptr(),
+                                                 v2.data_ptr(), o.data_ptr(), l.data_ptr(), m.data_ptr(),
+                                                 arena.data_ptr(), arena.numel(), backend._stream()),
+                "fa_ring_causal_forward")
+    return o, l, m
+
+
+def ring_backward_causal_native(backend, layout, rank, q2, k2, v2, o2, l2, m2, do2, dist=None, group=None):
+    """ring_backward_causal as ONE C-ABI call (fa_ring_causal_backward)."""
+    kv, acc, dims, arena = _native_setup(backend, rank, layout.world, q2, k2, v2, dist, group, True)
+    t = backend.torch
+    dq, dk, dv = t.empty_like(q2), t.empty_like(k2), t.empty_like(v2)
+    _capi.check(_capi.lib.fa_ring_causal_backward(kv.handle if kv else None, acc.handle if acc else None, *dims,
+                                                  q2.data_ptr(), k2.data_ptr(), v2.data_ptr(), o2.data_ptr(),
+                                                  l2.data_ptr(), m2.data_ptr(), do2.data_ptr(), dq.data_ptr(),
+                                                  dk.data_ptr(), dv.data_ptr(), arena.data_ptr(), arena.numel(),
+                                                  backend._stream()), "fa_ring_causal_backward")
+    return dq, dk, dv
+
+
 def _chunk_major(x, c):
     """[..., channels, 2c] (chunk r then chunk 2G-1-r along the sequence) -> [2, ..., channels, c]."""
     import torch
@@ -612,8 +687,8 @@ def ring_causal_1d_backward(Q, K, V, O, l, m, dO, sync_mode="none_front", group=
     O, l, m as returned by ring_causal_1d(..., returning_l_m=True). Returns (dQ, dK, dV) shards."""
     dist, rank, layout, backend = _causal_ring_setup(Q, V, sync_mode, group)
     c = layout.chunk
-    d_q, d_k, d_v = ring_backward_causal(backend, layout, rank, *(_chunk_major(x, c) for x in (Q, K, V, O, l, m, dO)),
-                                         dist, group)
+    run = ring_backward_causal_native if _native_driver(backend) else ring_backward_causal
+    d_q, d_k, d_v = run(backend, layout, rank, *(_chunk_major(x, c) for x in (Q, K, V, O, l, m, dO)), dist, group)
     return _shard_layout(d_q), _shard_layout(d_k), _shard_layout(d_v)
 
 
@@ -623,8 +698,8 @@ def ring_causal_1d(Q, K, V, sync_mode="none_front", group=None, returning_l_m=Fa
     2G-1-r. Returns O (and l, m) in the same sharded layout."""
     dist, rank, layout, backend = _causal_ring_setup(Q, V, sync_mode, group)
     c = layout.chunk
-    O2, l2, m2 = ring_forward_causal(backend, layout, rank, _chunk_major(Q, c), _chunk_major(K, c), _chunk_major(V, c),
-                                     dist, group)
+    run = ring_forward_causal_native if _native_driver(backend) else ring_forward_causal
+    O2, l2, m2 = run(backend, layout, rank, _chunk_major(Q, c), _chunk_major(K, c), _chunk_major(V, c), dist, group)
     if not returning_l_m:
         return _shard_layout(O2)
     return _shard_layout(O2), _shard_layout(l2), _shard_layout(m2)
