@@ -35,7 +35,7 @@ bool make_map_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols,
 
 constexpr int kXM = 128;        // resident rows of a CTA (TMEM lanes)
 constexpr int kXN = 64;         // streamed tile width
-constexpr int kXThreads = 256;  // 4 softmax warps, TMA warp, MMA warp, TMEM warp, spare
+constexpr int kXThreads = 384;  // 2 softmax warpgroups (each takes 32 of a tile's 64 columns), TMA / MMA / TMEM warps, spare
 constexpr int kXStages = 2;
 constexpr int kXStatPad = 64;
 constexpr float kXLog2e = 1.4426950408889634f;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
     const bool valid[1] = {true};
     build_schedule(sched, rule, true, lo, hi, valid, 1, kt_first, kt_last, kXN, p.nk, kXThreads / 32);
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one())
       for (int j = 0; j < 3; ++j) {
         prefetch_tensormap(&p.map_q[j]);
@@ -214,11 +214,11 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
         prefetch_tensormap(&p.map_v[j]);
         prefetch_tensormap(&p.map_do[j]);
       }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       mbar_init(bar_q_full, 1);
       mbar_init(bar_s_full, 1);
-      mbar_init(bar_p_ready, kXM);
+      mbar_init(bar_p_ready, 2 * kXM);
       mbar_init(bar_final, 1);
       for (int s = 0; s < kXStages; ++s) {
         mbar_init(bar_kv_full + 8 * s, 1);
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       }
       fence_barrier_init();
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
   // TMEM columns: S [0, 64)  dP [64, 128)  dQ [128, 192)  dQ small terms [192, 256)  dS pieces [256 + 32 j, +32)
   constexpr uint32_t kColDp = 64, kColDq = 128, kColDqc = 192, kColDs = 256;
 
-  if (warp >= 4) {
-    if (warp == 4) {
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_q_full, Cfg::kResBytes);
         for (int j = 0; j < 3; ++j)
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
           ++t;
         }
       }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
       if (elect_one()) {
         TileIter it;
         it.init(sched, 1, kt_first, kt_last);
@@ -301,8 +302,12 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       }
     }
   } else {
-    const int r = threadIdx.x;                // query row
-    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    setmaxnreg_inc<224>();
+    // both warpgroups work on every tile: warpgroup x takes key columns [32x, 32x + 32) of the row (no row reduction is
+    // needed in the backward), which halves the softmax stretch of the S -> dS -> dQ chain
+    const int x = warp >> 2;
+    const int r = threadIdx.x & 127;          // query row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr;
     const int qi = q0 + r;
     const bool q_valid = qi < p.nq;
@@ -328,31 +333,26 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
       // masks first: nothing that may move registers between tcgen05.ld and tcgen05.wait::ld
-      uint32_t okm[2] = {0xffffffffu, 0xffffffffu};
-      if (cls == FA_TILE_PARTIAL || ragged) {
-        const int nvalid = k_hi - k0 + 1;
-        okm[0] = tile_mask32(rule, true, qpos, k0, 0, nvalid);
-        okm[1] = tile_mask32(rule, true, qpos, k0, 32, nvalid);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      uint32_t okm = 0xffffffffu;
+      if (cls == FA_TILE_PARTIAL || ragged) okm = tile_mask32(rule, true, qpos, k0, 32 * x, k_hi - k0 + 1);
+      {
         float s[32], dp[32];
-        tmem_ld32f(t_s + h * 32, s);
-        tmem_ld32f(t_s + kColDp + h * 32, dp);
+        tmem_ld32f(t_s + x * 32, s);
+        tmem_ld32f(t_s + kColDp + x * 32, dp);
         tmem_wait_ld();
         uint32_t c0[16], c1[16], c2[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float p0 = exp2f(fmaf(s[c], scale_log2, -lse2));
           float p1 = exp2f(fmaf(s[c + 1], scale_log2, -lse2));
-          p0 = (okm[h] >> c) & 1u ? p0 : 0.f;
-          p1 = (okm[h] >> (c + 1)) & 1u ? p1 : 0.f;
+          p0 = (okm >> c) & 1u ? p0 : 0.f;
+          p1 = (okm >> (c + 1)) & 1u ? p1 : 0.f;
           row_sum += p0 + p1;
           split3_pack(p0 * (dp[c] - dsum), p1 * (dp[c + 1] - dsum), c0[c >> 1], c1[c >> 1], c2[c >> 1]);
         }
-        tmem_st16(t_s + kColDs + h * 16, c0);
-        tmem_st16(t_s + kColDs + 32 + h * 16, c1);
-        tmem_st16(t_s + kColDs + 64 + h * 16, c2);
+        tmem_st16(t_s + kColDs + x * 16, c0);
+        tmem_st16(t_s + kColDs + 32 + x * 16, c1);
+        tmem_st16(t_s + kColDs + 64 + x * 16, c2);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -361,15 +361,21 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
     }
     // epilogue: dQ = scale * acc, fp32, straight to global (lanes = consecutive queries -> coalesced per channel)
     float* out = p.d_q + int64_t(b) * p.d * p.nq + qi;
+    {
+      // the two halves of the row sum meet in shared memory (the statistics staging area is unused by this kernel)
+      float* halves = reinterpret_cast<float*>(smem_gen + Cfg::kStatOffset);
+      halves[x * kXM + r] = row_sum;
+      named_bar_sync(1, 2 * kXM);
+      row_sum = halves[r] + halves[kXM + r];
+    }
     const float out_scale = !p.renormalise ? p.scale : (row_sum > 0.f ? p.scale / row_sum : 0.f);
-    if (q_valid)
+    if (q_valid && x == 0)
       p.lse2_refined[int64_t(b) * p.stat_pitch + qi] =
           !p.renormalise ? lse2 : (row_sum > 0.f ? lse2 + log2f(row_sum) : __int_as_float(0x7f800000));
     if (j > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < (D + 31) / 32; ++c) {
+      for (int c = x; c < (D + 31) / 32; c += 2) {   // the warpgroups share the channel chunks
         float o[32], oc[32];
         tmem_ld32f(t_s + kColDq + c * 32, o);
         tmem_ld32f(t_s + kColDqc + c * 32, oc);
@@ -380,13 +386,13 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dq_f32_kernel(const __grid_c
             if (c * 32 + e < p.d) out[int64_t(c * 32 + e) * p.nq] = (o[e] + oc[e]) * out_scale;
         }
       }
-    } else if (q_valid) {
+    } else if (q_valid && x == 0) {
       for (int c = 0; c < p.d; ++c) out[int64_t(c) * p.nq] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
     const bool valid[1] = {true};
     build_schedule(sched, rule, false, lo, hi, valid, 1, qt_first, qt_last, kXN, p.nq, kXThreads / 32);
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one())
       for (int j = 0; j < 3; ++j) {
         prefetch_tensormap(&p.map_q[j]);
@@ -440,11 +446,11 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         prefetch_tensormap(&p.map_v[j]);
         prefetch_tensormap(&p.map_do[j]);
       }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       mbar_init(bar_kv_res, 1);
       mbar_init(bar_s_full, 1);
-      mbar_init(bar_p_ready, kXM);
+      mbar_init(bar_p_ready, 2 * kXM);
       mbar_init(bar_final, 1);
       for (int s = 0; s < kXStages; ++s) {
         mbar_init(bar_full + 8 * s, 1);
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
       }
       fence_barrier_init();
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -468,8 +474,9 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
   // the bias reached 2.7e-5 after 16 tiles; the leading products alone add 6x less often.
   constexpr uint32_t kColDp = 64, kColP = 0, kColDs = 96, kColDv = 192, kColDk = 256, kColDvc = 320, kColDkc = 384;
 
-  if (warp >= 4) {
-    if (warp == 4) {
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();
+    if (warp == 8) {
       if (elect_one()) {
         mbar_arrive_expect_tx(bar_kv_res, Cfg::kResBytes);
         for (int j = 0; j < 3; ++j)
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
           ++t;
         }
       }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
       if (elect_one()) {
         TileIter it;
         it.init(sched, 1, qt_first, qt_last);
@@ -536,8 +543,10 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
       }
     }
   } else {
-    const int r = threadIdx.x;                // key row
-    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    setmaxnreg_inc<224>();
+    const int x = warp >> 2;                  // query-column half in the main loop; dV / dK role in the epilogue
+    const int r = threadIdx.x & 127;          // key row
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr;
     const int ki = k0 + r;
     const bool k_valid = ki < p.nk;
@@ -556,42 +565,34 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
       mbar_wait(bar_full + 8 * st, (t / kXStages) & 1);   // statistics visible to this thread
       mbar_wait(bar_s_full, t & 1);
       tc_fence_after();
-      uint32_t okm[2] = {0xffffffffu, 0xffffffffu};
-      if (cls == FA_TILE_PARTIAL || ragged) {
-        okm[0] = okm[1] = 0u;
-        if (k_valid) {
-          const int nvalid = q_hi - q0 + 1;
-          okm[0] = tile_mask32(rule, false, kpos, q0, 0, nvalid);
-          okm[1] = tile_mask32(rule, false, kpos, q0, 32, nvalid);
-        }
-      }
-      const float* lse_s = stat_gen + st * (2 * kXN);
+      uint32_t okm = 0xffffffffu;
+      if (cls == FA_TILE_PARTIAL || ragged)
+        okm = k_valid ? tile_mask32(rule, false, kpos, q0, 32 * x, q_hi - q0 + 1) : 0u;
+      const float* lse_s = stat_gen + st * (2 * kXN) + x * 32;
       const float* dsum_s = lse_s + kXN;
-      float s[64], dp[64];
-      tmem_ld32f(t_s, &s[0]);
-      tmem_ld32f(t_s + 32, &s[32]);
-      tmem_ld32f(t_s + kColDp, &dp[0]);
-      tmem_ld32f(t_s + kColDp + 32, &dp[32]);
+      float s[32], dp[32];
+      tmem_ld32f(t_s + x * 32, s);
+      tmem_ld32f(t_s + kColDp + x * 32, dp);
       tmem_wait_ld();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      // the pieces overwrite S^T / dP^T columns of BOTH halves: nobody stores before both warpgroups have loaded
+      named_bar_sync(1, 2 * kXM);
+      {
         uint32_t a0[16], a1[16], a2[16], c0[16], c1[16], c2[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          float p0 = exp2f(fmaf(s[h * 32 + c], scale_log2, -lse_s[h * 32 + c]));
-          float p1 = exp2f(fmaf(s[h * 32 + c + 1], scale_log2, -lse_s[h * 32 + c + 1]));
-          p0 = (okm[h] >> c) & 1u ? p0 : 0.f;
-          p1 = (okm[h] >> (c + 1)) & 1u ? p1 : 0.f;
+          float p0 = exp2f(fmaf(s[c], scale_log2, -lse_s[c]));
+          float p1 = exp2f(fmaf(s[c + 1], scale_log2, -lse_s[c + 1]));
+          p0 = (okm >> c) & 1u ? p0 : 0.f;
+          p1 = (okm >> (c + 1)) & 1u ? p1 : 0.f;
           split3_pack(p0, p1, a0[c >> 1], a1[c >> 1], a2[c >> 1]);
-          split3_pack(p0 * (dp[h * 32 + c] - dsum_s[h * 32 + c]), p1 * (dp[h * 32 + c + 1] - dsum_s[h * 32 + c + 1]),
-                      c0[c >> 1], c1[c >> 1], c2[c >> 1]);
+          split3_pack(p0 * (dp[c] - dsum_s[c]), p1 * (dp[c + 1] - dsum_s[c + 1]), c0[c >> 1], c1[c >> 1], c2[c >> 1]);
         }
-        tmem_st16(t_s + kColP + h * 16, a0);
-        tmem_st16(t_s + kColP + 32 + h * 16, a1);
-        tmem_st16(t_s + kColP + 64 + h * 16, a2);
-        tmem_st16(t_s + kColDs + h * 16, c0);
-        tmem_st16(t_s + kColDs + 32 + h * 16, c1);
-        tmem_st16(t_s + kColDs + 64 + h * 16, c2);
+        tmem_st16(t_s + kColP + x * 16, a0);
+        tmem_st16(t_s + kColP + 32 + x * 16, a1);
+        tmem_st16(t_s + kColP + 64 + x * 16, a2);
+        tmem_st16(t_s + kColDs + x * 16, c0);
+        tmem_st16(t_s + kColDs + 32 + x * 16, c1);
+        tmem_st16(t_s + kColDs + 64 + x * 16, c2);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -601,11 +602,12 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
     // epilogue: dV, dK = scale * acc in fp32, straight to global (lanes = consecutive keys -> coalesced per channel)
     float* out_v = p.d_v + int64_t(b) * p.v_d * p.nk + ki;
     float* out_k = p.d_k + int64_t(b) * p.d * p.nk + ki;
+    // warpgroup 0 writes dV, warpgroup 1 dK
     if (t > 0) {
       mbar_wait(bar_final, 0);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < (VD + 31) / 32; ++c) {
+      for (int c = 0; c < (x == 0 ? (VD + 31) / 32 : 0); ++c) {
         float o[32], oc[32];
         tmem_ld32f(t_s + kColDv + c * 32, o);
         tmem_ld32f(t_s + kColDvc + c * 32, oc);
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         }
       }
 #pragma unroll
-      for (int c = 0; c < (D + 31) / 32; ++c) {
+      for (int c = 0; c < (x == 1 ? (D + 31) / 32 : 0); ++c) {
         float o[32], oc[32];
         tmem_ld32f(t_s + kColDk + c * 32, o);
         tmem_ld32f(t_s + kColDkc + c * 32, oc);
@@ -629,13 +631,15 @@ __global__ void __launch_bounds__(kXThreads, 1) bwd_dkdv_f32_kernel(const __grid
         }
       }
     } else if (k_valid) {
-      for (int c = 0; c < p.v_d; ++c) out_v[int64_t(c) * p.nk] = 0.f;
-      for (int c = 0; c < p.d; ++c) out_k[int64_t(c) * p.nk] = 0.f;
+      if (x == 0)
+        for (int c = 0; c < p.v_d; ++c) out_v[int64_t(c) * p.nk] = 0.f;
+      else
+        for (int c = 0; c < p.d; ++c) out_k[int64_t(c) * p.nk] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
