@@ -37,6 +37,10 @@ WORKLOADS = {
     "C2": dict(desc="causal_1d fp16 fwd+bwd, batch*heads 16x16, head_dim 128, seq 8192", seq_dims=1,
                dtype="float16", batch=(16, 16), d=128, v_d=128, q=(8192,), k=(8192,), rule="causal",
                sync="none_front", w=1, s=0, c=0),
+    # C2 with channel-last tensors [16, 8192, 16, 128] read / written directly by the kernels
+    "C2cl": dict(desc="causal_1d fp16 fwd+bwd, channel-last tensors [16, 8192, 16 heads, 128] read directly, seq 8192",
+                 seq_dims=1, dtype="float16", batch=(16, 16), d=128, v_d=128, q=(8192,), k=(8192,), rule="causal",
+                 sync="none_front", w=1, s=0, c=0, channel_last_heads=16),
     "C1": dict(desc="local_1d fp32 README example Q[8,32,1024] K[8,32,2048] V[8,16,2048] w32 s0 scale_front",
                seq_dims=1, dtype="float32", batch=(8,), d=32, v_d=16, q=(1024,), k=(2048,), rule="local",
                sync="scale_front", w=32, s=0, c=0),
@@ -233,7 +237,8 @@ def ring_bench(args, w, nnz, config, rank, world, local_rank):
     value = fwd_flops / (ms * 1e-3) / 1e12
     peaks = measured_peaks()
     peak = (peaks["tensor_sustained"] or peaks["tensor_burst"]) * world
-    config = dict(config, flops_per_step=fwd_flops, parallelism=f"K/V ring, zig-zag chunks, {world} rank(s), NCCL send/recv")
+    config = dict(config, flops_per_step=fwd_flops, parallelism=f"K/V ring, zig-zag chunks, {world} rank(s), shards on the copy engines (fa_ring peer copies), "
+                  f"{os.environ.get('FA_RING_DRIVER', 'native')} driver")
     config["pass"] = "fwd+bwd" if args.ring_bwd else "fwd"
     line = {"metric": f"attention {config['pass']} TFLOPS (unmasked FLOPs), single sequence K/V ring", "value": value, "unit": "TFLOPS",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
@@ -390,6 +395,12 @@ def main():
     prob = _capi.make_problem(code, w["seq_dims"], w["rule"], w["sync"], bshape + (w["d"],) + w["q"],
                               bshape + (w["d"],) + w["k"], bshape + (w["v_d"],) + w["k"], w["w"], w["s"], w["c"])
     assert _capi.count_attended(prob) == nnz, "attended-pair count of the library differs from the host count"
+    if w.get("channel_last_heads"):
+        # same element counts, the kernels address them as [outer, seq, heads, channels]; l, m stay [batch, q]
+        assert local_units % w["channel_last_heads"] == 0
+        prob.layout, prob.heads = _capi.FA_LAYOUT_CHANNEL_LAST, w["channel_last_heads"]
+        args.no_e2e = True        # the host-buffer entry points take the reference's channel-first layout only
+        args.no_refkernel = True
 
     # ---------------- our arm -------------------------------------------------------------------
     import torch

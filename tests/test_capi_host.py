@@ -238,6 +238,10 @@ def test_channel_last_problem_validation():
     p32.layout, p32.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 3
     ws = _capi.lib.fa_workspace_bytes(C.byref(p32), 0)
     assert _capi.lib.fa_forward(C.byref(p32), one, one, one, one, one, one, one, ws, None) == _capi.FA_EINVAL_LAYOUT
+    # the host-buffer entry points chunk the batch: channel-first only
+    p.heads = 3
+    assert _capi.lib.fa_host_arena_bytes(C.byref(p), 0) == 0
+    assert _capi.lib.fa_forward_host(C.byref(p), one, one, one, one, one, one, one, 1 << 30, None) == _capi.FA_EINVAL_LAYOUT
     # python side: shapes are outer + sequence + (heads, channels)
     from tf_flash_attention_b200.flash_attention import _cf_shape
     assert _cf_shape((2, 100, 3, 64), 1) == (2, 3, 64, 100)

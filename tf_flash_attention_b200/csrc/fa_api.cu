@@ -583,6 +583,9 @@ int arena_layout(const fa_problem_t* p, int bwd, Arena* a) {
   FaRule r;
   int rc = make_rule(p, &r);
   if (rc) return rc;
+  // the host pipelines cut the batch into contiguous chunks: only the reference's channel-first layout is contiguous
+  // per batch element
+  if (p->layout != FA_LAYOUT_CHANNEL_FIRST) return FA_EINVAL_LAYOUT;
   const size_t e = elt(p->dtype), b = size_t(p->batch);
   a->nq_b = e * b * p->d * r.q.total;
   a->nk_b = e * b * p->d * r.k.total;

@@ -81,6 +81,25 @@ struct FwdSmem {
   static constexpr int kBytes = kDoubles * 8;
 };
 
+// Classes of 32 consecutive streamed tiles, one per lane, kept as two ballots per warp: fa_classify (two fa_box
+// evaluations with integer divisions) costs as much as the DMMAs of a 32-wide tile when every thread repeats it per
+// tile; the tile index is uniform over the CTA, so a warp classifies 32 tiles at once and looks the rest up.
+struct WarpTileClass {
+  uint32_t partial = 0, full = 0;
+  int base = -(1 << 30);
+  template <typename Classify>
+  __device__ __forceinline__ int get(int tile, Classify&& classify) {
+    if (tile < base || tile >= base + 32) {   // warp-uniform
+      base = tile;
+      const int c = classify(tile + int(threadIdx.x & 31));
+      partial = __ballot_sync(0xffffffffu, c == FA_TILE_PARTIAL);
+      full = __ballot_sync(0xffffffffu, c == FA_TILE_FULL);
+    }
+    const int b = tile - base;
+    return ((full >> b) & 1u) ? FA_TILE_FULL : ((partial >> b) & 1u) ? FA_TILE_PARTIAL : FA_TILE_SKIP;
+  }
+};
+
 template <int DP, int VP, int MT>
 __global__ void __launch_bounds__(threads_of(MT), 2) fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -126,8 +145,12 @@ __global__ void __launch_bounds__(threads_of(MT), 2) fwd_kernel(const FwdParams 
   const double* vg = p.v + b * p.v_d * int64_t(p.nk);
   int kt_first, kt_last;
   fa_k_tile_range(rule, q0, q_hi, kTile, &kt_first, &kt_last);
+  WarpTileClass tile_cls;
+  auto classify = [&](int kt) {   // beyond the last tile: SKIP
+    return kt * kTile < p.nk ? fa_classify(rule, q0, q_hi, kt * kTile, min(kt * kTile + kTile, p.nk) - 1) : int(FA_TILE_SKIP);
+  };
   auto next_live = [&](int kt) {   // first tile >= kt that is not skipped (kt_last + 1 if none)
-    while (kt <= kt_last && fa_classify(rule, q0, q_hi, kt * kTile, min(kt * kTile + kTile, p.nk) - 1) == FA_TILE_SKIP) ++kt;
+    while (kt <= kt_last && tile_cls.get(kt, classify) == FA_TILE_SKIP) ++kt;
     return kt;
   };
   auto issue = [&](int kt, int stage) {
@@ -139,6 +162,7 @@ __global__ void __launch_bounds__(threads_of(MT), 2) fwd_kernel(const FwdParams 
   int kt = next_live(kt_first), stage = 0;
   if (kt <= kt_last) issue(kt, 0);
   while (kt <= kt_last) {
+    const int cls = tile_cls.get(kt, classify);   // before the look-ahead moves the 32-tile window
     const int kn = next_live(kt + 1);
     if (kn <= kt_last) {
       issue(kn, stage ^ 1);
@@ -150,7 +174,6 @@ __global__ void __launch_bounds__(threads_of(MT), 2) fwd_kernel(const FwdParams 
     const double* Ks = sm + stage * FwdSmem<DP, VP>::kStage;
     const double* Vs = Ks + DP * kPitch;
     const int k0 = kt * kTile;
-    const int cls = fa_classify(rule, q0, q_hi, k0, min(k0 + kTile, p.nk) - 1);
 
     // S = (Q scale) K^T : 2 m-tiles x 4 n-tiles
     double s[MT][4][2];
@@ -291,8 +314,16 @@ struct BwdParams {
 
 __global__ void bwd_prep_kernel(const double* __restrict__ o, const double* __restrict__ d_o,
                                 const double* __restrict__ l, const double* __restrict__ m, double* __restrict__ lse,
-                                double* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq) {
+                                double* __restrict__ dsum, int64_t batch, int32_t v_d, int32_t nq, double* zero0,
+                                int64_t n0, double* zero1, int64_t n1, double* zero2, int64_t n2) {
   const int64_t total = batch * nq;
+  // outputs that the split grids add into with atomics are cleared here (this launch precedes them anyway), not by
+  // three memset nodes of their own
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n0 + n1 + n2; i += int64_t(gridDim.x) * blockDim.x) {
+    if (i < n0) zero0[i] = 0.0;
+    else if (i < n0 + n1) zero1[i - n0] = 0.0;
+    else zero2[i - n0 - n1] = 0.0;
+  }
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t b = i / nq, r = i - b * nq;
     const double* op = o + b * v_d * int64_t(nq) + r;
@@ -373,8 +404,12 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdPara
   int kt_first, kt_last;
   fa_k_tile_range(rule, q0, q_hi, kTile, &kt_first, &kt_last);
   split_range(&kt_first, &kt_last);   // small grids: the streamed range is shared out over gridDim.y CTAs
+  WarpTileClass tile_cls;
+  auto classify = [&](int kt) {   // beyond the last tile: SKIP
+    return kt * kTile < p.nk ? fa_classify(rule, q0, q_hi, kt * kTile, min(kt * kTile + kTile, p.nk) - 1) : int(FA_TILE_SKIP);
+  };
   auto next_live = [&](int kt) {
-    while (kt <= kt_last && fa_classify(rule, q0, q_hi, kt * kTile, min(kt * kTile + kTile, p.nk) - 1) == FA_TILE_SKIP) ++kt;
+    while (kt <= kt_last && tile_cls.get(kt, classify) == FA_TILE_SKIP) ++kt;
     return kt;
   };
   auto issue = [&](int kt, int stage) {
@@ -386,6 +421,7 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdPara
   int kt = next_live(kt_first), stage = 0;
   if (kt <= kt_last) issue(kt, 0);
   while (kt <= kt_last) {
+    const int cls = tile_cls.get(kt, classify);   // before the look-ahead moves the 32-tile window
     const int kn = next_live(kt + 1);
     if (kn <= kt_last) {
       issue(kn, stage ^ 1);
@@ -397,7 +433,6 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dq_kernel(const BwdPara
     const double* Ks = ring + stage * BwdSmem<DP, VP>::kStage;
     const double* Vs = Ks + DP * kPitch;
     const int k0 = kt * kTile;
-    const int cls = fa_classify(rule, q0, q_hi, k0, min(k0 + kTile, p.nk) - 1);
     double s[MT][4][2], dp[MT][4][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -507,8 +542,12 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdPa
   int qt_first, qt_last;
   fa_q_tile_range(rule, k0, k_hi, kTile, &qt_first, &qt_last);
   split_range(&qt_first, &qt_last);
+  WarpTileClass tile_cls;
+  auto classify = [&](int qt) {   // beyond the last tile: SKIP
+    return qt * kTile < p.nq ? fa_classify(rule, qt * kTile, min(qt * kTile + kTile, p.nq) - 1, k0, k_hi) : int(FA_TILE_SKIP);
+  };
   auto next_live = [&](int qt) {
-    while (qt <= qt_last && fa_classify(rule, qt * kTile, min(qt * kTile + kTile, p.nq) - 1, k0, k_hi) == FA_TILE_SKIP) ++qt;
+    while (qt <= qt_last && tile_cls.get(qt, classify) == FA_TILE_SKIP) ++qt;
     return qt;
   };
   auto issue = [&](int qt, int stage) {
@@ -526,6 +565,7 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdPa
   int qt = next_live(qt_first), stage = 0;
   if (qt <= qt_last) issue(qt, 0);
   while (qt <= qt_last) {
+    const int cls = tile_cls.get(qt, classify);   // before the look-ahead moves the 32-tile window
     const int qn = next_live(qt + 1);
     if (qn <= qt_last) {
       issue(qn, stage ^ 1);
@@ -539,7 +579,6 @@ __global__ void __launch_bounds__(threads_of(MT), 1) bwd_dkdv_kernel(const BwdPa
     const double* lse = stats + stage * 2 * kTile;
     const double* dsum = lse + kTile;
     const int q0 = qt * kTile;
-    const int cls = fa_classify(rule, q0, min(q0 + kTile, p.nq) - 1, k0, k_hi);
     // S^T = (K scale) Q^T, dP^T = V dO^T : rows = keys, columns = queries
     double s[MT][4][2], dp[MT][4][2];
 #pragma unroll
@@ -648,43 +687,42 @@ static cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
   double* dsum = lse + p.batch * p.nq;
   p.lse = lse;
   p.dsum = dsum;
-  {
-    const int64_t total = p.batch * p.nq;
-    const int blocks = int(std::min<int64_t>((total + 255) / 256, 148 * 8));
-    ScopedKernel timed("bwd_prep_f64", stream);
-    bwd_prep_kernel<<<blocks, 256, 0, stream>>>((const double*)a.o, (const double*)a.d_o, (const double*)a.l,
-                                                (const double*)a.m, lse, dsum, p.batch, p.v_d, p.nq);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
   auto splits_for = [](int64_t ctas, int64_t streamed_tiles) {   // 1 unless the grid leaves SMs idle
     int n = 1;
     while (ctas * n < 148 && n < 4 && streamed_tiles / (2 * n) >= 4) n *= 2;
     return n;
   };
+  const int64_t tiles_q = (p.nq + kRows - 1) / kRows, tiles_k = (p.nk + kRows - 1) / kRows;
+  const int ns_q = splits_for(p.batch * tiles_q, (p.nk + kTile - 1) / kTile);
+  const int ns_k = splits_for(p.batch * tiles_k, (p.nq + kTile - 1) / kTile);
+  {
+    const int64_t total = p.batch * p.nq;
+    const int64_t z0 = ns_q > 1 ? p.batch * p.d * int64_t(p.nq) : 0;
+    const int64_t z1 = ns_k > 1 ? p.batch * p.d * int64_t(p.nk) : 0, z2 = ns_k > 1 ? p.batch * p.v_d * int64_t(p.nk) : 0;
+    const int blocks = int(std::min<int64_t>((std::max(total, z0 + z1 + z2) + 255) / 256, 148 * 8));
+    ScopedKernel timed("bwd_prep_f64", stream);
+    bwd_prep_kernel<<<blocks, 256, 0, stream>>>((const double*)a.o, (const double*)a.d_o, (const double*)a.l,
+                                                (const double*)a.m, lse, dsum, p.batch, p.v_d, p.nq, p.d_q, z0, p.d_k, z1,
+                                                p.d_v, z2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   {
     auto kern = bwd_dq_kernel<DP, VP, MT>;
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
-    p.n_tiles = (p.nq + kRows - 1) / kRows;
-    const int ns = splits_for(p.batch * p.n_tiles, (p.nk + kTile - 1) / kTile);
-    if (ns > 1 && (e = cudaMemsetAsync(p.d_q, 0, size_t(p.batch) * p.d * p.nq * 8, stream)) != cudaSuccess) return e;
+    p.n_tiles = int(tiles_q);
     ScopedKernel timed("bwd_dq_f64_dmma", stream);
-    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns_q), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
     auto kern = bwd_dkdv_kernel<DP, VP, MT>;
     cudaError_t e = plan::ensure_smem(kern, BwdSmem<DP, VP>::kBytes);
     if (e != cudaSuccess) return e;
-    p.n_tiles = (p.nk + kRows - 1) / kRows;
-    const int ns = splits_for(p.batch * p.n_tiles, (p.nq + kTile - 1) / kTile);
-    if (ns > 1) {
-      if ((e = cudaMemsetAsync(p.d_k, 0, size_t(p.batch) * p.d * p.nk * 8, stream)) != cudaSuccess) return e;
-      if ((e = cudaMemsetAsync(p.d_v, 0, size_t(p.batch) * p.v_d * p.nk * 8, stream)) != cudaSuccess) return e;
-    }
+    p.n_tiles = int(tiles_k);
     ScopedKernel timed("bwd_dkdv_f64_dmma", stream);
-    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
+    kern<<<dim3(unsigned(p.batch * p.n_tiles), ns_k), threads_of(MT), BwdSmem<DP, VP>::kBytes, stream>>>(p);
     return cudaGetLastError();
   }
 }

@@ -47,18 +47,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// non-blocking test (never suspends): for issuers that poll several barriers
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -315,54 +303,10 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100) and exp2 on the FMA pipe -------------------
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// 2^x for a pair of x in [-126, 127] without the MUFU pipe: round-to-nearest split x = n + f with the
-// 1.5*2^23 trick, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.6e-5, below
-// the fp16 rounding of P), exponent insertion by integer add. ~3 FMA-pipe issue slots per element.
-__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& r0, float& r1) {
-  const float kMagic = 12582912.f;  // 1.5 * 2^23
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.f);
-  x1 = fmaxf(x1, -126.f);
-  x2 = pack2(x0, x1);
-  const uint64_t t2 = add2(x2, pack2(kMagic, kMagic));
-  const uint64_t n2 = add2(t2, pack2(-kMagic, -kMagic));
-  const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);
-  uint64_t p2 = fma2(pack2(0.05520550534f, 0.05520550534f), f2, pack2(0.24261397123f, 0.24261397123f));
-  p2 = fma2(p2, f2, pack2(0.69325476885f, 0.69325476885f));
-  p2 = fma2(p2, f2, pack2(0.99992769957f, 0.99992769957f));
-  float p0, p1, t0, t1;
-  unpack2(p2, p0, p1);
-  unpack2(t2, t0, t1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
