@@ -145,6 +145,18 @@ int fa_partial_finalize(const fa_problem_t* p, const void* o_acc, const void* l_
  *   fa_grad_accumulate: acc[i] = (first ? 0 : acc[i]) + part[i]    acc float (double for FA_F64)
  *   fa_grad_finalize  : out[i] = (dtype) acc[i]                                                  */
 int fa_grad_accumulate(int32_t dtype, const void* part, void* acc, int64_t n, int first, void* stream);
+/* The same sum for dQ made inside the backward launch: dq_acc [dq_fold, d, q] is a float accumulator that dQ of
+ * problem *p is ADDED into (finished values: the softmax scale is applied); batch element pb adds into accumulator
+ * element pb % dq_fold (0 = batch: one accumulator element per batch element; batch / 2: the two halves of a
+ * [Q_hi; Q_hi] pair launch of the ring fold into the same accumulator). d_k, d_v are written as by fa_backward.
+ * Saves the dQ scratch memset, the convert pass, the fp16 dQ tensor and its fa_grad_accumulate pass per block.
+ * Available where fa_backward_accumulate_supported() says so (fp16, channel-first, head_dim 128 with 64 or 128 value
+ * channels, lengths multiples of 8: the fused dQ/dK/dV kernel, whose TMA reduce-add then lands in dq_acc directly);
+ * FA_EINVAL_SHAPE otherwise, and the caller uses fa_backward + fa_grad_accumulate. Workspace as for fa_backward. */
+int fa_backward_accumulate_supported(const fa_problem_t* p, int64_t dq_fold);
+int fa_backward_accumulate(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                           const void* l, const void* m, const void* d_o, void* dq_acc, void* d_k, void* d_v,
+                           int64_t dq_fold, void* workspace, size_t workspace_bytes, void* stream);
 int fa_grad_finalize(int32_t dtype, const void* acc, void* out, int64_t n, void* stream);
 
 /* Layout adapter for the step either side of the op (no reference counterpart: README.md:40 of the reference assumes an

@@ -54,6 +54,46 @@ def test_single_rank_ring_backward_equals_plain_causal(dtype, d, seq, tol, drive
         assert err.max() <= tol, f"{name}: {err.max()}"
 
 
+@pytest.mark.parametrize("vd", [128, 64])
+def test_backward_accumulate_adds_dq_inside_the_launch(vd):
+    """fa_backward_accumulate (include/fa_b200.h): dQ of every batch element is added into the fp32 accumulator element
+    pb % dq_fold by the fused kernel's own reduce-add (no scratch / convert / fa_grad_accumulate); dK, dV as usual."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    B, d, nq, nk = 4, 128, 384, 512
+    Q, K, V, dO = da.random_inputs(rng, np.float16, (B,), d, vd, (nq,), (nk,))
+    ref = da.attention(Q, K, V, 1, "full", "none_front", dO=dO)
+    tq, tk, tv, tdo = (torch.from_numpy(x).cuda() for x in (Q, K, V, dO))
+    from tf_flash_attention_b200 import flash_attention as fa
+    O, l, m = fa.full_1d(tq, tk, tv, "none_front", returning_l_m=True)
+    p = _capi.make_problem(_capi.FA_F16, 1, "full", "none_front", Q.shape, K.shape, V.shape)
+    assert _capi.lib.fa_backward_accumulate_supported(C.byref(p), 0) == 1
+    assert _capi.lib.fa_backward_accumulate_supported(C.byref(p), 2) == 1
+    assert _capi.lib.fa_backward_accumulate_supported(C.byref(p), 5) == 0          # more accumulator elements than problems
+    need = _capi.lib.fa_workspace_bytes(C.byref(p), 1)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for fold in (B, 2):
+        acc = torch.full((fold, d, nq), 0.5, dtype=torch.float32, device="cuda")    # adds INTO the accumulator
+        dk, dv = torch.empty_like(tk), torch.empty_like(tv)
+        _capi.lib.fa_launch_count(1)
+        _capi.check(_capi.lib.fa_backward_accumulate(C.byref(p), tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), O.data_ptr(),
+                                                     l.data_ptr(), m.data_ptr(), tdo.data_ptr(), acc.data_ptr(),
+                                                     dk.data_ptr(), dv.data_ptr(), fold, ws.data_ptr(), need, st),
+                    "fa_backward_accumulate")
+        torch.cuda.synchronize()
+        assert _capi.lib.fa_launch_count(1) == 2                                  # statistics pass + the fused kernel
+        want = ref["dQ"].reshape(B // fold, fold, d, nq).sum(axis=0) + 0.5
+        err = np.abs(acc.cpu().numpy().astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
+        assert err.max() <= 2e-3, err.max()
+        for name, g in (("dK", dk), ("dV", dv)):
+            e2 = np.abs(g.cpu().numpy().astype(np.float64) - ref[name]) / np.maximum(1.0, np.abs(ref[name]))
+            assert e2.max() <= 2e-3, (name, e2.max())
+    # shapes the fused kernel does not take answer FA_EINVAL_SHAPE (the caller falls back to fa_backward + fa_grad_accumulate)
+    p64 = _capi.make_problem(_capi.FA_F16, 1, "full", "none_front", (B, 64, nq), (B, 64, nk), (B, 64, nk))
+    assert _capi.lib.fa_backward_accumulate_supported(C.byref(p64), 0) == 0
+
+
 def test_two_rank_ring_over_the_peer_copy_data_plane():
     """N > 1 on the GPU: two ranks under torchrun run ring_causal_1d and its backward over the fa_ring_* data plane
     (CUDA IPC slots, peer copies, stream-ordered flags) and compare their rows with the dense oracle

@@ -99,6 +99,8 @@ def _load():
         "fa_layout_transpose": (C.c_int, [C.c_int32, vp, vp, i64, i64, C.c_int32, C.c_int32, C.c_int, vp]),
         "fa_grad_accumulate": (C.c_int, [C.c_int32, vp, vp, i64, C.c_int, vp]),
         "fa_grad_finalize": (C.c_int, [C.c_int32, vp, vp, i64, vp]),
+        "fa_backward_accumulate_supported": (C.c_int, [PP, i64]),
+        "fa_backward_accumulate": (C.c_int, [PP, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, sz, vp]),
         "fa_strerror": (C.c_char_p, [C.c_int]),
         "fa_last_cuda_error": (C.c_int, []),
         "fa_last_path": (C.c_int, []),

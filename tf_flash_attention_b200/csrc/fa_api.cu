@@ -240,6 +240,50 @@ int fa_backward(const fa_problem_t* p, const void* q, const void* k, const void*
   return e == cudaSuccess ? FA_OK : cuda_fail(e);
 }
 
+// dQ ADDED into an fp32 accumulator inside the backward launch (K/V ring: every block's dQ used to go through the fused
+// kernel's scratch, a convert pass, an fp16 tensor and fa_grad_accumulate; the kernel's reduce-add can land in the
+// accumulator directly).
+static int fill_accumulate_args(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                                const void* l, const void* m, const void* d_o, void* dq_acc, void* d_k, void* d_v,
+                                int64_t dq_fold, void* workspace, size_t workspace_bytes, fa::LaunchArgs* a) {
+  int rc = fill_args(p, a);
+  if (rc) return rc;
+  a->q = q; a->k = k; a->v = v; a->o = (void*)o; a->l = (void*)l; a->m = (void*)m; a->d_o = d_o;
+  a->d_q = dq_acc; a->d_k = d_k; a->d_v = d_v;
+  a->workspace = workspace; a->workspace_bytes = workspace_bytes;
+  a->variant = fa::g_path_override;
+  a->grad_acc = 1;
+  a->dq_fold = dq_fold > 0 ? dq_fold : p->batch;
+  return 0;
+}
+
+int fa_backward_accumulate_supported(const fa_problem_t* p, int64_t dq_fold) {
+  fa::LaunchArgs a{};
+  void* dummy = reinterpret_cast<void*>(uintptr_t(256));   // a probe: only shape rules are evaluated
+  if (!p || fill_accumulate_args(p, dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, dummy, dq_fold, dummy,
+                                 ~size_t(0), &a))
+    return 0;
+  return (p->dtype == FA_F16 && fa::g_path_override != 1 && p->batch > 0 && fa::sm100_f16_backward_accumulate_supports(a)) ? 1 : 0;
+}
+
+int fa_backward_accumulate(const fa_problem_t* p, const void* q, const void* k, const void* v, const void* o,
+                           const void* l, const void* m, const void* d_o, void* dq_acc, void* d_k, void* d_v,
+                           int64_t dq_fold, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p) return FA_EINVAL_NULL;
+  fa::LaunchArgs a{};
+  int rc = fill_accumulate_args(p, q, k, v, o, l, m, d_o, dq_acc, d_k, d_v, dq_fold, workspace, workspace_bytes, &a);
+  if (rc) return rc;
+  if (p->batch == 0) return FA_OK;
+  if (!q || !k || !v || !o || !l || !m || !d_o || !dq_acc || !d_k || !d_v) return FA_EINVAL_NULL;
+  const size_t need = fa_workspace_bytes(p, 1);
+  if (workspace_bytes < need || (!workspace && need)) return FA_EINVAL_WORKSPACE;
+  if (p->dtype != FA_F16 || fa::g_path_override == 1 || !fa::sm100_f16_backward_accumulate_supports(a))
+    return FA_EINVAL_SHAPE;   // callers fall back to fa_backward + fa_grad_accumulate
+  fa::g_last_path = 2;
+  cudaError_t e = fa::sm100_f16_backward(a, (cudaStream_t)stream);
+  return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
 // ---- layout adapter ------------------------------------------------------------------------------
 int fa_layout_transpose(int32_t dtype, const void* x, void* y, int64_t batch, int64_t seq, int32_t heads,
                         int32_t channels, int to_channel_first, void* stream) {

@@ -1495,9 +1495,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 struct alignas(64) FusedParams {
   BwdParams base;
   CUtensorMap map_dq_acc;   // fp32 [batch*D, nq], box 32 x D, 128B swizzle
+  // ACC (fa_backward_accumulate): dQ is ADDED into the caller's fp32 accumulator - the reduce-add above lands there
+  // directly (scaled in the drain), so the scratch memset, the convert pass and the caller's fa_grad_accumulate pass
+  // disappear. Problem pb adds into accumulator element pb % dq_fold (the K/V ring launches [Q_hi; Q_hi] pairs whose
+  // two halves belong to the same accumulator). dK / dV are written as usual.
+  int32_t dq_fold;
 };
 
-template <int D, int VD, bool CL>
+template <int D, int VD, bool CL, bool ACC>
 __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __grid_constant__ FusedParams fp) {
   using Cfg = FusedCfg<D, VD>;
   constexpr int kStages = Cfg::kStages;
@@ -1607,6 +1612,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(bar_dq_free + 8 * x);
+      if constexpr (ACC) {   // the accumulator holds finished gradients: the softmax scale goes in here
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          va[e] = __float_as_uint(__uint_as_float(va[e]) * p.scale);
+          vb[e] = __float_as_uint(__uint_as_float(vb[e]) * p.scale);
+        }
+      }
       if (rr == 0) FB_STAMP(2, t, 1);
       const uint32_t row_off = rr * 128;
       auto stage_half = [&](const uint32_t (&v)[32], int h) {
@@ -1620,7 +1632,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
         named_bar_sync(3, 128);
         if (rr == 0) {
 #ifndef FA_FUSED_NO_RED
-          tma_reduce_add_2d(&fp.map_dq_acc, stage, qt * kBN + h * 32, b * D);
+          tma_reduce_add_2d(&fp.map_dq_acc, stage, qt * kBN + h * 32, (ACC ? b % fp.dq_fold : b) * D);
 #endif
           tma_store_commit();
         }
@@ -1841,29 +1853,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bwd_fused_kernel(const __gri
     const int CH = x == 0 ? VD : D;
     const uint32_t t_acc = tmem_base + lane_addr + (x == 0 ? 256 : 384);
     const float out_scale = x == 0 ? 1.f : p.scale;
-    uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
-    if (t > 0) {
-      mbar_wait(bar_final, 0);
-      tc_fence_after();
-      for (int c = 0; c < CH / 32; ++c) {
-        float o[32];
-        tmem_ld32f(t_acc + c * 32, o);
-        tmem_wait_ld();
-        stage_row32<CL>(stage_gen, r, c * 32, kBM, CH, o, out_scale);
+    {
+      uint8_t* stage_gen = smem_gen + (x == 0 ? Cfg::kKBytes : 0);
+      if (t > 0) {
+        mbar_wait(bar_final, 0);
+        tc_fence_after();
+        for (int c = 0; c < CH / 32; ++c) {
+          float o[32];
+          tmem_ld32f(t_acc + c * 32, o);
+          tmem_wait_ld();
+          stage_row32<CL>(stage_gen, r, c * 32, kBM, CH, o, out_scale);
+        }
+      } else {
+        mbar_wait(bar_kv_res, 0);
+        stage_row_zero<CL>(stage_gen, r, 0, CH, kBM, CH);
       }
-    } else {
-      mbar_wait(bar_kv_res, 0);
-      stage_row_zero<CL>(stage_gen, r, 0, CH, kBM, CH);
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1 + x, kBM);
-    if (r == 0) {
-      if (x == 0)
-        tile_store<CL>(&p.map_dv, v_smem, k0, kBM, VD, p.nk, bc);
-      else
-        tile_store<CL>(&p.map_dk, k_smem, k0, kBM, D, p.nk, bc);
-      tma_store_commit();
-      tma_store_wait_read();
+      fence_proxy_async_smem();
+      named_bar_sync(1 + x, kBM);
+      if (r == 0) {
+        if (x == 0)
+          tile_store<CL>(&p.map_dv, v_smem, k0, kBM, VD, p.nk, bc);
+        else
+          tile_store<CL>(&p.map_dk, k_smem, k0, kBM, D, p.nk, bc);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
     }
   }
   tc_fence_before();
@@ -2029,10 +2043,28 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       // fused dQ/dK/dV: fp32 dQ scratch behind the row statistics, with the row pitch of the dQ tensor the convert pass
       // writes (the padded pitch when the q side is packed; the columns past nq only ever receive zeros)
       if (!bwd_maps<D, VD, CL>(&p, a, kBN, kBM)) return cudaErrorInvalidValue;
+      if constexpr (!CL) {
+        if (a.grad_acc) {
+          // dQ added into the caller's fp32 accumulator through the kernel's own reduce-add: no scratch, no memset, no
+          // convert pass (dK / dV: fp16 tensors as usual)
+          FusedParams fp;
+          fp.base = p;
+          fp.dq_fold = int32_t(a.dq_fold);
+          if (!make_map_f32_sw128(&fp.map_dq_acc, a.d_q, a.dq_fold * D, nq, 32, D)) return cudaErrorInvalidValue;
+          auto kern = bwd_fused_kernel<D, VD, false, true>;
+          cudaError_t e = plan::ensure_smem(kern, FusedCfg<D, VD>::kSmemBytes);
+          if (e != cudaSuccess) return e;
+          fp.base.n_blocks = (nk + kBM - 1) / kBM;
+          ScopedKernel timed("bwd_fused_f16_sm100_acc", stream);
+          kern<<<unsigned(int64_t(fp.base.n_blocks) * p.batch), kFusedThreads, FusedCfg<D, VD>::kSmemBytes, stream>>>(fp);
+          return cudaGetLastError();
+        }
+      }
       float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + bwd_layout(a).off_acc);
       const size_t acc_bytes = size_t(a.batch) * D * qp * sizeof(float);
       FusedParams fp;
       fp.base = p;
+      fp.dq_fold = 1;
       if (!make_map_f32_sw128(&fp.map_dq_acc, acc, a.batch * D, qp, 32, D)) return cudaErrorInvalidValue;
       {
         ScopedKernel timed("bwd_dq_zero", stream);
@@ -2040,7 +2072,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
       }
       {
-        auto kern = bwd_fused_kernel<D, VD, CL>;
+        auto kern = bwd_fused_kernel<D, VD, CL, false>;
         cudaError_t e =
             plan::ensure_smem(kern, FusedCfg<D, VD>::kSmemBytes);
         if (e != cudaSuccess) return e;
@@ -2065,6 +2097,7 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       }
     }
   }
+  if (a.grad_acc) return cudaErrorNotSupported;   // only the fused kernel accumulates (checked by the caller)
   if (!bwd_maps<D, VD, CL>(&p, a, kBM, kBN)) return cudaErrorInvalidValue;   // dQ kernels: resident queries
   bool dq_done = false;
   if constexpr (D == 64 && VD == 64) {
@@ -2177,6 +2210,18 @@ bool sm100_f16_backward_supports(const LaunchArgs& a) {
 }
 
 size_t sm100_f16_bwd_workspace_bytes(const LaunchArgs& a) { return sm100::bwd_layout(a).total; }
+
+// fa_backward_accumulate: the fused head_dim-128 kernel on unpacked channel-first tensors (any gradient precision mode
+// but "precise everywhere", which runs the two-kernel backward)
+bool sm100_f16_backward_accumulate_supports(const LaunchArgs& a) {
+  if (!sm100_f16_backward_supports(a)) return false;
+  if (a.layout != 0 || a.d != 128 || (a.v_d != 128 && a.v_d != 64) || a.variant == 4 || a.grad_split == 1) return false;
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  if (nq % 8 || nk % 8) return false;                       // no pack pass in front of accumulators
+  if (a.dq_fold < 1 || a.dq_fold > a.batch) return false;
+  if ((reinterpret_cast<uintptr_t>(a.d_q) & 15) != 0) return false;
+  return true;
+}
 
 template <bool CL>
 static cudaError_t backward_dispatch_layout(const LaunchArgs& a, cudaStream_t stream) {

@@ -32,6 +32,10 @@ struct LaunchArgs {
   // 0 = channel-first [batch][channels][sequence] (the reference's layout); 1 = channel-last
   // [outer][sequence][heads][channels] with batch = outer * heads (fp16 tcgen05 kernels only; l, m stay [batch][q])
   int32_t layout, heads;
+  // fa_backward_accumulate: d_q is an fp32 accumulator that dQ is ADDED into; problem pb adds into accumulator element
+  // pb % dq_fold. fp16 fused head_dim-128 backward only.
+  int32_t grad_acc;
+  int64_t dq_fold;
   int32_t grad_split;  // fp16 backward: dS handed to the tensor cores as hi + lo fp16 pairs (fa_set_grad_precision)
   int32_t variant;  // fa_set_path_override value (0 auto; 4 = fp16 backward as two kernels; 5 / 6 = forward tile configuration)
 };
@@ -77,6 +81,7 @@ cudaError_t pack_channels_f32(const float* src, float* dst, int64_t batch, int64
 // tcgen05 / TMEM / TMA family for half (fa_fwd_f16_sm100.cu, fa_bwd_f16_sm100.cu)
 bool sm100_f16_forward_supports(const LaunchArgs& a);
 bool sm100_f16_backward_supports(const LaunchArgs& a);
+bool sm100_f16_backward_accumulate_supports(const LaunchArgs& a);
 size_t sm100_f16_workspace_bytes(const LaunchArgs& a, bool backward);
 cudaError_t sm100_f16_forward(const LaunchArgs& a, cudaStream_t stream);
 cudaError_t sm100_f16_backward(const LaunchArgs& a, cudaStream_t stream);

@@ -441,6 +441,19 @@ int fa_ring_causal_backward(fa_ring_t* kv, fa_ring_t* acc_ring, int32_t dtype, i
   auto add = [&](const void* part, void* acc, size_t n) {
     return fa_grad_accumulate(dtype, part, acc, int64_t(n), 0, st);
   };
+  // dQ lands in its fp32 accumulator inside the backward launch where the fused kernel takes the shape (fp16, head_dim
+  // 128): no fp16 dQ block, no fa_grad_accumulate pass for it
+  const bool dq_in_kernel = fa_backward_accumulate_supported(&causal2, 2 * batch) &&
+                            fa_backward_accumulate_supported(&full2, 2 * batch) &&
+                            fa_backward_accumulate_supported(&full2, batch) &&
+                            fa_backward_accumulate_supported(&full1, batch);
+  // one block: gradients of problem p; dQ goes to dq_dst (fold = accumulator elements it spans), dK / dV to the part buffers
+  auto block = [&](const fa_problem_t& p, const void* q, const void* k, const void* v, const void* o, const void* l,
+                   const void* m, const void* d_o, char* dq_dst, int64_t fold) {
+    if (dq_in_kernel)
+      return fa_backward_accumulate(&p, q, k, v, o, l, m, d_o, dq_dst, pdk, pdv, fold, ws, A.ws_bytes, st);
+    return fa_backward(&p, q, k, v, o, l, m, d_o, pdq, pdk, pdv, ws, A.ws_bytes, st);
+  };
   const char* cur_k = static_cast<const char*>(k2);
   const char* cur_v = static_cast<const char*>(v2);
   for (int step = 0; step < world; ++step) {
@@ -453,17 +466,17 @@ int fa_ring_causal_backward(fa_ring_t* kv, fa_ring_t* acc_ring, int32_t dtype, i
     const int src_rank = ((rank - step) % world + world) % world;
     // this step's backward launch is queued BEFORE the wait for the travelling accumulators: their transfer overlaps it
     if (step == 0) {
-      RING_OK(fa_backward(&causal2, q2, cur_k, cur_v, o2, l2, m2, do2, pdq, pdk, pdv, ws, A.ws_bytes, st));
+      RING_OK(block(causal2, q2, cur_k, cur_v, o2, l2, m2, do2, dq_acc, 2 * batch));
     } else if (src_rank < rank) {
       char *dk = base + A.dup_k, *dv = base + A.dup_v;
       for (int h = 0; h < 2; ++h) {
         RING_CU(cudaMemcpyAsync(dk + h * hq * es, cur_k, hq * es, cudaMemcpyDeviceToDevice, st));
         RING_CU(cudaMemcpyAsync(dv + h * hv * es, cur_v, hv * es, cudaMemcpyDeviceToDevice, st));
       }
-      RING_OK(fa_backward(&full2, q2, dk, dv, o2, l2, m2, do2, pdq, pdk, pdv, ws, A.ws_bytes, st));
+      RING_OK(block(full2, q2, dk, dv, o2, l2, m2, do2, dq_acc, 2 * batch));
     } else {
-      RING_OK(fa_backward(&full2, base + A.q_hh, cur_k, cur_v, base + A.o_hh, base + A.l_hh, base + A.m_hh,
-                          base + A.do_hh, pdq, pdk, pdv, ws, A.ws_bytes, st));
+      RING_OK(block(full2, base + A.q_hh, cur_k, cur_v, base + A.o_hh, base + A.l_hh, base + A.m_hh, base + A.do_hh,
+                    dq_acc + hq * as, batch));   // both halves belong to Q_hi
     }
     if (step > 0) {   // the accumulators of the shard being processed arrive one hop behind it
       RING_OK(fa_ring_recv_wait(acc_ring, (step - 1) % 2, st));
@@ -471,23 +484,24 @@ int fa_ring_causal_backward(fa_ring_t* kv, fa_ring_t* acc_ring, int32_t dtype, i
       dv_acc = dk_acc + al256(kab);
     }
     if (step == 0) {
-      RING_OK(add(pdq, dq_acc, 2 * hq));
+      if (!dq_in_kernel) RING_OK(add(pdq, dq_acc, 2 * hq));
       RING_OK(add(pdk, dk_acc, 2 * hq));
       RING_OK(add(pdv, dv_acc, 2 * hv));
       // Q_hi x K_lo, full: results into the first halves of the part buffers
-      RING_OK(fa_backward(&full1, hi(q2, hq * es), cur_k, cur_v, hi(o2, hv * es), hi(l2, hr * ls), hi(m2, hr * es),
-                          hi(do2, hv * es), pdq, pdk, pdv, ws, A.ws_bytes, st));
-      RING_OK(add(pdq, dq_acc + hq * as, hq));
+      RING_OK(block(full1, hi(q2, hq * es), cur_k, cur_v, hi(o2, hv * es), hi(l2, hr * ls), hi(m2, hr * es),
+                    hi(do2, hv * es), dq_acc + hq * as, batch));
+      if (!dq_in_kernel) RING_OK(add(pdq, dq_acc + hq * as, hq));
       RING_OK(add(pdk, dk_acc, hq));
       RING_OK(add(pdv, dv_acc, hv));
     } else if (src_rank < rank) {
-      RING_OK(add(pdq, dq_acc, 2 * hq));
+      if (!dq_in_kernel) RING_OK(add(pdq, dq_acc, 2 * hq));
       for (int h = 0; h < 2; ++h) {   // both halves belong to K_lo(src)
         RING_OK(add(pdk + h * hq * es, dk_acc, hq));
         RING_OK(add(pdv + h * hv * es, dv_acc, hv));
       }
     } else {
-      for (int h = 0; h < 2; ++h) RING_OK(add(pdq + h * hq * es, dq_acc + hq * as, hq));   // both belong to Q_hi
+      if (!dq_in_kernel)
+        for (int h = 0; h < 2; ++h) RING_OK(add(pdq + h * hq * es, dq_acc + hq * as, hq));   // both belong to Q_hi
       RING_OK(add(pdk, dk_acc, 2 * hq));
       RING_OK(add(pdv, dv_acc, 2 * hv));
     }
