@@ -164,7 +164,7 @@ size_t fa_workspace_bytes(const fa_problem_t* p, int is_backward) {
     if (fa::sm100_f32_backward_supports(probe)) s = fa::sm100_f32_backward_workspace_bytes(a);
   }
   if (p->dtype == FA_F32 && !is_backward) {
-    // hi / lo TF32 copies of Q, K, V for the 3xTF32 forward (only when that kernel can take the shape)
+    // hi / lo TF32 copies of Q, K, V (and a padded O) for the 3xTF32 forward, when that kernel takes the shape
     fa::LaunchArgs probe = a;
     probe.o = nullptr;
     probe.workspace = reinterpret_cast<void*>(uintptr_t(256));

@@ -1,4 +1,5 @@
-// fa_bwd_f32_sm100.cu — fp32 backward on the tensor cores (head dims 64/64, 32/32, 32/16): split-precision tcgen05 kernels.
+// fa_bwd_f32_sm100.cu — fp32 backward on the tensor cores: split-precision tcgen05 kernels instantiated for head dims
+// 64/64, 32/32, 32/16; any channel counts up to 64 and any lengths run on them (the split pass pads).
 //
 // The forward runs fp32 as 3xTF32 (fa_fwd_f32_sm100.cu). The backward needs every streamed tile in BOTH operand
 // orientations (K as the MN-major B operand of S = Q K^T and as the K-major B operand of dQ = dS K, Q likewise in the

@@ -11,7 +11,9 @@
 // MN-major operands straight from TMA (box = 32 floats of sequence x all channels, 128-byte swizzle),
 // V is K-major. One 128-row Q tile per CTA, 64-key tiles, K/V ring of 4 stages (each stage = hi + lo).
 // Replaces the reference's float instantiation of ForwardImpl (flash_attention/kernel/flash_attention.cu:
-// 425-1077, FFMA). The fp32 backward and fp64 run on the FFMA / DFMA kernels of fa_generic.cu.
+// 425-1077, FFMA). Instantiated for head dims 64/64, 32/32, 32/16; any channel counts up to 64, any lengths and any
+// alignment run on them: the split pass writes zero-padded copies in the kernel's shape and a padded O is copied out.
+// The fp32 backward is fa_bwd_f32_sm100.cu, fp64 fa_f64_dmma.cu.
 #include "fa_common.cuh"
 #include "fa_launch.h"
 #include "fa_plan.h"
