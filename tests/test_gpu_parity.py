@@ -13,7 +13,6 @@ import numpy as np
 import pytest
 
 from oracle import dense_attention as da
-from oracle import pattern
 from tests.helpers import TOL, case_id, load_pattern_golden, max_abs_err, scaled_err
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import dense_attention as da
 from tf_flash_attention_b200 import _capi, flash_attention as fa
-from tools.debug_sm100 import run
 import numpy as np
 def detail(dims, rule, mode, w, s, c, batch, d, vd, qs, ks, seed=0):
     rng = np.random.default_rng(seed)

@@ -1,5 +1,5 @@
 """Developer probe (not a test): runs the tcgen05 paths on a few shapes and prints error stats."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oracle import dense_attention as da
