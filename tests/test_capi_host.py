@@ -219,6 +219,42 @@ def test_ring_driver_argument_checks():
     assert b == _capi.FA_EINVAL_NULL
 
 
+def test_backward_accumulate_probe_and_argument_checks():
+    """fa_backward_accumulate_supported is a host-only probe: the fused head_dim-128 fp16 kernel on unpacked channel-first
+    tensors is the only path that adds dQ into an accumulator; everything else answers no (and the entry point
+    FA_EINVAL_SHAPE), so callers keep fa_backward + fa_grad_accumulate as the fallback."""
+    import ctypes as C
+    sup = _capi.lib.fa_backward_accumulate_supported
+    mk = lambda dt, d, vd, nq, nk, rule="causal": _capi.make_problem(dt, 1, rule, "none_front", (4, d, nq), (4, d, nk), (4, vd, nk))  # noqa: E731
+    assert sup(C.byref(mk(_capi.FA_F16, 128, 128, 512, 512)), 0) == 1
+    assert sup(C.byref(mk(_capi.FA_F16, 128, 64, 512, 384, "full")), 2) == 1
+    assert sup(C.byref(mk(_capi.FA_F16, 128, 128, 512, 512)), 5) == 0       # fold larger than the batch
+    assert sup(C.byref(mk(_capi.FA_F16, 128, 128, 500, 512)), 0) == 0       # packed lengths
+    assert sup(C.byref(mk(_capi.FA_F16, 64, 64, 512, 512)), 0) == 0         # two-kernel backward
+    assert sup(C.byref(mk(_capi.FA_F16, 128, 96, 512, 512)), 0) == 0        # value channels padded by the descriptors
+    assert sup(C.byref(mk(_capi.FA_F32, 64, 64, 512, 512)), 0) == 0
+    p = mk(_capi.FA_F16, 128, 128, 512, 512)
+    p.layout, p.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 2
+    assert sup(C.byref(p), 0) == 0
+    try:
+        _capi.lib.fa_set_grad_precision(1)                                   # precise everywhere: two-kernel backward
+        assert sup(C.byref(mk(_capi.FA_F16, 128, 128, 512, 512)), 0) == 0
+        _capi.lib.fa_set_grad_precision(0)
+        _capi.lib.fa_set_path_override(4)
+        assert sup(C.byref(mk(_capi.FA_F16, 128, 128, 512, 512)), 0) == 0
+    finally:
+        _capi.lib.fa_set_grad_precision(0)
+        _capi.lib.fa_set_path_override(0)
+    one = 256
+    q = mk(_capi.FA_F16, 64, 64, 512, 512)
+    ws = _capi.lib.fa_workspace_bytes(C.byref(q), 1)
+    call = lambda pr, acc=one, nbytes=1 << 30: _capi.lib.fa_backward_accumulate(  # noqa: E731
+        C.byref(pr), one, one, one, one, one, one, one, acc, one, one, 0, one, nbytes, None)
+    assert call(q) == _capi.FA_EINVAL_SHAPE
+    assert call(q, acc=None) == _capi.FA_EINVAL_NULL
+    assert call(q, nbytes=ws - 1) == _capi.FA_EINVAL_WORKSPACE
+
+
 def test_channel_last_problem_validation():
     """fa_problem_t.layout / heads (include/fa_b200.h): validated on the host before any launch; a dtype no kernel
     reads channel-last answers FA_EINVAL_LAYOUT so the caller can run the adapter (fa_layout_transpose) instead."""
