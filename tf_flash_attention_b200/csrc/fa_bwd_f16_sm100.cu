@@ -1905,25 +1905,29 @@ __global__ void bwd_dq_convert(const float4* __restrict__ acc, uint4* __restrict
 // pass scales, rounds and transposes 64 positions x 128 channels per block through shared memory into
 // [outer][q][heads][128] fp16
 __global__ void __launch_bounds__(256) bwd_dq_convert_cl(const float* __restrict__ acc, __half* __restrict__ dq,
-                                                         int32_t nq, int64_t pitch, int32_t heads, float scale) {
+                                                         int64_t batch, int32_t nq, int64_t pitch, int32_t heads,
+                                                         float scale) {
   constexpr int kPitch = 130;   // halves per staged position row: 4-byte aligned rows, 2-way bank conflicts at most
   __shared__ __half tile[64 * kPitch];
-  const int b = blockIdx.y, q0 = blockIdx.x * 64;
+  const int q0 = blockIdx.x * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = q0 + 2 * lane;
-  for (int d = warp; d < 128; d += 8) {
-    float2 v = make_float2(0.f, 0.f);
-    if (q < pitch) v = *reinterpret_cast<const float2*>(acc + (int64_t(b) * 128 + d) * pitch + q);   // pitch is even
-    tile[(2 * lane) * kPitch + d] = __float2half_rn(v.x * scale);
-    tile[(2 * lane + 1) * kPitch + d] = __float2half_rn(v.y * scale);
-  }
-  __syncthreads();
-  const int64_t ob = b / heads, h = b % heads;
-  for (int r = warp; r < 64 && q0 + r < nq; r += 8) {
-    __half2* dst = reinterpret_cast<__half2*>(dq + ((ob * nq + q0 + r) * heads + h) * 128);
-    const __half2* src = reinterpret_cast<const __half2*>(tile + r * kPitch);
-    dst[lane] = src[lane];
-    dst[lane + 32] = src[lane + 32];
+  for (int64_t b = blockIdx.y; b < batch; b += gridDim.y) {   // gridDim.y is capped at 65535
+    for (int d = warp; d < 128; d += 8) {
+      float2 v = make_float2(0.f, 0.f);
+      if (q < pitch) v = *reinterpret_cast<const float2*>(acc + (b * 128 + d) * pitch + q);   // pitch is even
+      tile[(2 * lane) * kPitch + d] = __float2half_rn(v.x * scale);
+      tile[(2 * lane + 1) * kPitch + d] = __float2half_rn(v.y * scale);
+    }
+    __syncthreads();
+    const int64_t ob = b / heads, h = b % heads;
+    for (int r = warp; r < 64 && q0 + r < nq; r += 8) {
+      __half2* dst = reinterpret_cast<__half2*>(dq + ((ob * nq + q0 + r) * heads + h) * 128);
+      const __half2* src = reinterpret_cast<const __half2*>(tile + r * kPitch);
+      dst[lane] = src[lane];
+      dst[lane + 32] = src[lane + 32];
+    }
+    __syncthreads();   // the tile is reused by the next batch element
   }
 }
 
@@ -2084,8 +2088,8 @@ cudaError_t launch_bwd(const LaunchArgs& a, cudaStream_t stream) {
       }
       if constexpr (CL) {
         ScopedKernel timed("bwd_dq_convert_cl", stream);
-        bwd_dq_convert_cl<<<dim3(unsigned((nq + 63) / 64), unsigned(a.batch)), 256, 0, stream>>>(
-            acc, reinterpret_cast<__half*>(a.d_q), nq, qp, a.heads, p.scale);
+        bwd_dq_convert_cl<<<dim3(unsigned((nq + 63) / 64), unsigned(std::min<int64_t>(a.batch, 65535))), 256, 0, stream>>>(
+            acc, reinterpret_cast<__half*>(a.d_q), a.batch, nq, qp, a.heads, p.scale);
         return cudaGetLastError();
       } else {
         const int64_t n8 = a.batch * int64_t(D) * qp / 8;
