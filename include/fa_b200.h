@@ -238,6 +238,11 @@ int fa_last_cuda_error(void);          /* cudaError_t of the last FA_ECUDA on th
  * 0 none, 1 generic SIMT (FFMA / DFMA), 2 tcgen05 fp16, 3 tcgen05 fp32 split precision
  * (forward: 3xTF32; backward: three bf16 pieces per operand), 4 fp64 on the FP64 tensor cores (DMMA). */
 int fa_last_path(void);
+/* The same answer BEFORE the call, host only: which family fa_forward (is_backward = 0) / fa_backward will take for *p
+ * given 256-byte-aligned tensors and a workspace of fa_workspace_bytes(). When it is 1 (generic kernels) `reason`
+ * (may be NULL) receives why the tensor-core family declines: channel counts, a sequence beyond the 2048 streamed tiles
+ * of a CTA's schedule, accumulate, ... Negative = the FA_EINVAL_* the call would return.                          */
+int fa_dispatch_path(const fa_problem_t* p, int is_backward, char* reason, size_t reason_len);
 /* Number of kernel launches issued by this library in this process since the last reset. */
 int64_t fa_launch_count(int reset);
 /* Per-kernel device timing for bench.py: when enabled every kernel this library launches is

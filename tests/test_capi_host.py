@@ -219,6 +219,48 @@ def test_ring_driver_argument_checks():
     assert b == _capi.FA_EINVAL_NULL
 
 
+def test_dispatch_path_names_the_family_and_the_reason():
+    """fa_dispatch_path (host only): no silent cliffs - a caller can ask which family a problem takes and why the
+    tensor-core kernels decline it (sequences beyond the 2048-tile schedule dropped to SIMT with
+    fa_last_path() as the only trace)."""
+    import ctypes as C
+    dp = fa.dispatch_path
+    assert dp(1, "causal", (4, 128, 8192), (4, 128, 8192), (4, 128, 8192), np.float16) == ("tcgen05_f16", "")
+    assert dp(1, "causal", (4, 24, 342), (4, 24, 342), (4, 9, 342), np.float16, backward=True) == ("tcgen05_f16", "")
+    assert dp(2, "local", (2, 17, 13, 9), (2, 17, 13, 9), (2, 31, 13, 9), np.float32, window_size=3) == ("tcgen05_f32_split", "")
+    assert dp(1, "full", (2, 64, 100), (2, 64, 100), (2, 64, 100), np.float64, backward=True) == ("dmma_f64", "")
+    # the schedule holds 2048 streamed tiles: 64-key tiles for head_dim <= 64, 128-key tiles for the head_dim-128 forward
+    assert dp(1, "full", (1, 64, 64), (1, 64, 131072), (1, 64, 131072), np.float16)[0] == "tcgen05_f16"
+    name, why = dp(1, "full", (1, 64, 64), (1, 64, 131072 + 64), (1, 64, 131072 + 64), np.float16)
+    assert name == "generic_simt" and "2048" in why and "ring" in why
+    assert dp(1, "full", (1, 128, 64), (1, 128, 262144), (1, 128, 262144), np.float16)[0] == "tcgen05_f16"
+    assert dp(1, "full", (1, 128, 64), (1, 128, 262144 + 128), (1, 128, 262144 + 128), np.float16)[0] == "generic_simt"
+    name, why = dp(1, "full", (1, 128, 64), (1, 128, 131072 + 64), (1, 128, 131072 + 64), np.float16, backward=True)
+    assert name == "generic_simt" and "2048" in why
+    assert dp(1, "full", (1, 160, 64), (1, 160, 64), (1, 160, 64), np.float16) == ("generic_simt", "more than 128 channels: generic kernels")
+    assert dp(1, "full", (1, 96, 64), (1, 96, 64), (1, 96, 64), np.float32)[1].startswith("more than 64 channels")
+    assert dp(1, "full", (1, 96, 64), (1, 96, 64), (1, 96, 64), np.float64, backward=True)[0] == "generic_simt"
+    p = _capi.make_problem(_capi.FA_F16, 1, "full", "none_front", (1, 64, 64), (1, 64, 64), (1, 64, 64))
+    p.accumulate = 1
+    assert _capi.dispatch_path(p) == ("generic_simt", "accumulate = 1 is served by the generic forward kernels")
+    assert _capi.dispatch_path(p, backward=True)[0] == "tcgen05_f16"
+    p.accumulate = 0
+    p.layout, p.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 1
+    assert _capi.dispatch_path(p)[0] == "tcgen05_f16"
+    p32 = _capi.make_problem(_capi.FA_F32, 1, "full", "none_front", (1, 64, 64), (1, 64, 64), (1, 64, 64))
+    p32.layout, p32.heads = _capi.FA_LAYOUT_CHANNEL_LAST, 1
+    with pytest.raises(_capi.InvalidArgumentError) as e:
+        _capi.dispatch_path(p32)
+    assert e.value.status == _capi.FA_EINVAL_LAYOUT
+    try:
+        _capi.lib.fa_set_path_override(1)
+        assert dp(1, "causal", (4, 128, 512), (4, 128, 512), (4, 128, 512), np.float16)[0] == "generic_simt"
+    finally:
+        _capi.lib.fa_set_path_override(0)
+    assert _capi.lib.fa_dispatch_path(None, 0, None, 0) == _capi.FA_EINVAL_NULL
+    assert _capi.lib.fa_dispatch_path(C.byref(p), 0, None, 0) == 2            # the reason buffer is optional
+
+
 def test_backward_accumulate_probe_and_argument_checks():
     """fa_backward_accumulate_supported is a host-only probe: the fused head_dim-128 fp16 kernel on unpacked channel-first
     tensors is the only path that adds dQ into an accumulator; everything else answers no (and the entry point

@@ -104,6 +104,7 @@ def _load():
         "fa_strerror": (C.c_char_p, [C.c_int]),
         "fa_last_cuda_error": (C.c_int, []),
         "fa_last_path": (C.c_int, []),
+        "fa_dispatch_path": (C.c_int, [PP, C.c_int, C.c_char_p, sz]),
         "fa_launch_count": (i64, [C.c_int]),
         "fa_set_path_override": (None, [C.c_int]),
         "fa_set_grad_precision": (C.c_int, [C.c_int]),
@@ -183,6 +184,15 @@ def check_backward_shapes(p, shapes):
         r, d = _dims(s)
         args += [r, d]
     check(lib.fa_check_backward_shapes(p.seq_dims, *args, C.byref(p)), "shape check")
+
+
+def dispatch_path(p, backward=False):
+    """(kernel family name, reason) fa_forward / fa_backward will take for problem p (host only; fa_dispatch_path)."""
+    buf = C.create_string_buffer(320)
+    rc = lib.fa_dispatch_path(C.byref(p), int(backward), buf, len(buf))
+    if rc < 0:
+        check(rc, "fa_dispatch_path")
+    return PATH_NAMES[rc], buf.value.decode()
 
 
 def pattern_mask(p):

@@ -13,6 +13,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_launch.h"
+#include "sm100_tiles.cuh"
 
 namespace fa {
 // process-wide (autograd runs the backward on another thread than the forward)
@@ -282,6 +283,54 @@ int fa_backward_accumulate(const fa_problem_t* p, const void* q, const void* k, 
   fa::g_last_path = 2;
   cudaError_t e = fa::sm100_f16_backward(a, (cudaStream_t)stream);
   return e == cudaSuccess ? FA_OK : cuda_fail(e);
+}
+
+// Which kernel family a call will take, and when it is the generic one, why (host only). The tensor-core families
+// decline a problem silently (fa_last_path() afterwards is the only trace); a framework can ask beforehand.
+int fa_dispatch_path(const fa_problem_t* p, int is_backward, char* reason, size_t reason_len) {
+  auto say = [&](const char* msg) {
+    if (reason && reason_len) snprintf(reason, reason_len, "%s", msg);
+  };
+  say("");
+  if (!p) return FA_EINVAL_NULL;
+  fa::LaunchArgs a{};
+  int rc = fill_args(p, &a);
+  if (rc) return rc;
+  void* al = reinterpret_cast<void*>(uintptr_t(256));   // probe: aligned tensors, workspace as large as asked for
+  a.q = a.k = a.v = a.d_o = al;
+  a.o = a.l = a.m = a.d_q = a.d_k = a.d_v = a.workspace = al;
+  a.workspace_bytes = ~size_t(0);
+  a.variant = fa::g_path_override;
+  const bool bwd = is_backward != 0;
+  if (fa::g_path_override == 1) {
+    say("fa_set_path_override(1): generic kernels forced");
+    return a.layout ? FA_EINVAL_LAYOUT : 1;
+  }
+  const int64_t nq = a.rule.q.total, nk = a.rule.k.total;
+  const int64_t cap = 32 * int64_t(fa::sm100::kMaxTileWords);   // streamed tiles of a CTA's schedule
+  if (p->dtype == FA_F16 && (bwd ? fa::sm100_f16_backward_supports(a) : fa::sm100_f16_forward_supports(a))) return 2;
+  if (p->dtype == FA_F32 && (bwd ? fa::sm100_f32_backward_supports(a) : fa::sm100_f32_forward_supports(a))) return 3;
+  if (p->dtype == FA_F64 && (bwd ? fa::f64_dmma_backward_supports(a) : fa::f64_dmma_forward_supports(a))) return 4;
+  const int max_ch = p->dtype == FA_F16 ? 128 : 64;
+  const int64_t tile = (p->dtype == FA_F16 && !bwd && (p->d > 64 || p->v_d > 64)) ? 128 : 64;
+  if (a.layout != 0) {
+    say("channel-last operands are read directly only by the fp16 tensor-core kernels (channels multiples of 8 up to 128)");
+    return FA_EINVAL_LAYOUT;
+  }
+  if (p->d > max_ch || p->v_d > max_ch)
+    say(p->dtype == FA_F16 ? "more than 128 channels: generic kernels" : "more than 64 channels: generic kernels");
+  else if (!bwd && a.accumulate)
+    say("accumulate = 1 is served by the generic forward kernels");
+  else if (p->dtype != FA_F64 && ((nk + tile - 1) / tile > cap || (bwd && (nq + 63) / 64 > cap)))
+    say("sequence longer than the 2048 streamed tiles a CTA's schedule holds (131072 positions at 64 per tile, 262144 "
+        "keys for the head_dim-128 forward): generic kernels; shard the sequence (K/V ring) to stay on the tensor cores");
+  else
+    say("batch x tiles exceeds a 31-bit grid: generic kernels");
+  if (!fa::generic_supports(a)) {
+    say("more than 256 channels: no kernel");
+    return FA_EINVAL_SHAPE;
+  }
+  return 1;
 }
 
 // ---- layout adapter ------------------------------------------------------------------------------

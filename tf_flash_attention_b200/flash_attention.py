@@ -359,6 +359,16 @@ def estimate_forward_flops(seq_dims, rule, q_shape, k_shape, v_shape, dtype, syn
     return _capi.estimate_forward_flops(p, shared_mem_bytes)
 
 
+def dispatch_path(seq_dims, rule, q_shape, k_shape, v_shape, dtype, sync_mode='none_front', window_size=1,
+                  log2_stride_size=0, is_causal=False, backward=False):
+    '''Which kernel family a call with these (channel-first) shapes takes, and - when it is the generic SIMT family -
+    why the tensor-core kernels decline it (host only; `fa_dispatch_path`). Returns (name, reason).'''
+    code = _NP_DTYPES[np.dtype(dtype)]
+    p = _capi.make_problem(code, seq_dims, rule, sync_mode, tuple(q_shape), tuple(k_shape), tuple(v_shape),
+                           window_size, log2_stride_size, is_causal)
+    return _capi.dispatch_path(p, backward)
+
+
 # ---- layout adapters (SURVEY.md section 8 f3: the step either side of the op) -----------------------------------
 def from_channel_last(x):
     """[batch, seq, heads, channels] (torch CUDA tensor) -> the op's channel-first [batch, heads, channels, seq]."""
