@@ -171,10 +171,15 @@ __global__ void bwd_prep_f16_cl(const __half* __restrict__ o, const __half* __re
   }
   const int g = threadIdx.x % G;
   const int64_t rows = outer * nq * heads;
-  for (int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) / G; row < rows;
-       row += int64_t(gridDim.x) * blockDim.x / G) {
+  // every lane of a warp runs the same number of iterations (the shuffles below name the whole warp): rows past the end
+  // are predicated off, not skipped
+  const int64_t first = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) / G, step = int64_t(gridDim.x) * blockDim.x / G;
+  const int64_t warp_first = (blockIdx.x * int64_t(blockDim.x) + (threadIdx.x & ~31)) / G;
+  for (int64_t it = 0; warp_first + it * step < rows; ++it) {
+    const int64_t row = first + it * step;
+    const bool live = row < rows;
     float acc = 0.f;
-    if (g * 8 < v_d) {
+    if (live && g * 8 < v_d) {
       const uint4 x = *reinterpret_cast<const uint4*>(o + row * v_d + g * 8);
       const uint4 y = *reinterpret_cast<const uint4*>(d_o + row * v_d + g * 8);
       const __half2* xh = reinterpret_cast<const __half2*>(&x);
@@ -188,7 +193,7 @@ __global__ void bwd_prep_f16_cl(const __half* __restrict__ o, const __half* __re
     }
 #pragma unroll
     for (int w = G / 2; w > 0; w >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, w, G);
-    if (g == 0) {
+    if (live && g == 0) {
       const int64_t h = row % heads, oq = row / heads, q = oq % nq, ob = oq / nq;
       const int64_t b = ob * heads + h;
       dsum[b * sp + q] = acc;
