@@ -579,7 +579,7 @@ def main():
             del A64, B64
             peak_note = f"; fp64: cuBLAS DGEMM 4096^3 measured in this run ({peak:.1f} TFLOP/s; nominal 40)"
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures summarised in profiles/r1_fwd_ncu_c.md and profiles/r1_bwd_fused_ncu.md (bwd: the fused kernel)" if traffic else None, "peak_source": peaks["source"] + peak_note,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full captures of round 2 summarised in profiles/r2_c2_ncu.md (forward 2.155 GB = the algorithmic bytes; fused backward 5.35 GB against 3.2 GB algorithmic: the fp32 dQ scratch spilling out of L2)" if traffic else None, "peak_source": peaks["source"] + peak_note,
                     "frac_of_burst": ach / (peaks["tensor_burst"] or peak), "frac_of_nominal_2250": ach / 2250.0,
                     "algorithmic": what}
         # HBM side of the roofline: algorithmic bytes of the same kernel(s) over their duration.
